@@ -1,0 +1,3 @@
+"""`import snuffy_multiclass` shim: the reference module name bound to the B200-native implementation."""
+from snuffy_b200.snuffy_multiclass import *  # noqa: F401,F403
+from snuffy_b200.snuffy_multiclass import device  # noqa: F401

@@ -1,0 +1,77 @@
+"""ctypes binding of ``libsnuffy_b200.so`` — the C-ABI boundary of the hot path.
+
+Every entry point is declared in ``include/snuffy_b200.h``; this module mirrors that header one to one.
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("SNUFFY_B200_LIB", os.path.join(_HERE, "libsnuffy_b200.so"))
+
+# activation ids shared with csrc/common.cuh (snuffy.py:216-221 names)
+ACT_IDS = {"none": 0, "relu": 1, "gelu": 2, "leakyrelu": 3, "selu": 4, "tanh": 5}
+
+P = c_void_p
+I = c_int64
+# name -> (restype, argtypes).  Order follows include/snuffy_b200.h.
+_SIGNATURES = {
+    "snuffy_version": (c_int, []),
+    "snuffy_last_error": (c_char_p, []),
+    "snuffy_sm_count": (c_int, []),
+    "snuffy_launch_count": (ctypes.c_longlong, []),
+    "snuffy_scores_fwd": (c_int, [P, P, P, P, I, I, I, P]),
+    "snuffy_select_topk": (c_int, [P, I, I, I, I, P, P, P]),
+    "snuffy_select_random": (c_int, [P, I, I, I, c_uint64, c_uint64, P, P]),
+    "snuffy_compact_flags": (c_int, [P, I, I, I, P, P, P]),
+    "snuffy_gather_rows": (c_int, [P, P, I, I, I, I, P, P]),
+    "snuffy_build_row_map": (c_int, [P, I, I, I, P, P]),
+    "snuffy_ln_rows_fwd": (c_int, [P, P, P, P, P, I, I, c_int, P, P, I, c_int, P, P]),
+    "snuffy_ln_mean_head_chunks": (c_int64, [I, I]),
+    "snuffy_ln_mean_head_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P, P, P, P, P, P]),
+    "snuffy_gemm_f32": (c_int, [P, I, c_int, P, I, c_int, P, I, I, I, I, c_float, P, c_int, P, I, P, P, P, c_float, c_uint64,
+                               c_uint64, P]),
+    "snuffy_gemm_tc_block_n": (c_int, [I]),
+    "snuffy_plane_elems": (c_int64, [I, I, c_int]),
+    "snuffy_gemm_tc": (c_int, [P, I, P, I, I, I, I, c_int, P, c_int, P, I, P, P, P, I, P, P, I, c_float, c_uint64, c_uint64,
+                              P]),
+    "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),
+    "snuffy_sparse_attn_fwd": (c_int, [P, I, P, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
+    "snuffy_dsmil_workspace": (c_int64, [I, I, I]),
+    "snuffy_dsmil_pool_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P, P, P, P, P, I, P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class SnuffyLibraryError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"snuffy_b200: native library not found at {LIB_PATH}. Build it with ./build.sh "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the hot path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    msg = lib.snuffy_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        raise SnuffyLibraryError(f"{what or 'libsnuffy_b200'} failed (status {status}): {last_error()}")

@@ -1,0 +1,57 @@
+// Library-wide pieces of the C ABI: error reporting, version, device queries.
+#include "common.cuh"
+#include <stdarg.h>
+#include <string.h>
+#include <atomic>
+
+namespace snuffy {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+
+int check_launch(const char* what, int launches) {
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+        return 3;
+    }
+    return 0;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace snuffy
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int snuffy_version(void) { return 100; }
+
+const char* snuffy_last_error(void) { return snuffy::g_error; }
+
+int snuffy_sm_count(void) { return snuffy::sm_count(); }
+
+// kernels launched by this library since load (bench.py reports the per-step delta as gpu_launches)
+long long snuffy_launch_count(void) { return snuffy::g_launches.load(); }
+
+}  // extern "C"
+#pragma GCC visibility pop

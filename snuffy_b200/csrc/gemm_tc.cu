@@ -1,0 +1,386 @@
+// tcgen05 split-bf16 GEMM for the dense projections of the aggregator (SURVEY.md §8a rows a8, a11:
+// Q/V projection snuffy.py:188, FFN snuffy.py:225).  These are the true contractions of the path.
+//
+//   C[m, n] = epilogue( sum_k A(m,k) * B(n,k) ),   A = A_hi + A_lo, B = B_hi + B_lo  (bf16 planes)
+//   A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi       (3 tensor-core passes, fp32 accumulate in TMEM)
+//
+// which reproduces the fp32 product to ~2^-16 relative -- plain bf16/tf32 inputs break the 1e-4 parity bar and
+// flip top-K indices.  Operands arrive as pre-tiled planes (common.cuh): every pipeline stage
+// is a contiguous chunk in HBM moved by one cp.async.bulk per plane, landing directly in the SWIZZLE_NONE
+// K-major core-matrix layout the UMMA shared-memory descriptor describes.  No tensor maps, no swizzle.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      bulk-copy producer (+ TMEM alloc/dealloc)          full/empty mbarrier ring
+//   warp 1      single-thread tcgen05.mma issuer                    accumulators double-buffered in TMEM
+//   warps 2..5  epilogue: tcgen05.ld -> bias/activation -> (a) split-bf16 planes for the next GEMM, written
+//               straight from the row-owner register layout (512 B coalesced per warp store), and/or
+//               (b) fp32 rows (+ residual read through row_map) transposed through shared memory.
+#include "common.cuh"
+
+namespace snuffy {
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_PLANE_BYTES = TC_BM * PLANE_KB * 2;          // 8 KB per plane per stage
+
+template <int BN> struct TcCfg {
+    static constexpr uint32_t B_PLANE_BYTES = BN * PLANE_KB * 2;
+    static constexpr uint32_t STAGE_BYTES = 2 * TC_A_PLANE_BYTES + 2 * B_PLANE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;             // epilogue transpose buffers
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 256;
+    static constexpr uint32_t TMEM_COLS = 2 * BN;                      // two accumulator stages
+};
+
+struct TcGemmParams {
+    const __nv_bfloat16* A; int64_t a_plane_stride;
+    const __nv_bfloat16* B; int64_t b_plane_stride;
+    int M, N, K;
+    int m_tiles, n_tiles, num_kb;
+    int npairs;                      // 3: hi.hi + hi.lo + lo.hi   1: hi.hi only
+    const float* bias; int act;
+    const float* resid; int64_t ldr; const int32_t* row_map; const float* resid_alt;
+    float* out; int64_t ldc;
+    float* preact;                   // optional fp32 [M, ldc] value before the activation
+    __nv_bfloat16* out_planes; int64_t out_plane_stride;   // optional: result as A-operand planes, K_next = N
+    float drop_p; uint64_t seed, offset;                   // dropout on the activated value (before the residual)
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 8000000000ll) {     // ~4 s: a protocol bug must fail loudly, never hang the box
+            printf("snuffy gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// SWIZZLE_NONE, K-major shared-memory matrix descriptor: core matrix = 8 rows x 16 B stored contiguously;
+// LBO = byte stride between the two k-halves of one K=16 MMA, SBO = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    return d;                                      // base offset 0, layout type SWIZZLE_NONE (0)
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const TcGemmParams p) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char* stage_base = tc_smem;
+    float* stg_base = reinterpret_cast<float*>(tc_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tc_smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base word
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES;
+    const uint32_t tfull0 = empty0 + 8 * Cfg::STAGES, tempty0 = tfull0 + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const bool use_lo = p.npairs > 1;
+    const uint32_t stage_tx = use_lo ? Cfg::STAGE_BYTES : (TC_A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer
+        int stage = 0; uint32_t phase = 0;
+        const int64_t a_chunk = (int64_t)TC_BM * PLANE_KB, b_chunk = (int64_t)BN * PLANE_KB;   // elements
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const __nv_bfloat16* a_src = p.A + (int64_t)mt * p.num_kb * a_chunk;
+            const __nv_bfloat16* b_src = p.B + (int64_t)nt * p.num_kb * b_chunk;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (lane == 0) {
+                    const uint32_t bar = full0 + 8 * stage;
+                    const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * TC_A_PLANE_BYTES;
+                    mbar_expect_tx(bar, stage_tx);
+                    bulk_g2s(sa, a_src + kb * a_chunk, TC_A_PLANE_BYTES, bar);
+                    bulk_g2s(sb, b_src + kb * b_chunk, Cfg::B_PLANE_BYTES, bar);
+                    if (use_lo) {
+                        bulk_g2s(sa + TC_A_PLANE_BYTES, a_src + p.a_plane_stride + kb * a_chunk, TC_A_PLANE_BYTES, bar);
+                        bulk_g2s(sb + Cfg::B_PLANE_BYTES, b_src + p.b_plane_stride + kb * b_chunk, Cfg::B_PLANE_BYTES, bar);
+                    }
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * TC_A_PLANE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < PLANE_KB / 16; ++ks) {
+                        const uint64_t a_hi = make_smem_desc(sa + ks * 2 * LBO_A, LBO_A, SBO);
+                        const uint64_t b_hi = make_smem_desc(sb + ks * 2 * LBO_B, LBO_B, SBO);
+                        if (use_lo) {
+                            const uint64_t a_lo = make_smem_desc(sa + TC_A_PLANE_BYTES + ks * 2 * LBO_A, LBO_A, SBO);
+                            const uint64_t b_lo = make_smem_desc(sb + Cfg::B_PLANE_BYTES + ks * 2 * LBO_B, LBO_B, SBO);
+                            // small cross terms first, the dominant hi.hi term last
+                            tc_mma_bf16(d_tmem, a_lo, b_hi, IDESC, (kb | ks) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
+                            tc_mma_bf16(d_tmem, a_hi, b_hi, IDESC, 1u);
+                        } else {
+                            tc_mma_bf16(d_tmem, a_hi, b_hi, IDESC, (kb | ks) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(empty0 + 8 * stage);                 // frees the smem slot when these MMAs retire
+                    if (kb == p.num_kb - 1) tc_commit(tfull0 + 8 * acc);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quadrant warp % 4)
+        const int quad = warp & 3;
+        float* stg = stg_base + (size_t)(warp - 2) * 32 * 33;
+        int acc = 0; uint32_t acc_phase = 0;
+        const int kpad_next = (int)plane_kblocks(p.N) * PLANE_KB;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const int64_t m_own = (int64_t)mt * TC_BM + quad * 32 + lane;     // row this thread owns in TMEM
+            const int n0 = nt * BN;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N && col0 >= kpad_next) break;
+                float v[32];
+                tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                }
+                if (p.preact) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                    __syncwarp();
+#pragma unroll
+                    for (int rr = 0; rr < 32; rr += 4) {
+                        const int row = rr + (lane >> 3), c4 = (lane & 7) * 4;
+                        const int64_t m = (int64_t)mt * TC_BM + quad * 32 + row;
+                        const int col = col0 + c4;
+                        if (m < p.M && col < p.N)
+                            *reinterpret_cast<float4*>(p.preact + m * p.ldc + col) =
+                                make_float4(stg[row * 33 + c4], stg[row * 33 + c4 + 1], stg[row * 33 + c4 + 2],
+                                            stg[row * 33 + c4 + 3]);
+                    }
+                    __syncwarp();
+                }
+                if (p.act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = act_apply(p.act, v[j]);
+                }
+                if (p.drop_p > 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        v[j] *= drop_keep_scale(p.seed, p.offset, (uint64_t)(m_own * p.N + col0 + j), p.drop_p);
+                }
+                if (p.out_planes) {
+                    // thread owns row m_own and 32 consecutive k of the next GEMM: 4 units of 8
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = col0 + u * 8;
+                        if (k < kpad_next) {
+                            bf16x8 h, l;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) split_bf16(v[u * 8 + j], h.v[j], l.v[j]);
+                            const int64_t off = plane_unit_offset(m_own, k, p.N, TC_BM);
+                            *reinterpret_cast<bf16x8*>(p.out_planes + off) = h;
+                            *reinterpret_cast<bf16x8*>(p.out_planes + p.out_plane_stride + off) = l;
+                        }
+                    }
+                }
+                if (p.out) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                    __syncwarp();
+#pragma unroll
+                    for (int rr = 0; rr < 32; rr += 4) {
+                        const int row = rr + (lane >> 3), c4 = (lane & 7) * 4;
+                        const int64_t m = (int64_t)mt * TC_BM + quad * 32 + row;
+                        const int col = col0 + c4;
+                        if (m < p.M && col < p.N) {
+                            float4 o = make_float4(stg[row * 33 + c4], stg[row * 33 + c4 + 1], stg[row * 33 + c4 + 2],
+                                                   stg[row * 33 + c4 + 3]);
+                            if (p.resid) {
+                                const float* rrow = p.resid + m * p.ldr;
+                                if (p.row_map) {
+                                    const int32_t slot = __ldg(p.row_map + m);
+                                    if (slot >= 0) rrow = p.resid_alt + (int64_t)slot * p.ldr;
+                                }
+                                const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + col));
+                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                            }
+                            *reinterpret_cast<float4*>(p.out + m * p.ldc + col) = o;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace snuffy
+
+using namespace snuffy;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+// Rows-per-chunk (= BLOCK_N of the kernel that will consume them) a [N, K] weight should be tiled with.
+int snuffy_gemm_tc_block_n(int64_t N) {
+    const int64_t n128 = (N + 127) / 128;
+    return (n128 % 2 == 0) ? 256 : 128;
+}
+
+// bf16 elements in ONE plane of a [rows, K] operand tiled with rc rows per chunk
+int64_t snuffy_plane_elems(int64_t rows, int64_t K, int rc) { return plane_elems(rows, K, rc); }
+
+// C = epilogue(A . B^T) with A, B given as split-bf16 planes (A tiled with 128 rows per chunk, B with
+// snuffy_gemm_tc_block_n(N)).  Outputs (each optional, at least one): fp32 `out` [M, ldc] (+ residual, optionally
+// redirected through row_map), fp32 `preact`, and `out_planes` = the activated result as A planes with K_next = N.
+int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                   int64_t M, int64_t N, int64_t K, int passes, const float* bias, int act, const float* resid,
+                   int64_t ldr, const int32_t* row_map, const float* resid_alt, float* out, int64_t ldc,
+                   float* preact, void* out_planes, int64_t out_plane_stride, float dropout_p, uint64_t seed,
+                   uint64_t offset, cudaStream_t stream) {
+    SNUFFY_REQUIRE(A_planes && B_planes, "snuffy_gemm_tc: null operand");
+    SNUFFY_REQUIRE(out || out_planes || preact, "snuffy_gemm_tc: no output requested");
+    SNUFFY_REQUIRE(M >= 1 && N >= 1 && K >= 1, "snuffy_gemm_tc: empty problem");
+    SNUFFY_REQUIRE(passes == 1 || passes == 3, "snuffy_gemm_tc: passes must be 1 or 3");
+    SNUFFY_REQUIRE(N % 4 == 0 && (!out || (ldc % 4 == 0 && (uintptr_t)out % 16 == 0)) &&
+                       (!preact || (ldc % 4 == 0 && (uintptr_t)preact % 16 == 0)) &&
+                       (!resid || (ldr % 4 == 0 && (uintptr_t)resid % 16 == 0)),
+                   "snuffy_gemm_tc: N, ldc, ldr must be multiples of 4 and fp32 pointers 16-byte aligned");
+    SNUFFY_REQUIRE(!row_map || (resid && resid_alt), "snuffy_gemm_tc: row_map needs resid and resid_alt");
+    SNUFFY_REQUIRE((uintptr_t)A_planes % 16 == 0 && (uintptr_t)B_planes % 16 == 0 && a_plane_stride % 8 == 0 &&
+                       b_plane_stride % 8 == 0, "snuffy_gemm_tc: planes must be 16-byte aligned");
+    TcGemmParams p{};
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A_planes); p.a_plane_stride = a_plane_stride;
+    p.B = reinterpret_cast<const __nv_bfloat16*>(B_planes); p.b_plane_stride = b_plane_stride;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    const int bn = snuffy_gemm_tc_block_n(N);
+    p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    p.n_tiles = (int)((N + bn - 1) / bn);
+    p.num_kb = (int)plane_kblocks(K);
+    p.npairs = passes;
+    p.bias = bias; p.act = act; p.resid = resid; p.ldr = ldr; p.row_map = row_map; p.resid_alt = resid_alt;
+    p.out = out; p.ldc = ldc; p.preact = preact;
+    p.out_planes = reinterpret_cast<__nv_bfloat16*>(out_planes); p.out_plane_stride = out_plane_stride;
+    p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = total < sm_count() ? total : sm_count();
+    if (bn == 256) {
+        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TcCfg<256>::SMEM_BYTES));
+        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p);
+    } else {
+        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TcCfg<128>::SMEM_BYTES));
+        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(p);
+    }
+    return check_launch("snuffy_gemm_tc");
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,298 @@
+// LayerNorm kernels of the aggregator (eps 1e-5, affine; snuffy.py:80,97,107,110,86):
+//   ln_rows       : u = LN(y) for every row, where y is "x with the selected rows replaced"
+//                   (read through row_map, never materialised; snuffy.py:152-155), written as fp32
+//                   and/or as the split-bf16 operand planes the tcgen05 GEMM consumes (common.cuh).
+//   ln_mean_head  : final LN -> mean over ALL N tokens -> linear head (snuffy.py:86,71), one pass
+//                   over x, deterministic two-level reduction, no atomics on data.
+#include "common.cuh"
+
+namespace snuffy {
+
+constexpr float LN_EPS = 1e-5f;
+
+// One warp per row, 8 rows (= one 8-row core-matrix group of the plane layout) per CTA.
+// Each lane keeps 8 consecutive elements per iteration: e = (it*32 + lane)*8.
+template <int MAXIT>
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map, const float* __restrict__ alt,
+               const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int d,
+               float* __restrict__ out_f32, __nv_bfloat16* __restrict__ planes, int64_t plane_stride,
+               float* __restrict__ stats, int apply_ln, int rc) {
+    extern __shared__ __align__(16) unsigned char ln_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * 8;
+    const int64_t row = row0 + warp;
+    const int nunits = (int)plane_kblocks(d) * 4;          // 16-byte units per row incl. K padding
+    bf16x8* s_hi = reinterpret_cast<bf16x8*>(ln_smem);      // [nunits][8 rows]
+    bf16x8* s_lo = s_hi + (size_t)nunits * 8;
+
+    float v[MAXIT][8];
+    const bool live = row < rows;
+    const float* src = nullptr;
+    if (live) {
+        src = x + row * (int64_t)d;
+        if (row_map) {
+            const int32_t slot = row_map[row];
+            if (slot >= 0) src = alt + (int64_t)slot * d;
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        const int e = (it * 32 + lane) * 8;
+        if (live && e < d) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + e + 4));
+            v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w;
+            v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += v[it][j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[it][j] = 0.f;
+        }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (apply_ln) {
+        mean = warp_sum(sum) / (float)d;
+        float sq = 0.f;
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int e = (it * 32 + lane) * 8;
+            if (e < d) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float t = v[it][j] - mean; sq = fmaf(t, t, sq); }
+            }
+        }
+        rstd = rsqrtf(warp_sum(sq) / (float)d + LN_EPS);
+        if (stats && live && lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        const int e = (it * 32 + lane) * 8;
+        const int unit = it * 32 + lane;
+        if (unit < nunits) {
+            float u[8];
+            if (live && e < d) {
+                if (apply_ln) {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e + 4));
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + e));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + e + 4));
+                    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u[j] = (v[it][j] - mean) * rstd * g[j] + bb[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u[j] = v[it][j];
+                }
+                if (out_f32) {
+                    float* o = out_f32 + row * (int64_t)d + e;
+                    *reinterpret_cast<float4*>(o) = make_float4(u[0], u[1], u[2], u[3]);
+                    *reinterpret_cast<float4*>(o + 4) = make_float4(u[4], u[5], u[6], u[7]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = 0.f;
+            }
+            if (planes) {
+                bf16x8 h, l;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) split_bf16(u[j], h.v[j], l.v[j]);
+                s_hi[unit * 8 + warp] = h;
+                s_lo[unit * 8 + warp] = l;
+            }
+        }
+    }
+    if (planes) {
+        __syncthreads();
+        // each unit's 8 rows are 128 contiguous bytes in the plane: coalesced copy-out
+        for (int s = threadIdx.x; s < nunits * 8; s += blockDim.x) {
+            const int unit = s >> 3, rr = s & 7;
+            const int64_t off = plane_unit_offset(row0, (int64_t)unit * 8, d, rc) + rr * 8;
+            *reinterpret_cast<bf16x8*>(planes + off) = s_hi[s];
+            *reinterpret_cast<bf16x8*>(planes + plane_stride + off) = s_lo[s];
+        }
+    }
+}
+
+// generic-d fallback (d % 8 != 0): fp32 output only
+__global__ void __launch_bounds__(256)
+ln_rows_scalar_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map, const float* __restrict__ alt,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int d,
+                      float* __restrict__ out_f32, float* __restrict__ stats, int apply_ln) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* src = x + row * (int64_t)d;
+    if (row_map) { const int32_t slot = row_map[row]; if (slot >= 0) src = alt + (int64_t)slot * d; }
+    float mean = 0.f, rstd = 1.f;
+    if (apply_ln) {
+        float sum = 0.f;
+        for (int e = lane; e < d; e += 32) sum += src[e];
+        mean = warp_sum(sum) / (float)d;
+        float sq = 0.f;
+        for (int e = lane; e < d; e += 32) { const float t = src[e] - mean; sq = fmaf(t, t, sq); }
+        rstd = rsqrtf(warp_sum(sq) / (float)d + LN_EPS);
+        if (stats && lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+    }
+    for (int e = lane; e < d; e += 32)
+        out_f32[row * (int64_t)d + e] = apply_ln ? (src[e] - mean) * rstd * gamma[e] + beta[e] : src[e];
+}
+
+// ------------------------------------------------------------------ final LN + mean + head
+// grid (chunks, B).  Each CTA normalises its rows (warp per row), sums the normalised rows,
+// writes one partial [d] and takes a ticket; the last CTA of the bag folds the partials in a
+// fixed order, applies the affine (mean(z*g+b) = g*mean(z)+b), divides by N and runs the C x d head.
+__global__ void __launch_bounds__(256)
+ln_mean_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ Wh, const float* __restrict__ bh, int64_t N, int d, int C,
+                    float* __restrict__ partials, unsigned int* __restrict__ tickets, float* __restrict__ stats,
+                    float* __restrict__ pooled, float* __restrict__ bag_out) {
+    extern __shared__ __align__(16) float hs[];            // [8 warps][d] then reused
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = gridDim.x, chunk = blockIdx.x, bag = blockIdx.y;
+    const int64_t per = (N + chunks - 1) / chunks;
+    const int64_t r0 = chunk * per, r1 = min(N, r0 + per);
+    const float* xb = x + (int64_t)bag * N * d;
+    float* wacc = hs + (size_t)warp * d;
+    for (int e = lane; e < d; e += 32) wacc[e] = 0.f;
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+        const float* src = xb + r * d;
+        float sum = 0.f;
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = ld_stream(reinterpret_cast<const float4*>(src + e));
+            sum += (a.x + a.y) + (a.z + a.w);
+        }
+        const float mean = warp_sum(sum) / (float)d;
+        float sq = 0.f;
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));   // L1/L2 hit
+            const float t0 = a.x - mean, t1 = a.y - mean, t2 = a.z - mean, t3 = a.w - mean;
+            sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)d + LN_EPS);
+        if (stats && lane == 0) { stats[((int64_t)bag * N + r) * 2] = mean; stats[((int64_t)bag * N + r) * 2 + 1] = rstd; }
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));
+            float4 w = *reinterpret_cast<float4*>(wacc + e);
+            w.x += (a.x - mean) * rstd; w.y += (a.y - mean) * rstd;
+            w.z += (a.z - mean) * rstd; w.w += (a.w - mean) * rstd;
+            *reinterpret_cast<float4*>(wacc + e) = w;
+        }
+    }
+    __syncthreads();
+    float* part = partials + ((int64_t)bag * chunks + chunk) * d;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += hs[(size_t)w * d + e];
+        part[e] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&tickets[bag], 1u);
+        s_last = (t == (unsigned)chunks - 1u);
+        if (s_last) tickets[bag] = 0;                      // leave the workspace reusable
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float inv_n = 1.f / (float)N;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) {
+        float s = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) s += __ldcg(partials + ((int64_t)bag * chunks + ch) * d + e);
+        const float p = gamma[e] * (s * inv_n) + beta[e];
+        hs[e] = p;
+        if (pooled) pooled[(int64_t)bag * d + e] = p;
+    }
+    __syncthreads();
+    for (int j = warp; j < C; j += 8) {
+        float acc = 0.f;
+        for (int e = lane; e < d; e += 32) acc = fmaf(hs[e], Wh[(int64_t)j * d + e], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) bag_out[(int64_t)bag * C + j] = acc + (bh ? bh[j] : 0.f);
+    }
+}
+
+}  // namespace snuffy
+
+using namespace snuffy;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+// LN over rows of y = (row_map ? x with mapped rows taken from alt : x); apply_ln = 0 turns it into a
+// plain gather/convert (used to split raw activations).  Outputs (each optional): fp32 [rows, d];
+// split-bf16 planes (hi at `planes`, lo at `planes + plane_stride`, tiled with `plane_rc` rows per chunk:
+// 128 for an A operand, snuffy_gemm_tc_block_n(rows) for a weight); stats [rows, 2] = (mean, rstd).
+int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt, const float* gamma,
+                       const float* beta, int64_t rows, int64_t d, int apply_ln, float* out_f32, void* planes,
+                       int64_t plane_stride, int plane_rc, float* stats, cudaStream_t stream) {
+    SNUFFY_REQUIRE(x && rows >= 0 && d > 0, "snuffy_ln_rows_fwd: bad arguments");
+    SNUFFY_REQUIRE(!apply_ln || (gamma && beta), "snuffy_ln_rows_fwd: LayerNorm needs gamma and beta");
+    SNUFFY_REQUIRE(!row_map || alt, "snuffy_ln_rows_fwd: row_map given without the replacement rows");
+    SNUFFY_REQUIRE(!planes || plane_rc == 128 || plane_rc == 256, "snuffy_ln_rows_fwd: plane_rc must be 128 or 256");
+    if (rows == 0) return 0;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    const bool vec = d % 8 == 0 && ((uintptr_t)x % 16 == 0) && (!alt || (uintptr_t)alt % 16 == 0) &&
+                     (!out_f32 || (uintptr_t)out_f32 % 16 == 0);
+    if (!vec) {
+        SNUFFY_REQUIRE(!planes && out_f32, "snuffy_ln_rows_fwd: d=%lld not a multiple of 8 supports fp32 output only",
+                       (long long)d);
+        ln_rows_scalar_kernel<<<grid, 256, 0, stream>>>(x, row_map, alt, gamma, beta, rows, (int)d, out_f32, stats,
+                                                        apply_ln);
+        return check_launch("snuffy_ln_rows_fwd");
+    }
+    SNUFFY_REQUIRE(d <= 4096, "snuffy_ln_rows_fwd: d=%lld > 4096 unsupported", (long long)d);
+    const size_t smem = planes ? (size_t)plane_kblocks(d) * 4 * 8 * 16 * 2 : 0;
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(planes);
+#define LN_LAUNCH(MAXIT)                                                                                        \
+    do {                                                                                                        \
+        if (smem > 48 * 1024)                                                                                   \
+            SNUFFY_CUDA(cudaFuncSetAttribute(ln_rows_kernel<MAXIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                      \
+        ln_rows_kernel<MAXIT><<<grid, 256, smem, stream>>>(x, row_map, alt, gamma, beta, rows, (int)d, out_f32,  \
+                                                           pl, plane_stride, stats, apply_ln, plane_rc);        \
+    } while (0)
+    const int iters = (int)((plane_kblocks(d) * 4 + 31) / 32);
+    if (iters <= 2) LN_LAUNCH(2);
+    else if (iters <= 4) LN_LAUNCH(4);
+    else if (iters <= 8) LN_LAUNCH(8);
+    else LN_LAUNCH(16);
+#undef LN_LAUNCH
+    return check_launch("snuffy_ln_rows_fwd");
+}
+
+// workspace floats needed by snuffy_ln_mean_head_fwd (partials) -- tickets are B uint32 (zeroed once by the caller)
+int64_t snuffy_ln_mean_head_chunks(int64_t B, int64_t N) {
+    int64_t chunks = (2 * (int64_t)sm_count() + B - 1) / (B > 0 ? B : 1);
+    const int64_t max_chunks = (N + 7) / 8;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    return chunks;
+}
+
+// bag[B, C] = head( mean_n LN_f(x[b, n, :]) )        snuffy.py:86 + 71
+int snuffy_ln_mean_head_fwd(const float* x, const float* gamma, const float* beta, const float* Wh, const float* bh,
+                            int64_t B, int64_t N, int64_t d, int64_t C, float* partials, uint32_t* tickets,
+                            float* stats, float* pooled, float* bag_out, cudaStream_t stream) {
+    SNUFFY_REQUIRE(x && gamma && beta && Wh && partials && tickets && bag_out, "snuffy_ln_mean_head_fwd: null pointer");
+    SNUFFY_REQUIRE(B >= 1 && N >= 1 && C >= 1 && d % 4 == 0 && (uintptr_t)x % 16 == 0,
+                   "snuffy_ln_mean_head_fwd: needs d %% 4 == 0 and 16-byte aligned rows (d=%lld)", (long long)d);
+    const int64_t chunks = snuffy_ln_mean_head_chunks(B, N);
+    const size_t smem = (size_t)8 * d * sizeof(float);
+    SNUFFY_REQUIRE(smem <= 200 * 1024, "snuffy_ln_mean_head_fwd: d=%lld too large", (long long)d);
+    if (smem > 48 * 1024)
+        SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)chunks, (unsigned)B);
+    ln_mean_head_kernel<<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
+                                                     stats, pooled, bag_out);
+    return check_launch("snuffy_ln_mean_head_fwd");
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

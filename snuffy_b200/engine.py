@@ -1,0 +1,239 @@
+"""Host-side orchestration of the aggregator hot path: which kernel runs when, on what buffers.
+
+The math contract is SURVEY.md Appendix A (reference: snuffy.py:126-157, 160-205, 224-225, 68-86;
+snuffy_multiclass.py:130-171).  Nothing here computes on tensors with PyTorch ops — every step is a call
+into ``libsnuffy_b200.so`` through :mod:`snuffy_b200.ops`; PyTorch only owns the buffers and the stream.
+
+Data layout in HBM (all fp32 unless noted):
+  x        [B*N, d]      layer input, never modified (the reference clones before its scatter)
+  sel      [B, Ksel] i64 selected rows S = T ++ R;   row_map [B*N] i32  (-1 | slot)
+  xs       [B*Ksel, d]   raw selected rows (the attention KEYS);  xs_new = xs + attention output
+  planes   split-bf16 operand planes (hi, lo), pre-tiled for tcgen05 (csrc/common.cuh)
+  qv       [B*N, 2d]     Q | V projections of LN1(x)
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import Planes
+
+PRECISIONS = ("bf16x3", "fp32", "bf16x1")
+
+
+def default_precision() -> str:
+    p = os.environ.get("SNUFFY_B200_PRECISION", "bf16x3")
+    if p not in PRECISIONS:
+        raise ValueError(f"SNUFFY_B200_PRECISION must be one of {PRECISIONS}, got {p!r}")
+    return p
+
+
+# ------------------------------------------------------------------ random-patch stream
+class _RandomStream:
+    """(seed, offset) pairs for the device sampler: seed follows torch.manual_seed, offset counts draws."""
+
+    def __init__(self):
+        self._seed = None
+        self._offset = 0
+
+    def next(self) -> Tuple[int, int]:
+        seed = torch.initial_seed()
+        if seed != self._seed:
+            self._seed, self._offset = seed, 0
+        self._offset += 1
+        return seed, self._offset
+
+
+_RANDOM = _RandomStream()
+
+
+def k_top_of(big_lambda: int, random_patch_share: float) -> int:
+    # Python doubles, exactly as the reference writes it (snuffy.py:124,129)
+    return math.ceil(big_lambda * (1.0 - random_patch_share))
+
+
+def k_rand_of(big_lambda: int, random_patch_share: float, n: int) -> int:
+    # snuffy.py:137-140
+    return min(int(big_lambda * random_patch_share), max(0, n - k_top_of(big_lambda, random_patch_share)))
+
+
+# ------------------------------------------------------------------ selection
+def select_binary(c: torch.Tensor, big_lambda: int, random_patch_share: float, random_mode: str = "device",
+                  top: Optional[torch.Tensor] = None, flags: Optional[torch.Tensor] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Binary-path selection (snuffy.py:128-147) for c [B, N, 1].  Returns (S [B, Ksel], T [B, Ktop], flags).
+
+    T and the taken-flags depend only on c, so callers pass them back in for layers > 0; the random part is
+    re-drawn on every call like the reference.  random_mode: "device" (Philox on the GPU, no sync) or "numpy"
+    (the reference's NumPy global-RNG stream: bit-identical indices, costs a D2H + H2D round trip)."""
+    B, N, C = c.shape
+    kt = min(k_top_of(big_lambda, random_patch_share), N)
+    kr = k_rand_of(big_lambda, random_patch_share, N)
+    if top is None:
+        flags = torch.zeros(B, N, dtype=torch.uint8, device=c.device) if kr > 0 else None
+        top = ops.select_topk(c, kt, flags).view(B, kt)
+    if kr == 0:
+        return top, top, flags
+    if random_mode == "numpy":
+        rnd = []
+        for b in range(B):                                   # host round trip, reference stream
+            taken = top[b].tolist()
+            remaining = list(set(range(N)) - set(taken))
+            rnd.append(torch.from_numpy(np.random.choice(remaining, kr, replace=False)))
+        rand = torch.stack(rnd).to(device=c.device, dtype=torch.int64)
+    elif random_mode == "device":
+        seed, offset = _RANDOM.next()
+        rand = ops.select_random(flags, kr, seed, offset)
+    else:
+        raise ValueError(f"random_mode must be 'device' or 'numpy', got {random_mode!r}")
+    return torch.cat((top, rand), dim=1), top, flags
+
+
+def select_multiclass(c: torch.Tensor, big_lambda: int, random_patch_share: float, random_mode: str = "device",
+                      cache: Optional[dict] = None) -> torch.Tensor:
+    """Multiclass selection (snuffy_multiclass.py:130-160) for c [B, N, C] -> S [B, 2*ref] int64."""
+    B, N, C = c.shape
+    kt = min(k_top_of(big_lambda, random_patch_share), N)
+    if cache is not None and "uniq" in cache:
+        uniq, ref, flags = cache["uniq"], cache["ref"], cache["flags"]
+    else:
+        flags = torch.zeros(B, N, dtype=torch.uint8, device=c.device)
+        ops.select_topk(c, kt, flags)
+        uniq, counts = ops.compact_flags(flags, C * kt)
+        if C == 1:
+            ref = kt                                         # one class: no duplicates, no sync needed
+        else:
+            ref = int(counts.min().item())                   # shapes depend on it: one sync per forward
+        ref = min(ref, N - ref)
+        if cache is not None:
+            cache.update(uniq=uniq, ref=ref, flags=flags)
+    if ref <= 0:
+        raise ValueError(f"snuffy_multiclass: empty selection (N={N}, top share={kt})")
+    top = uniq[:, :ref]
+    if random_mode == "numpy":
+        counts_h = None
+        rnd = []
+        fl = flags.cpu().numpy()
+        for b in range(B):
+            remaining = np.nonzero(fl[b] == 0)[0]
+            rnd.append(torch.from_numpy(np.random.choice(remaining, ref, replace=False)))
+        rand = torch.stack(rnd).to(device=c.device, dtype=torch.int64)
+    elif random_mode == "device":
+        seed, offset = _RANDOM.next()
+        rand = ops.select_random(flags, ref, seed, offset)
+    else:
+        raise ValueError(f"random_mode must be 'device' or 'numpy', got {random_mode!r}")
+    return torch.cat((top, rand), dim=1).contiguous()
+
+
+# ------------------------------------------------------------------ per-layer weights
+@dataclass
+class LayerWeights:
+    """Views of one EncoderLayer's parameters plus derived operands (fused Q|V weight, tcgen05 planes)."""
+    wq: torch.Tensor; bq: torch.Tensor
+    wk: torch.Tensor; bk: torch.Tensor
+    wv: torch.Tensor; bv: torch.Tensor
+    wo: torch.Tensor; bo: torch.Tensor
+    w1: torch.Tensor; b1: torch.Tensor
+    w2: torch.Tensor; b2: torch.Tensor
+    g1: torch.Tensor; be1: torch.Tensor
+    g2: torch.Tensor; be2: torch.Tensor
+    wqv: Optional[torch.Tensor] = None
+    bqv: Optional[torch.Tensor] = None
+    wqv_planes: Optional[Planes] = None
+    w1_planes: Optional[Planes] = None
+    w2_planes: Optional[Planes] = None
+
+    def prepare(self, precision: str) -> None:
+        if self.wqv is None:
+            # one [2d, d] operand so LN1(x) is read once for both projections
+            self.wqv = torch.cat((self.wq.detach(), self.wv.detach()), dim=0).contiguous()
+            self.bqv = torch.cat((self.bq.detach(), self.bv.detach()), dim=0).contiguous()
+        if precision != "fp32" and self.wqv_planes is None:
+            self.wqv_planes = ops.weight_planes(self.wqv)
+            self.w1_planes = ops.weight_planes(self.w1.detach())
+            self.w2_planes = ops.weight_planes(self.w2.detach())
+
+
+@dataclass
+class LayerTape:
+    """What one layer's forward leaves behind for the backward pass."""
+    sel: torch.Tensor
+    row_map: torch.Tensor
+    xs: torch.Tensor
+    xs_new: torch.Tensor
+    kp: torch.Tensor
+    qv: torch.Tensor
+    o: torch.Tensor
+    ln1_stats: torch.Tensor
+    ln2_stats: torch.Tensor
+    attn_stats: torch.Tensor
+    h_pre: torch.Tensor
+    x_in: torch.Tensor
+    drop: Tuple[float, int, int]
+
+
+def tc_supported(d: int) -> bool:
+    return d % 8 == 0
+
+
+def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w: LayerWeights, heads: int,
+                          activation: str, precision: str, want_probs: bool, save: bool = False,
+                          attn_dropout: float = 0.0) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[LayerTape]]:
+    """One EncoderLayer (snuffy.py:126-157) on x [B*N, d] with the selection sel [B, Ksel].
+
+    Eval-mode semantics except for the attention dropout (train mode, snuffy.py:166-167).  Returns
+    (x_next [B*N, d], P [B, h, N, Ksel] or None, tape or None)."""
+    d = x.shape[1]
+    rows = B * N
+    Ksel = sel.shape[1]
+    if precision != "fp32" and not tc_supported(d):
+        precision = "fp32"                                   # tcgen05 planes need d % 8 == 0; still the CUDA path
+    w.prepare(precision)
+    passes = 1 if precision == "bf16x1" else 3
+
+    xs = ops.gather_rows(x.view(B, N, d), sel).view(B * Ksel, d)            # raw keys (App. B-1)
+    row_map = ops.build_row_map(sel, N)
+
+    # --- attention sub-layer: u = LN1(x); Q,V over all N rows; keys from the raw selected rows
+    if precision == "fp32":
+        u, _, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_f32=True, want_stats=save)
+        qv = ops.gemm_f32(u, w.wqv, M=rows, N=2 * d, K=d, bias=w.bqv)
+    else:
+        _, up, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_planes=True, want_stats=save)
+        qv, _, _ = ops.gemm_tc(up, w.wqv_planes, M=rows, N=2 * d, K=d, passes=passes, bias=w.bqv)
+    kp = ops.linear_f32(xs, w.wk, w.bk)
+    drop = (0.0, 0, 0)
+    if attn_dropout > 0.0:
+        seed, offset = _RANDOM.next()
+        drop = (attn_dropout, seed, offset)
+    o, probs, attn_stats = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, N, Ksel, heads, want_probs=want_probs,
+                                           want_stats=save, dropout_p=drop[0], seed=drop[1], offset=drop[2])
+    xs_new = ops.linear_f32(o, w.wo, w.bo, resid=xs)                         # X_S' = X_S + W3 O + b3
+
+    # --- feed-forward sub-layer over y = x with rows S replaced by X_S' (read through row_map)
+    h_pre = None
+    if precision == "fp32":
+        u2, _, ln2_stats = ops.ln_rows(x, w.g2, w.be2, row_map=row_map, alt=xs_new, want_f32=True, want_stats=save)
+        res = ops.gemm_f32(u2, w.w1, M=rows, N=w.w1.shape[0], K=d, bias=w.b1, act=activation, want_preact=save)
+        hdn, h_pre = res if save else (res, None)
+        x_next = ops.gemm_f32(hdn, w.w2, M=rows, N=d, K=w.w1.shape[0], bias=w.b2, resid=x, row_map=row_map,
+                              resid_alt=xs_new)
+    else:
+        _, yp, ln2_stats = ops.ln_rows(x, w.g2, w.be2, row_map=row_map, alt=xs_new, want_planes=True, want_stats=save)
+        dff = w.w1.shape[0]
+        _, h_pre, hp = ops.gemm_tc(yp, w.w1_planes, M=rows, N=dff, K=d, passes=passes, bias=w.b1, act=activation,
+                                   want_out=False, want_preact=save, want_planes=True)
+        x_next, _, _ = ops.gemm_tc(hp, w.w2_planes, M=rows, N=d, K=dff, passes=passes, bias=w.b2, resid=x,
+                                   row_map=row_map, resid_alt=xs_new)
+    tape = None
+    if save:
+        tape = LayerTape(sel=sel, row_map=row_map, xs=xs, xs_new=xs_new, kp=kp, qv=qv, o=o, ln1_stats=ln1_stats,
+                         ln2_stats=ln2_stats, attn_stats=attn_stats, h_pre=h_pre, x_in=x, drop=drop)
+    return x_next, probs, tape

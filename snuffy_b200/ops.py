@@ -1,0 +1,256 @@
+"""Tensor-level wrappers over the C ABI (one Python function per ``extern "C"`` entry point).
+
+PyTorch is used for device memory and the current CUDA stream only; every computation happens inside
+``libsnuffy_b200.so``.  All wrappers are asynchronous on ``torch.cuda.current_stream()`` and never
+synchronise, so a whole forward can be captured into a CUDA graph.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDS, check, lib
+
+
+_U64 = 2**64 - 1
+
+
+# ------------------------------------------------------------------ helpers
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"snuffy_b200: `{name}` must live on a CUDA device (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"snuffy_b200: `{name}` must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Planes:
+    """Split-bf16 operand planes of an fp32 [rows, K] matrix (layout: csrc/common.cuh)."""
+
+    __slots__ = ("buf", "rows", "K", "rc", "stride")
+
+    def __init__(self, rows: int, K: int, rc: int, device, zero: bool = False):
+        self.rows, self.K, self.rc = rows, K, rc
+        self.stride = lib.snuffy_plane_elems(rows, K, rc)
+        alloc = torch.zeros if zero else torch.empty
+        self.buf = alloc(2 * self.stride, dtype=torch.bfloat16, device=device)
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+
+# ------------------------------------------------------------------ a1: instance scores
+def scores(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """c = x W^T + b over the last dim (snuffy.py:39-41).  x [..., d] -> c [..., C]."""
+    x = _f32(x, "x")
+    weight = _f32(weight, "weight")
+    d = x.shape[-1]
+    C = weight.shape[0]
+    rows = x.numel() // d if d else 0
+    c = torch.empty(*x.shape[:-1], C, dtype=torch.float32, device=x.device)
+    check(lib.snuffy_scores_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), c.data_ptr(), rows, d, C, _stream()),
+          "snuffy_scores_fwd")
+    return c
+
+
+# ------------------------------------------------------------------ a6 / a12: selection
+def select_topk(c: torch.Tensor, k: int, flags: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """c [B, N, C] -> idx [B, C, k] int64: per (bag, class) the k best rows in descending score order
+    (ties: lower index first).  `flags` [B, N] uint8 (zeroed by the caller) receives 1 at every winner."""
+    c = _f32(c, "c")
+    B, N, C = c.shape
+    idx = torch.empty(B, C, k, dtype=torch.int64, device=c.device)
+    check(lib.snuffy_select_topk(c.data_ptr(), B, N, C, k, idx.data_ptr(), _ptr(flags), _stream()), "snuffy_select_topk")
+    return idx
+
+
+def select_random(flags: torch.Tensor, k: int, seed: int, offset: int) -> torch.Tensor:
+    """flags [B, N] uint8 -> idx [B, k] int64, k distinct un-flagged rows, uniform without replacement."""
+    B, N = flags.shape
+    idx = torch.empty(B, k, dtype=torch.int64, device=flags.device)
+    check(lib.snuffy_select_random(flags.data_ptr(), B, N, k, seed & _U64, offset & _U64, idx.data_ptr(),
+                                   _stream()), "snuffy_select_random")
+    return idx
+
+
+def compact_flags(flags: torch.Tensor, cap: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Ascending indices of flagged rows per bag (torch.unique order): (idx [B, cap], counts [B] int32)."""
+    B, N = flags.shape
+    out = torch.zeros(B, cap, dtype=torch.int64, device=flags.device)
+    counts = torch.empty(B, dtype=torch.int32, device=flags.device)
+    check(lib.snuffy_compact_flags(flags.data_ptr(), B, N, cap, out.data_ptr(), counts.data_ptr(), _stream()),
+          "snuffy_compact_flags")
+    return out, counts
+
+
+def gather_rows(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """x [B, N, d], idx [B, K] -> [B, K, d] (raw rows, snuffy.py:131,145-147)."""
+    x = _f32(x, "x")
+    B, N, d = x.shape
+    K = idx.shape[1]
+    out = torch.empty(B, K, d, dtype=torch.float32, device=x.device)
+    check(lib.snuffy_gather_rows(x.data_ptr(), idx.data_ptr(), B, N, K, d, out.data_ptr(), _stream()), "snuffy_gather_rows")
+    return out
+
+
+def build_row_map(idx: torch.Tensor, N: int) -> torch.Tensor:
+    """idx [B, K] -> row_map [B*N] int32: -1 or the slot b*K+k of a selected row."""
+    B, K = idx.shape
+    row_map = torch.empty(B * N, dtype=torch.int32, device=idx.device)
+    check(lib.snuffy_build_row_map(idx.data_ptr(), B, N, K, row_map.data_ptr(), _stream()), "snuffy_build_row_map")
+    return row_map
+
+
+# ------------------------------------------------------------------ LayerNorm
+def ln_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
+            row_map: Optional[torch.Tensor] = None, alt: Optional[torch.Tensor] = None, apply_ln: bool = True,
+            want_f32: bool = False, want_planes: bool = False, plane_rc: int = 128, want_stats: bool = False,
+            zero_planes: bool = False):
+    """LN over the rows of y = x-with-mapped-rows-replaced.  Returns (fp32 or None, Planes or None, stats or None)."""
+    x = _f32(x, "x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    out = torch.empty(rows, d, dtype=torch.float32, device=x.device) if want_f32 else None
+    planes = Planes(rows, d, plane_rc, x.device, zero=zero_planes) if want_planes else None
+    stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device) if want_stats else None
+    check(lib.snuffy_ln_rows_fwd(x.data_ptr(), _ptr(row_map), _ptr(alt), _ptr(gamma), _ptr(beta), rows, d,
+                                 1 if apply_ln else 0, _ptr(out), planes.ptr if planes else None,
+                                 planes.stride if planes else 0, plane_rc, _ptr(stats), _stream()), "snuffy_ln_rows_fwd")
+    return out, planes, stats
+
+
+_HEAD_WS = {}
+
+
+def ln_mean_head(x: torch.Tensor, gamma, beta, w_head, b_head, *, want_stats: bool = False, want_pooled: bool = False):
+    """bag[B, C] = head(mean_n LN_f(x[b]))  (snuffy.py:86,71).  x [B, N, d]."""
+    x = _f32(x, "x")
+    B, N, d = x.shape
+    C = w_head.shape[0]
+    chunks = lib.snuffy_ln_mean_head_chunks(B, N)
+    key = (x.device.index, B)
+    tickets = _HEAD_WS.get(key)
+    if tickets is None:                      # zeroed once; the kernel leaves it zeroed
+        tickets = _HEAD_WS[key] = torch.zeros(B, dtype=torch.int32, device=x.device)
+    partials = torch.empty(B * chunks * d, dtype=torch.float32, device=x.device)
+    stats = torch.empty(B * N, 2, dtype=torch.float32, device=x.device) if want_stats else None
+    pooled = torch.empty(B, d, dtype=torch.float32, device=x.device) if want_pooled else None
+    bag = torch.empty(B, C, dtype=torch.float32, device=x.device)
+    check(lib.snuffy_ln_mean_head_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w_head.data_ptr(), _ptr(b_head),
+                                      B, N, d, C, partials.data_ptr(), tickets.data_ptr(), _ptr(stats), _ptr(pooled),
+                                      bag.data_ptr(), _stream()), "snuffy_ln_mean_head_fwd")
+    return bag, stats, pooled
+
+
+# ------------------------------------------------------------------ GEMMs
+def gemm_f32(a: torch.Tensor, b: torch.Tensor, *, a_kc: bool = True, b_kc: bool = True, M: int, N: int, K: int,
+             bias=None, act: str = "none", resid=None, row_map=None, resid_alt=None, alpha: float = 1.0,
+             want_preact: bool = False, lda: Optional[int] = None, ldb: Optional[int] = None,
+             out: Optional[torch.Tensor] = None, drop: Tuple[float, int, int] = (0.0, 0, 0)):
+    """fp32 SIMT GEMM  C[M,N] = act(alpha * A.B^T + bias) + resid  (csrc/gemm_simt.cu)."""
+    a = _f32(a, "a")
+    b = _f32(b, "b")
+    lda = lda if lda is not None else a.shape[-1]
+    ldb = ldb if ldb is not None else b.shape[-1]
+    c = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=a.device)
+    pre = torch.empty(M, N, dtype=torch.float32, device=a.device) if want_preact else None
+    ldr = resid.shape[-1] if resid is not None else 0
+    check(lib.snuffy_gemm_f32(a.data_ptr(), lda, 1 if a_kc else 0, b.data_ptr(), ldb, 1 if b_kc else 0, c.data_ptr(), N,
+                              M, N, K, alpha, _ptr(bias), ACT_IDS[act], _ptr(resid), ldr, _ptr(row_map), _ptr(resid_alt),
+                              _ptr(pre), float(drop[0]), drop[1] & _U64, drop[2] & _U64, _stream()), "snuffy_gemm_f32")
+    return (c, pre) if want_preact else c
+
+
+def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias=None, act: str = "none", resid=None,
+               drop: Tuple[float, int, int] = (0.0, 0, 0)) -> torch.Tensor:
+    """y = dropout(act(x W^T + b)) (+ resid) for x [rows, K], weight [N, K]."""
+    rows, K = x.shape
+    return gemm_f32(x, weight, M=rows, N=weight.shape[0], K=K, bias=bias, act=act, resid=resid, drop=drop)
+
+
+def weight_planes(weight: torch.Tensor) -> Planes:
+    """Split an nn.Linear weight [N, K] into B-operand planes (zero padded to the kernel's BLOCK_N)."""
+    weight = _f32(weight, "weight")
+    n = weight.shape[0]
+    rc = lib.snuffy_gemm_tc_block_n(n)
+    _, planes, _ = ln_rows(weight, None, None, apply_ln=False, want_planes=True, plane_rc=rc, zero_planes=True)
+    return planes
+
+
+def gemm_tc(a: Planes, b: Planes, *, M: int, N: int, K: int, passes: int = 3, bias=None, act: str = "none",
+            resid=None, row_map=None, resid_alt=None, want_out: bool = True, want_preact: bool = False,
+            want_planes: bool = False, device=None, drop: Tuple[float, int, int] = (0.0, 0, 0)):
+    """tcgen05 split-bf16 GEMM (csrc/gemm_tc.cu).  Returns (out fp32 or None, preact or None, Planes or None)."""
+    device = device if device is not None else a.buf.device
+    out = torch.empty(M, N, dtype=torch.float32, device=device) if want_out else None
+    pre = torch.empty(M, N, dtype=torch.float32, device=device) if want_preact else None
+    op = Planes(M, N, 128, device) if want_planes else None
+    ldr = resid.shape[-1] if resid is not None else 0
+    check(lib.snuffy_gemm_tc(a.ptr, a.stride, b.ptr, b.stride, M, N, K, passes, _ptr(bias), ACT_IDS[act], _ptr(resid),
+                             ldr, _ptr(row_map), _ptr(resid_alt), _ptr(out), N, _ptr(pre), op.ptr if op else None,
+                             op.stride if op else 0, float(drop[0]), drop[1] & _U64, drop[2] & _U64, _stream()),
+          "snuffy_gemm_tc")
+    return out, pre, op
+
+
+# ------------------------------------------------------------------ a9: sparse attention
+def _rows_view(t: torch.Tensor, name: str) -> torch.Tensor:
+    """2-D fp32 CUDA tensor whose last dim is contiguous (rows may be strided, e.g. a column slice of Q|V)."""
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise TypeError(f"snuffy_b200: `{name}` must be a float32 CUDA tensor")
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.reshape(-1, t.shape[-1]).contiguous()
+    return t
+
+
+def sparse_attn(q: torch.Tensor, v: torch.Tensor, kp: torch.Tensor, B: int, N: int, Ksel: int, h: int, *,
+                want_probs: bool = True, want_stats: bool = False, dropout_p: float = 0.0, seed: int = 0,
+                offset: int = 0):
+    """q, v [B*N, d] (row-strided views allowed), kp [B*Ksel, d] -> O [B*Ksel, d], P [B, h, N, Ksel] or None,
+    stats [B, h, N, 2] = (row max, 1/row sum) or None.   snuffy.py:160-168."""
+    q, v = _rows_view(q, "q"), _rows_view(v, "v")
+    kp = _f32(kp, "kp")
+    d = kp.shape[-1]
+    dev = q.device
+    ws_bytes = lib.snuffy_sparse_attn_workspace(B, N, Ksel, h, d)
+    if ws_bytes < 0:
+        raise ValueError(f"d_model={d} is not divisible by h={h}")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    o = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
+    probs = torch.empty(B, h, N, Ksel, dtype=torch.float32, device=dev) if want_probs else None
+    stats = torch.empty(B, h, N, 2, dtype=torch.float32, device=dev) if want_stats else None
+    check(lib.snuffy_sparse_attn_fwd(q.data_ptr(), q.stride(0), v.data_ptr(), v.stride(0), kp.data_ptr(), B, N, Ksel, h,
+                                     d, float(dropout_p), seed & _U64, offset & _U64, o.data_ptr(), _ptr(probs),
+                                     _ptr(stats), ws.data_ptr(), ws_bytes, _stream()), "snuffy_sparse_attn_fwd")
+    return o, probs, stats
+
+
+# ------------------------------------------------------------------ a15: DSMIL pooling
+def dsmil_pool(q: torch.Tensor, q_max: torch.Tensor, v: torch.Tensor, w_fcc: torch.Tensor, b_fcc):
+    """A[N,C], Bm[C,d], logits[C] (dsmil.py:83-91)."""
+    q, q_max, v, w_fcc = _f32(q, "q"), _f32(q_max, "q_max"), _f32(v, "v"), _f32(w_fcc, "w_fcc")
+    N, dq = q.shape
+    C = q_max.shape[0]
+    d = v.shape[1]
+    dev = q.device
+    ws_bytes = lib.snuffy_dsmil_workspace(N, d, C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    A = torch.empty(N, C, dtype=torch.float32, device=dev)
+    Bm = torch.empty(C, d, dtype=torch.float32, device=dev)
+    logits = torch.empty(C, dtype=torch.float32, device=dev)
+    check(lib.snuffy_dsmil_pool_fwd(q.data_ptr(), q_max.data_ptr(), v.data_ptr(), w_fcc.data_ptr(), _ptr(b_fcc), N, d, dq,
+                                    C, A.data_ptr(), Bm.data_ptr(), logits.data_ptr(), None, ws.data_ptr(), ws_bytes,
+                                    _stream()), "snuffy_dsmil_pool_fwd")
+    return A, Bm, logits

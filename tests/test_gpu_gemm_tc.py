@@ -1,0 +1,86 @@
+"""tcgen05 split-bf16 GEMM (csrc/gemm_tc.cu) against float64 numpy and against the fp32 SIMT GEMM."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import decode_planes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from snuffy_b200 import ops as _ops
+    return _ops
+
+
+def _operands(ops, M, N, K, seed):
+    rs = np.random.RandomState(seed)
+    a = rs.standard_normal((M, K)).astype(np.float32)
+    b = (rs.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    _, ap, _ = ops.ln_rows(ad, None, None, apply_ln=False, want_planes=True)
+    return a, b, ad, bd, ap, ops.weight_planes(bd)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 256, 64), (256, 512, 512), (300, 384, 96), (1000, 2048, 512),
+                                   (1000, 512, 2048), (10000, 1024, 512), (777, 48, 48), (64, 32, 32)])
+def test_gemm_tc_three_pass_matches_fp32(ops, M, N, K):
+    a, b, ad, bd, ap, bp = _operands(ops, M, N, K, M + N + K)
+    out, _, _ = ops.gemm_tc(ap, bp, M=M, N=N, K=K, passes=3)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    err = np.abs(out.cpu().numpy() - ref).max()
+    # 3-pass split keeps ~16 mantissa bits per operand: error ~ 2^-16 * |a||b| * sqrt(K) terms, far below 1e-4
+    assert err < 3e-5 * max(1.0, np.abs(ref).max()), err
+    simt = ops.gemm_f32(ad, bd, M=M, N=N, K=K).cpu().numpy()
+    assert np.abs(out.cpu().numpy() - simt).max() < 3e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_gemm_tc_single_pass_is_bf16(ops):
+    M, N, K = 256, 256, 128
+    a, b, ad, bd, ap, bp = _operands(ops, M, N, K, 1)
+    out, _, _ = ops.gemm_tc(ap, bp, M=M, N=N, K=K, passes=1)
+    r = lambda t: torch.from_numpy(t).to(torch.bfloat16).to(torch.float64).numpy()
+    ref = r(a) @ r(b).T
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "gelu"])
+def test_gemm_tc_epilogue(ops, act):
+    from oracle import snuffy_oracle as so
+    M, N, K, ks = 700, 256, 64, 11
+    a, b, ad, bd, ap, bp = _operands(ops, M, N, K, 3)
+    rs = np.random.RandomState(9)
+    bias = rs.standard_normal(N).astype(np.float32)
+    resid = rs.standard_normal((M, N)).astype(np.float32)
+    alt = rs.standard_normal((ks, N)).astype(np.float32)
+    sel = rs.permutation(M)[:ks]
+    rm = -np.ones(M, np.int32)
+    rm[sel] = np.arange(ks)
+    t = lambda v, dt=torch.float32: torch.as_tensor(v, dtype=dt).cuda()
+    out, pre, planes = ops.gemm_tc(ap, bp, M=M, N=N, K=K, passes=3, bias=t(bias), act=act, resid=t(resid),
+                                   row_map=t(rm, torch.int32), resid_alt=t(alt), want_out=True, want_preact=True,
+                                   want_planes=True)
+    z = a.astype(np.float64) @ b.astype(np.float64).T + bias
+    fn = (lambda v: v) if act == "none" else so.activation_fn(act)
+    r = resid.astype(np.float64).copy()
+    r[sel] = alt
+    assert np.abs(pre.cpu().numpy() - z).max() < 3e-5
+    assert np.abs(out.cpu().numpy() - (fn(z) + r)).max() < 3e-5
+    hi, lo = decode_planes(planes, M, N)
+    assert np.abs(hi + lo - fn(z)).max() < 6e-5         # activated value, split again for the next GEMM
+
+
+def test_gemm_tc_chained_like_ffn(ops):
+    """planes_out of GEMM 1 feed GEMM 2 as the A operand (FFN up -> down), K padding included."""
+    M, d, dff = 500, 48, 192
+    rs = np.random.RandomState(5)
+    x = rs.standard_normal((M, d)).astype(np.float32)
+    w1 = (rs.standard_normal((dff, d)) / np.sqrt(d)).astype(np.float32)
+    w2 = (rs.standard_normal((d, dff)) / np.sqrt(dff)).astype(np.float32)
+    t = lambda v: torch.from_numpy(v).cuda()
+    _, xp, _ = ops.ln_rows(t(x), None, None, apply_ln=False, want_planes=True)
+    _, _, hp = ops.gemm_tc(xp, ops.weight_planes(t(w1)), M=M, N=dff, K=d, act="relu", want_out=False, want_planes=True)
+    out, _, _ = ops.gemm_tc(hp, ops.weight_planes(t(w2)), M=M, N=d, K=dff, resid=t(x))
+    ref = x + np.maximum(x.astype(np.float64) @ w1.T.astype(np.float64), 0) @ w2.T.astype(np.float64)
+    assert np.abs(out.cpu().numpy() - ref).max() < 5e-5
