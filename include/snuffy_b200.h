@@ -1,0 +1,119 @@
+/* libsnuffy_b200 — C ABI of the B200-native Snuffy / DSMIL MIL-aggregator hot path.
+ *
+ * The reference (jafarinia/snuffy @ 4b5b918) has no FFI: its hot path is a set of nn.Module classes whose
+ * forward() methods call PyTorch ATen ops.  Each entry point below replaces the ATen op
+ * sequence at the cited reference lines; the drop-in nn.Modules in snuffy_b200/{snuffy,snuffy_multiclass,
+ * dsmil}.py bind them through ctypes (snuffy_b200/_lib.py) — see INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types, no exceptions, no exit().
+ *   - every function returns 0 on success; on failure a non-zero status and snuffy_last_error() (per host
+ *     thread) describes it.  Arguments are validated before any launch.
+ *   - all pointers are DEVICE pointers to contiguous row-major fp32 unless stated; indices are int64;
+ *     every function takes an explicit cudaStream_t, is asynchronous, re-entrant and never synchronises
+ *     (a whole forward can be captured into a CUDA graph).
+ *   - "planes" = split-bf16 operand planes (hi, lo) pre-tiled for tcgen05 (layout: csrc/common.cuh).
+ */
+#ifndef SNUFFY_B200_H
+#define SNUFFY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* snuffy_stream_t;   /* == cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int         snuffy_version(void);
+const char* snuffy_last_error(void);
+int         snuffy_sm_count(void);
+long long   snuffy_launch_count(void);          /* kernels launched since load (bench.py: gpu_launches) */
+
+/* ---- a1: instance scores  c = x W^T + b            (snuffy.py:39-41 FCLayer.forward, nn.Linear)      */
+int snuffy_scores_fwd(const float* x, const float* W, const float* bias, float* c,
+                      int64_t rows, int64_t d, int64_t C, snuffy_stream_t stream);
+
+/* ---- a6/a12: patch selection                                                                         */
+/* per (bag, class) the K best rows, descending score, ties -> lower index. Replaces torch.sort + slice
+ * (snuffy.py:128-129, snuffy_multiclass.py:136-138, dsmil.py:78-81 with K = 1).
+ * scores [B,N,C]; idx_out [B,C,K] int64; flags [B,N] uint8 (optional, caller-zeroed) marks winners.   */
+int snuffy_select_topk(const float* scores, int64_t B, int64_t N, int64_t C, int64_t K,
+                       int64_t* idx_out, uint8_t* flags, snuffy_stream_t stream);
+/* K distinct un-flagged rows per bag, uniform without replacement (Philox4x32-10 keyed by seed/offset).
+ * Replaces .tolist() + python set difference + np.random.choice + .to(device)  (snuffy.py:136-143,
+ * snuffy_multiclass.py:152-157) without the D2H/H2D round trip.  idx_out [B,K] int64.                  */
+int snuffy_select_random(const uint8_t* flags, int64_t B, int64_t N, int64_t K, uint64_t seed,
+                         uint64_t offset, int64_t* idx_out, snuffy_stream_t stream);
+/* ascending distinct flagged rows per bag = torch.unique of the flattened per-class top-K
+ * (snuffy_multiclass.py:139-141).  out [B,cap] int64, counts [B] int32.                                */
+int snuffy_compact_flags(const uint8_t* flags, int64_t B, int64_t N, int64_t cap, int64_t* out,
+                         int32_t* counts, snuffy_stream_t stream);
+/* out[B,K,d] = x[b, idx[b,k], :]      (torch.index_select / gather: snuffy.py:131,145-147,103-106)     */
+int snuffy_gather_rows(const float* x, const int64_t* idx, int64_t B, int64_t N, int64_t K, int64_t d,
+                       float* out, snuffy_stream_t stream);
+/* row_map[B*N] int32 = -1 | slot b*K+k.  Replaces y = x.clone(); y[:, S, :] = x_sel (snuffy.py:152-155):
+ * later kernels read "x with the selected rows replaced" through this map, x is never copied.          */
+int snuffy_build_row_map(const int64_t* idx, int64_t B, int64_t N, int64_t K, int32_t* row_map,
+                         snuffy_stream_t stream);
+
+/* ---- LayerNorm (eps 1e-5, affine)                                                                    */
+/* rows of y = (row_map ? x with mapped rows taken from alt : x) -> LN -> fp32 and/or planes and/or
+ * (mean, rstd).  apply_ln = 0: plain convert/split.  Replaces nn.LayerNorm at snuffy.py:107,110 and
+ * produces the tcgen05 A operand in the same pass.  plane_rc: 128 (activations) or
+ * snuffy_gemm_tc_block_n(rows) (weights).                                                              */
+int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt, const float* gamma,
+                       const float* beta, int64_t rows, int64_t d, int apply_ln, float* out_f32,
+                       void* planes, int64_t plane_stride, int plane_rc, float* stats,
+                       snuffy_stream_t stream);
+/* bag[B,C] = head(mean_n LN_f(x[b,n,:]))   (Encoder.norm + BClassifier: snuffy.py:86 + 71) in one pass.
+ * partials: B*chunks*d floats (chunks = snuffy_ln_mean_head_chunks); tickets: B uint32 zeroed once.     */
+int64_t snuffy_ln_mean_head_chunks(int64_t B, int64_t N);
+int snuffy_ln_mean_head_fwd(const float* x, const float* gamma, const float* beta, const float* Wh,
+                            const float* bh, int64_t B, int64_t N, int64_t d, int64_t C,
+                            float* partials, uint32_t* tickets, float* stats, float* pooled,
+                            float* bag_out, snuffy_stream_t stream);
+
+/* ---- GEMMs                                                                                            */
+/* fp32 SIMT: C[M,N] = dropout(act(alpha * A.B^T + bias)) + resid(row_map).  a_kc/b_kc = 1: operand stored
+ * [rows,K]; 0: stored [K,rows].  Replaces nn.Linear on [Ksel,d] rows (snuffy.py:188 key proj, 205 out proj),
+ * dsmil's q/v MLPs (dsmil.py:56-66) and all backward contractions.                                     */
+int snuffy_gemm_f32(const float* A, int64_t lda, int a_kc, const float* B, int64_t ldb, int b_kc,
+                    float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha,
+                    const float* bias, int act, const float* resid, int64_t ldr, const int32_t* row_map,
+                    const float* resid_alt, float* preact, float dropout_p, uint64_t seed,
+                    uint64_t offset, snuffy_stream_t stream);
+/* tcgen05 split-bf16 (3-pass) GEMM on planes: the Q|V projection (snuffy.py:188) and the FFN
+ * (snuffy.py:225) over all N tokens.  Outputs: fp32 out (+residual through row_map), fp32 preact,
+ * and/or the activated result as A planes for the next GEMM.                                           */
+int     snuffy_gemm_tc_block_n(int64_t N);
+int64_t snuffy_plane_elems(int64_t rows, int64_t K, int rc);
+int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_planes,
+                   int64_t b_plane_stride, int64_t M, int64_t N, int64_t K, int passes,
+                   const float* bias, int act, const float* resid, int64_t ldr, const int32_t* row_map,
+                   const float* resid_alt, float* out, int64_t ldc, float* preact, void* out_planes,
+                   int64_t out_plane_stride, float dropout_p, uint64_t seed, uint64_t offset,
+                   snuffy_stream_t stream);
+
+/* ---- a9: sparse attention  O = concat_j softmax_keys(Q_j Kp_j^T / sqrt(dk))^T V_j                      */
+/* Replaces matmul / div / softmax / dropout / matmul / transpose+contiguous (snuffy.py:160-168, 187-201).
+ * Q,V [B*N,d] with row strides ldq/ldv; Kp [B*Ksel,d]; O [B*Ksel,d]; P_out [B,h,N,Ksel] optional
+ * (pre-dropout, as the reference returns it); stats_out [B,h,N,2] = (row max, 1/row sum) optional.     */
+int64_t snuffy_sparse_attn_workspace(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d);
+int snuffy_sparse_attn_fwd(const float* Q, int64_t ldq, const float* V, int64_t ldv, const float* Kp,
+                           int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d, float dropout_p,
+                           uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
+                           void* workspace, int64_t workspace_bytes, snuffy_stream_t stream);
+
+/* ---- a15: DSMIL critical-instance pooling   (dsmil.py:83-91: mm, softmax over dim 0, mm, Conv1d)       */
+int64_t snuffy_dsmil_workspace(int64_t N, int64_t d, int64_t C);
+int snuffy_dsmil_pool_fwd(const float* Q, const float* qmax, const float* V, const float* Wfcc,
+                          const float* bfcc, int64_t N, int64_t d, int64_t dq, int64_t C, float* A,
+                          float* Bm, float* logits, float* stats_out, void* workspace,
+                          int64_t workspace_bytes, snuffy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNUFFY_B200_H */

@@ -12,7 +12,7 @@
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      bulk-copy producer (+ TMEM alloc/dealloc)          full/empty mbarrier ring
 //   warp 1      single-thread tcgen05.mma issuer                    accumulators double-buffered in TMEM
-//   warps 2..5  epilogue: tcgen05.ld -> bias/activation -> (a) split-bf16 planes for the next GEMM, written
+//   warps 2..9  epilogue: tcgen05.ld -> bias/activation -> (a) split-bf16 planes for the next GEMM, written
 //               straight from the row-owner register layout (512 B coalesced per warp store), and/or
 //               (b) fp32 rows (+ residual read through row_map) transposed through shared memory.
 #include "common.cuh"
@@ -20,14 +20,14 @@
 namespace snuffy {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;          // producer warp + MMA warp + 8 epilogue warps
 constexpr uint32_t TC_A_PLANE_BYTES = TC_BM * PLANE_KB * 2;          // 8 KB per plane per stage
 
 template <int BN> struct TcCfg {
     static constexpr uint32_t B_PLANE_BYTES = BN * PLANE_KB * 2;
     static constexpr uint32_t STAGE_BYTES = 2 * TC_A_PLANE_BYTES + 2 * B_PLANE_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;             // epilogue transpose buffers
+    static constexpr uint32_t STG_BYTES = 8 * 32 * 33 * 4;             // epilogue transpose buffers (one per warp)
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 256;
     static constexpr uint32_t TMEM_COLS = 2 * BN;                      // two accumulator stages
 };
@@ -134,7 +134,7 @@ gemm_tc_kernel(const TcGemmParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -218,26 +218,40 @@ gemm_tc_kernel(const TcGemmParams p) {
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quadrant warp % 4)
-        const int quad = warp & 3;
+        // ------------------------------------------------ epilogue: 8 warps, warp % 4 = TMEM lane quadrant,
+        // (warp - 2) / 4 = which half of the tile's columns.  All global loads of a chunk are issued before its stores.
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         float* stg = stg_base + (size_t)(warp - 2) * 32 * 33;
         int acc = 0; uint32_t acc_phase = 0;
-        const int kpad_next = (int)plane_kblocks(p.N) * PLANE_KB;
+        const int nkb_next = (int)plane_kblocks(p.N);
+        const int kpad_next = nkb_next * PLANE_KB;
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;           // coalesced phase: 4 rows x 8 float4 per pass
+        constexpr int CH = BN / 64;                                // 32-column chunks per half
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-            const int64_t m_own = (int64_t)mt * TC_BM + quad * 32 + lane;     // row this thread owns in TMEM
-            const int n0 = nt * BN;
+            const int rr_own = quad * 32 + lane;                   // row of the tile this thread owns in TMEM
+            const int64_t m_own = (int64_t)mt * TC_BM + rr_own;
+            const int64_t m_base = (int64_t)mt * TC_BM + quad * 32;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n0 + c * 32;
+            for (int cc = 0; cc < CH; ++cc) {
+                const int c = half * CH + cc;
+                const int col0 = nt * BN + c * 32;
                 if (col0 >= p.N && col0 >= kpad_next) break;
                 float v[32];
                 tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                 if (p.bias) {
+                    if (col0 + 32 <= p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+                    }
                 }
                 if (p.preact) {
 #pragma unroll
@@ -245,8 +259,8 @@ gemm_tc_kernel(const TcGemmParams p) {
                     __syncwarp();
 #pragma unroll
                     for (int rr = 0; rr < 32; rr += 4) {
-                        const int row = rr + (lane >> 3), c4 = (lane & 7) * 4;
-                        const int64_t m = (int64_t)mt * TC_BM + quad * 32 + row;
+                        const int row = rr + rsub;
+                        const int64_t m = m_base + row;
                         const int col = col0 + c4;
                         if (m < p.M && col < p.N)
                             *reinterpret_cast<float4*>(p.preact + m * p.ldc + col) =
@@ -255,9 +269,15 @@ gemm_tc_kernel(const TcGemmParams p) {
                     }
                     __syncwarp();
                 }
-                if (p.act != ACT_NONE) {
+                switch (p.act) {          // hoisted: one uniform branch per chunk, straight-line code per activation
+                    case ACT_RELU:
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = act_apply(p.act, v[j]);
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                        break;
+                    case ACT_NONE: break;
+                    default:
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = act_apply(p.act, v[j]);
                 }
                 if (p.drop_p > 0.f) {
 #pragma unroll
@@ -265,17 +285,19 @@ gemm_tc_kernel(const TcGemmParams p) {
                         v[j] *= drop_keep_scale(p.seed, p.offset, (uint64_t)(m_own * p.N + col0 + j), p.drop_p);
                 }
                 if (p.out_planes) {
-                    // thread owns row m_own and 32 consecutive k of the next GEMM: 4 units of 8
+                    // thread owns row m_own and 32 consecutive k of the next GEMM = one chunk column block:
+                    // kb = col0 / 32, four 16-byte units (kg = 0..3) that are 128 rows * 16 B apart.  Rows >= M are
+                    // written as zeros so that consumers contracting over rows never meet non-finite padding.
+                    if (col0 < kpad_next) {
+                        const bool live = m_own < p.M;
+                        __nv_bfloat16* dst = p.out_planes + (((int64_t)mt * nkb_next + (col0 >> 5)) * 4) * (TC_BM * 8) + rr_own * 8;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = col0 + u * 8;
-                        if (k < kpad_next) {
+                        for (int u = 0; u < 4; ++u) {
                             bf16x8 h, l;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) split_bf16(v[u * 8 + j], h.v[j], l.v[j]);
-                            const int64_t off = plane_unit_offset(m_own, k, p.N, TC_BM);
-                            *reinterpret_cast<bf16x8*>(p.out_planes + off) = h;
-                            *reinterpret_cast<bf16x8*>(p.out_planes + p.out_plane_stride + off) = l;
+                            for (int j = 0; j < 8; ++j) split_bf16(live ? v[u * 8 + j] : 0.f, h.v[j], l.v[j]);
+                            *reinterpret_cast<bf16x8*>(dst + u * (TC_BM * 8)) = h;
+                            *reinterpret_cast<bf16x8*>(dst + p.out_plane_stride + u * (TC_BM * 8)) = l;
                         }
                     }
                 }
@@ -283,23 +305,32 @@ gemm_tc_kernel(const TcGemmParams p) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
                     __syncwarp();
+                    const int col = col0 + c4;
+                    float4 r4[8];
+                    if (p.resid) {
+                        const float* rrow[8];
 #pragma unroll
-                    for (int rr = 0; rr < 32; rr += 4) {
-                        const int row = rr + (lane >> 3), c4 = (lane & 7) * 4;
-                        const int64_t m = (int64_t)mt * TC_BM + quad * 32 + row;
-                        const int col = col0 + c4;
+                        for (int i = 0; i < 8; ++i) {
+                            const int64_t m = m_base + i * 4 + rsub;
+                            rrow[i] = p.resid + (m < p.M ? m : 0) * p.ldr;
+                            if (p.row_map && m < p.M) {
+                                const int32_t slot = __ldg(p.row_map + m);
+                                if (slot >= 0) rrow[i] = p.resid_alt + (int64_t)slot * p.ldr;
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            r4[i] = (col < p.N) ? __ldg(reinterpret_cast<const float4*>(rrow[i] + col))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + rsub;
+                        const int64_t m = m_base + row;
                         if (m < p.M && col < p.N) {
                             float4 o = make_float4(stg[row * 33 + c4], stg[row * 33 + c4 + 1], stg[row * 33 + c4 + 2],
                                                    stg[row * 33 + c4 + 3]);
-                            if (p.resid) {
-                                const float* rrow = p.resid + m * p.ldr;
-                                if (p.row_map) {
-                                    const int32_t slot = __ldg(p.row_map + m);
-                                    if (slot >= 0) rrow = p.resid_alt + (int64_t)slot * p.ldr;
-                                }
-                                const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + col));
-                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                            }
+                            if (p.resid) { o.x += r4[i].x; o.y += r4[i].y; o.z += r4[i].z; o.w += r4[i].w; }
                             *reinterpret_cast<float4*>(p.out + m * p.ldc + col) = o;
                         }
                     }
