@@ -12,7 +12,7 @@ mkdir -p build
 pids=()
 for f in "$SRC"/*.cu; do
   o=build/$(basename "${f%.cu}").o
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$SRC/common.cuh" -nt "$o" ]]; then
+  if [[ ! -f "$o" || "$f" -nt "$o" || "$SRC/common.cuh" -nt "$o" || "$SRC/tc_ptx.cuh" -nt "$o" ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" &
     pids+=($!)
   fi

@@ -106,6 +106,16 @@ int snuffy_sparse_attn_fwd(const float* Q, int64_t ldq, const float* V, int64_t 
                            uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
                            void* workspace, int64_t workspace_bytes, snuffy_stream_t stream);
 
+/* Tensor-core version of the same contract (tcgen05, split-bf16 3-pass, P never leaves the SM): Q and V arrive as
+ * the planes the Q|V projection wrote over [B*N, ldk] (Q at column q_col0, V at v_col0).  The workspace query
+ * returns -1 for shapes it does not serve (needs dk % 32 == 0, dk <= 128, operands within 227 KB of smem).     */
+int64_t snuffy_sparse_attn_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d);
+int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0,
+                              int64_t v_col0, const float* Kp, int64_t B, int64_t N, int64_t Ksel,
+                              int64_t h, int64_t d, float dropout_p, uint64_t seed, uint64_t offset,
+                              float* O, float* P_out, float* stats_out, void* workspace,
+                              int64_t workspace_bytes, snuffy_stream_t stream);
+
 /* ---- a15: DSMIL critical-instance pooling   (dsmil.py:83-91: mm, softmax over dim 0, mm, Conv1d)       */
 int64_t snuffy_dsmil_workspace(int64_t N, int64_t d, int64_t C);
 int snuffy_dsmil_pool_fwd(const float* Q, const float* qmax, const float* V, const float* Wfcc,

@@ -40,6 +40,8 @@ _SIGNATURES = {
                               P]),
     "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),
     "snuffy_sparse_attn_fwd": (c_int, [P, I, P, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
+    "snuffy_sparse_attn_tc_workspace": (c_int64, [I, I, I, I, I]),
+    "snuffy_sparse_attn_tc_fwd": (c_int, [P, I, I, I, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
     "snuffy_dsmil_workspace": (c_int64, [I, I, I]),
     "snuffy_dsmil_pool_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P, P, P, P, P, I, P]),
 }

@@ -245,6 +245,10 @@ fold_partials_kernel(const float* __restrict__ part, int splits, int64_t n4, flo
     reinterpret_cast<float4*>(out)[i] = acc;
 }
 
+void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream) {
+    fold_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(part, splits, n4, out);
+}
+
 struct AttnPlan { int KC, nkc, nvs, splits, rows_per_split; size_t smem; };
 
 static AttnPlan plan_attn(int B, int N, int Ksel, int h, int dk) {

@@ -1,0 +1,365 @@
+// Snuffy sparse attention on the 5th-gen tensor cores (snuffy.py:160-168, 187-201).
+//
+//   S_j = Q_j Kp_j^T / sqrt(dk)   [N, Ksel]    softmax over the Ksel keys of each query row
+//   O_j = P_j^T V_j               [Ksel, dk]   transposed aggregation: the contraction runs over the N queries
+//
+// Both contractions are split-bf16 3-pass tcgen05.mma (fp32 accumulate in TMEM) so the result matches fp32 to
+// ~2^-16; with fp32 SIMT math this kernel is ~8x compute-bound over its HBM time.
+//
+// Operands:
+//   Q, V  : the Q|V projection GEMM writes its result directly as split-bf16 A-operand planes over
+//           [B*N, 2d] (csrc/common.cuh).  A (row-tile, head) block of Q is 128 x dk, K-major: the A operand of
+//           S = Q Kp^T.  The same block of V, read through an MN-major descriptor, is the B operand of
+//           O = P^T V (N = dv contiguous in each 16-byte unit, K = query row).  No transposes, one bulk copy each.
+//   Kp    : fp32 [B*Ksel, d]; each CTA splits its head's keys into shared memory once per work item.
+//   P     : never leaves the SM: the softmax warps write it as MN-major split-bf16 planes (M = key, K = query).
+//
+// Work item = (bag, head, row-tile range).  Per 128-query tile:
+//   warp 0   bulk-copy producer: Q tile, V tile (single buffers, re-armed by tcgen05.commit)
+//   warp 1   MMA issuer:  S(t) = Q Kp^T  -> TMEM[0, KP);  O += P(t-1)^T V(t-1) -> TMEM[256, 256 + 2*dk)
+//   warps 2-5  one query row per thread: three passes over the TMEM row (max, sum, normalise), P -> smem,
+//            at the end of the item O -> registers -> per-split partial (folded by fold_partials_kernel).
+#include "tc_ptx.cuh"
+
+namespace snuffy {
+
+void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream);
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_TILE = 128;            // queries per tile (UMMA M)
+constexpr uint32_t AT_O_COL = 256;      // TMEM column of the O accumulators
+
+struct AttnTcParams {
+    const __nv_bfloat16* planes; int64_t plane_stride;   // Q|V planes over [rows, ldk], A layout, RC = 128
+    int nkb;                          // k-blocks (of 32 columns) per row tile of the planes = ldk / 32
+    int q_kb0, v_kb0;                 // first k-block of Q / V columns (head j adds j * dk / 32)
+    const float* Kp;                  // [B*Ksel, d]
+    int B, N, Ksel, KP, h, dk, d;
+    int splits, tiles_per_split;
+    float c_log2;                     // log2(e) / sqrt(dk)
+    float* O_part;                    // [splits, B*Ksel, d]
+    float* P_out;                     // [B, h, N, Ksel] or null (pre-dropout)
+    float* stats_out;                 // [B, h, N, 2] (row max of the scaled scores, 1 / row sum) or null
+    float drop_p; uint64_t seed, offset;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const AttnTcParams p) {
+    extern __shared__ __align__(1024) unsigned char at_smem[];
+    const int dk = p.dk, KP = p.KP;
+    const uint32_t P_PLANE = (uint32_t)KP * 256u;            // [KP/8 key groups][128 queries][8 keys] bf16
+    const uint32_t QV_PLANE = (uint32_t)AT_TILE * dk * 2u;   // [dk/8][128][8] bf16
+    const uint32_t KP_PLANE = (uint32_t)KP * dk * 2u;        // [dk/8][KP][8] bf16
+    // order matters: the second 128-key MMA block reads past KP inside sP; what follows must be mapped smem
+    unsigned char* sP = at_smem;
+    unsigned char* sK = sP + 2 * P_PLANE;
+    unsigned char* sQ = sK + 2 * KP_PLANE;
+    unsigned char* sV = sQ + 2 * QV_PLANE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * QV_PLANE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const uint32_t b0 = smem_u32(bars);
+    const uint32_t q_full = b0, q_empty = b0 + 8, v_full = b0 + 16, v_empty = b0 + 24, s_full = b0 + 32,
+                   s_empty = b0 + 40, p_full = b0 + 48, p_empty = b0 + 56, o_full = b0 + 64;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+        mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int mblocks = (KP + 127) / 128;
+    const int ksteps = dk / 16;
+    const int chunks_per_head = dk / PLANE_KB;
+    const int64_t chunk_elems = (int64_t)AT_TILE * PLANE_KB;
+    const int items = p.B * p.h * p.splits;
+    uint32_t it = 0;          // tiles processed by this CTA so far (every role counts the same sequence)
+    uint32_t item_no = 0;
+
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_no) {
+        const int split = item % p.splits;
+        const int j = (item / p.splits) % p.h;
+        const int b = item / (p.splits * p.h);
+        const int64_t g_lo = (int64_t)b * p.N, g_hi = g_lo + p.N;           // global rows of this bag
+        const int64_t t_first = g_lo / AT_TILE, t_last = (g_hi + AT_TILE - 1) / AT_TILE;
+        const int64_t t0 = t_first + (int64_t)split * p.tiles_per_split;
+        const int64_t t1 = min(t_last, t0 + p.tiles_per_split);
+        const int ntiles = (int)max((int64_t)0, t1 - t0);
+
+        __syncthreads();                       // previous item: O read out, every MMA retired
+        if (warp >= 2) {
+            // ---- split this head's keys into the K-major B operand of S = Q Kp^T (zero rows beyond Ksel)
+            const int units = KP * (dk / 8);
+            for (int idx = threadIdx.x - 64; idx < units; idx += AT_THREADS - 64) {
+                const int key = idx % KP, kg = idx / KP;
+                bf16x8 hi, lo;
+                if (key < p.Ksel) {
+                    const float* src = p.Kp + ((int64_t)b * p.Ksel + key) * p.d + j * dk + kg * 8;
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                    const float4 c = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) split_bf16(f[e], hi.v[e], lo.v[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { hi.v[e] = __float2bfloat16_rn(0.f); lo.v[e] = hi.v[e]; }
+                }
+                *reinterpret_cast<bf16x8*>(sK + (size_t)idx * 16) = hi;
+                *reinterpret_cast<bf16x8*>(sK + KP_PLANE + (size_t)idx * 16) = lo;
+            }
+            fence_proxy_async_smem();
+        }
+        __syncthreads();
+
+        if (warp == 0) {
+            // ------------------------------------------------ producer
+            for (int t = 0; t < ntiles; ++t, ++it) {
+                const int64_t rt = t0 + t;
+                const __nv_bfloat16* qsrc = p.planes + (rt * p.nkb + p.q_kb0 + j * chunks_per_head) * chunk_elems;
+                const __nv_bfloat16* vsrc = p.planes + (rt * p.nkb + p.v_kb0 + j * chunks_per_head) * chunk_elems;
+                mbar_wait(q_empty, (it & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(q_full, 2 * QV_PLANE);
+                    bulk_g2s(smem_u32(sQ), qsrc, QV_PLANE, q_full);
+                    bulk_g2s(smem_u32(sQ) + QV_PLANE, qsrc + p.plane_stride, QV_PLANE, q_full);
+                }
+                mbar_wait(v_empty, (it & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(v_full, 2 * QV_PLANE);
+                    bulk_g2s(smem_u32(sV), vsrc, QV_PLANE, v_full);
+                    bulk_g2s(smem_u32(sV) + QV_PLANE, vsrc + p.plane_stride, QV_PLANE, v_full);
+                }
+                __syncwarp();
+            }
+        } else if (warp == 1) {
+            // ------------------------------------------------ MMA issuer
+            const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                    ((uint32_t)(dk >> 3) << 17) | (8u << 24);
+            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP), aV = smem_u32(sV);
+            auto mma2 = [&](uint32_t itp, bool first) {
+                // O[mblk] (+)= P(t)^T V(t): A = P planes (MN-major, M = key), B = V planes (MN-major, N = dv)
+                mbar_wait(p_full, itp & 1);
+                mbar_wait(v_full, itp & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    for (int mb = 0; mb < mblocks; ++mb) {
+                        const uint32_t d_tmem = tmem_base + AT_O_COL + (uint32_t)(mb * dk);
+                        for (int ks = 0; ks < AT_TILE / 16; ++ks) {
+                            const uint32_t pa = aP + mb * (16 * 2048) + ks * 256, va = aV + ks * 256;
+                            const uint64_t p_hi = make_smem_desc(pa, 128, 2048), p_lo = make_smem_desc(pa + P_PLANE, 128, 2048);
+                            const uint64_t v_hi = make_smem_desc(va, 128, 2048), v_lo = make_smem_desc(va + QV_PLANE, 128, 2048);
+                            tc_mma_bf16(d_tmem, p_lo, v_hi, idesc2, (first && ks == 0) ? 0u : 1u);
+                            tc_mma_bf16(d_tmem, p_hi, v_lo, idesc2, 1u);
+                            tc_mma_bf16(d_tmem, p_hi, v_hi, idesc2, 1u);
+                        }
+                    }
+                    tc_commit(p_empty);
+                    tc_commit(v_empty);
+                }
+                __syncwarp();
+            };
+            for (int t = 0; t < ntiles; ++t, ++it) {
+                mbar_wait(q_full, it & 1);
+                mbar_wait(s_empty, (it & 1) ^ 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t qa = aQ + ks * 2 * 2048, ka = aK + ks * 2 * (KP * 16);
+                        const uint64_t q_hi = make_smem_desc(qa, 2048, 128), q_lo = make_smem_desc(qa + QV_PLANE, 2048, 128);
+                        const uint64_t k_hi = make_smem_desc(ka, KP * 16, 128), k_lo = make_smem_desc(ka + KP_PLANE, KP * 16, 128);
+                        tc_mma_bf16(tmem_base, q_lo, k_hi, idesc1, ks ? 1u : 0u);
+                        tc_mma_bf16(tmem_base, q_hi, k_lo, idesc1, 1u);
+                        tc_mma_bf16(tmem_base, q_hi, k_hi, idesc1, 1u);
+                    }
+                    tc_commit(q_empty);
+                    tc_commit(s_full);
+                }
+                __syncwarp();
+                if (t > 0) mma2(it - 1, t == 1);
+            }
+            if (ntiles > 0) mma2(it - 1, ntiles == 1);
+            if (lane == 0) tc_commit(o_full);
+            __syncwarp();
+        } else {
+            // ------------------------------------------------ softmax warps: thread = one query row of the tile
+            const int quad = warp & 3;
+            const int rr = quad * 32 + lane;
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+            const int nchunks = (KP + 31) / 32;
+            for (int t = 0; t < ntiles; ++t, ++it) {
+                const int64_t g = (t0 + t) * AT_TILE + rr;
+                const bool valid = g >= g_lo && g < g_hi;
+                const int n = (int)(g - g_lo);
+                mbar_wait(s_full, it & 1);
+                tc_fence_after();
+                float mx = -INFINITY;
+                for (int c = 0; c < nchunks; ++c) {
+                    float v[32];
+                    tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) mx = fmaxf(mx, v[e]);
+                }
+                if (!valid) mx = 0.f;                        // padding rows may hold anything, incl. NaN
+                const float mc = mx * p.c_log2;
+                float sum = 0.f;
+                for (int c = 0; c < nchunks; ++c) {
+                    float v[32];
+                    tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) sum += exp2f(fmaf(v[e], p.c_log2, -mc));
+                }
+                const float inv = valid ? 1.f / sum : 0.f;
+                if (p.stats_out && valid) {
+                    float* so = p.stats_out + (((int64_t)b * p.h + j) * p.N + n) * 2;
+                    so[0] = mx * (p.c_log2 * 0.69314718055994530942f);     // max of the scaled scores (natural units)
+                    so[1] = inv;
+                }
+                mbar_wait(p_empty, (it & 1) ^ 1);            // MMA of the previous tile has consumed P
+                for (int c = 0; c < nchunks; ++c) {
+                    float v[32];
+                    tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        v[e] = (valid && c * 32 + e < p.Ksel) ? exp2f(fmaf(v[e], p.c_log2, -mc)) * inv : 0.f;
+                    if (p.P_out && valid) {
+                        float* po = p.P_out + (((int64_t)b * p.h + j) * p.N + n) * p.Ksel + c * 32;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) po[e] = v[e];
+                    }
+                    if (p.drop_p > 0.f && valid) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const uint64_t idx = (((uint64_t)(b * p.h + j) * p.N + n) * p.Ksel + c * 32 + e);
+                            v[e] *= drop_keep_scale(p.seed, p.offset, idx, p.drop_p);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int kgp = c * 4 + u;
+                        if (kgp * 8 < KP) {
+                            bf16x8 hi, lo;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) split_bf16(v[u * 8 + e], hi.v[e], lo.v[e]);
+                            *reinterpret_cast<bf16x8*>(sP + (size_t)kgp * 2048 + rr * 16) = hi;
+                            *reinterpret_cast<bf16x8*>(sP + P_PLANE + (size_t)kgp * 2048 + rr * 16) = lo;
+                        }
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
+            }
+            // ---- item epilogue: O (TMEM lane = key) -> this split's partial
+            mbar_wait(o_full, item_no & 1);
+            tc_fence_after();
+            for (int mb = 0; mb < mblocks; ++mb) {
+                const int key = mb * 128 + rr;
+                for (int c = 0; c < dk / 32; ++c) {
+                    float v[32];
+                    tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * dk + c * 32), v);
+                    if (key < p.Ksel) {
+                        float* o = p.O_part + (((int64_t)split * p.B + b) * p.Ksel + key) * p.d + j * dk + c * 32;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            float4 w = ntiles > 0 ? make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            *reinterpret_cast<float4*>(o + e) = w;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+struct AttnTcPlan { int KP, splits, tiles_per_split, grid; size_t smem; bool ok; };
+
+static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d) {
+    AttnTcPlan pl{};
+    if (h <= 0 || d % h) return pl;
+    const int dk = (int)(d / h);
+    if (dk % 32 || dk > 128 || Ksel < 1 || Ksel > 256) return pl;
+    pl.KP = (int)((Ksel + 15) / 16 * 16);
+    pl.smem = (size_t)2 * pl.KP * 256 + (size_t)2 * pl.KP * dk * 2 + (size_t)4 * AT_TILE * dk * 2 + 128;
+    if (pl.smem > 227 * 1024) return pl;
+    // the second 128-key MMA block addresses 16 key groups from its base: must stay inside the CTA's window
+    if (pl.KP > 128 && (size_t)(16 + 16) * 2048 + (size_t)pl.KP * 256 > pl.smem) return pl;
+    const int64_t tiles = (N + AT_TILE - 1) / AT_TILE + 1;         // a bag may straddle one extra row tile
+    const int64_t target = (B * h >= 32 ? 4 : 2) * (int64_t)sm_count();
+    int64_t splits = (target + B * h - 1) / (B * h);
+    if (splits > tiles) splits = tiles;
+    if (splits < 1) splits = 1;
+    pl.tiles_per_split = (int)((tiles + splits - 1) / splits);
+    pl.splits = (int)((tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
+    const int64_t items = B * h * pl.splits;
+    pl.grid = (int)(items < sm_count() ? items : sm_count());
+    pl.ok = true;
+    return pl;
+}
+
+}  // namespace snuffy
+
+using namespace snuffy;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+// bytes of workspace for snuffy_sparse_attn_tc_fwd, or -1 when the shape is not served by the tensor-core kernel
+// (needs dk % 32 == 0, dk <= 128, Ksel <= 256 and the operand tiles to fit 227 KB) -> use snuffy_sparse_attn_fwd.
+int64_t snuffy_sparse_attn_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d) {
+    const AttnTcPlan pl = plan_attn_tc(B, N, Ksel, h, d);
+    if (!pl.ok) return -1;
+    return (int64_t)pl.splits * B * Ksel * d * 4 + 256;
+}
+
+// Same contract as snuffy_sparse_attn_fwd, but Q and V arrive as the split-bf16 planes the Q|V projection wrote
+// (planes over [B*N, ldk] columns, Q at column q_col0, V at column v_col0; ldk, q_col0, v_col0 multiples of 32).
+int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,
+                              const float* Kp, int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d,
+                              float dropout_p, uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
+                              void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+    SNUFFY_REQUIRE(qv_planes && Kp && O && workspace, "snuffy_sparse_attn_tc_fwd: null pointer");
+    const AttnTcPlan pl = plan_attn_tc(B, N, Ksel, h, d);
+    SNUFFY_REQUIRE(pl.ok, "snuffy_sparse_attn_tc_fwd: unsupported shape (h=%lld d=%lld Ksel=%lld)", (long long)h,
+                   (long long)d, (long long)Ksel);
+    SNUFFY_REQUIRE(ldk % 32 == 0 && q_col0 % 32 == 0 && v_col0 % 32 == 0 && q_col0 + d <= ldk && v_col0 + d <= ldk,
+                   "snuffy_sparse_attn_tc_fwd: Q/V column ranges must be 32-aligned inside the planes");
+    SNUFFY_REQUIRE(workspace_bytes >= snuffy_sparse_attn_tc_workspace(B, N, Ksel, h, d),
+                   "snuffy_sparse_attn_tc_fwd: workspace too small");
+    SNUFFY_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "snuffy_sparse_attn_tc_fwd: dropout_p out of range");
+    SNUFFY_REQUIRE((uintptr_t)Kp % 16 == 0 && (uintptr_t)O % 16 == 0 && (uintptr_t)qv_planes % 16 == 0 && d % 4 == 0,
+                   "snuffy_sparse_attn_tc_fwd: pointers must be 16-byte aligned");
+    AttnTcParams p{};
+    p.planes = reinterpret_cast<const __nv_bfloat16*>(qv_planes); p.plane_stride = plane_stride;
+    p.nkb = (int)(ldk / 32); p.q_kb0 = (int)(q_col0 / 32); p.v_kb0 = (int)(v_col0 / 32);
+    p.Kp = Kp; p.B = (int)B; p.N = (int)N; p.Ksel = (int)Ksel; p.KP = pl.KP; p.h = (int)h; p.dk = (int)(d / h); p.d = (int)d;
+    p.splits = pl.splits; p.tiles_per_split = pl.tiles_per_split;
+    p.c_log2 = (float)(1.4426950408889634 / sqrt((double)p.dk));
+    p.O_part = reinterpret_cast<float*>(workspace);
+    p.P_out = P_out; p.stats_out = stats_out;
+    p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
+    SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    attn_tc_kernel<<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
+    launch_fold_partials(p.O_part, pl.splits, B * Ksel * d / 4, O, stream);
+    return check_launch("snuffy_sparse_attn_tc_fwd", 2);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -25,6 +25,8 @@ from . import ops
 from .ops import Planes
 
 PRECISIONS = ("bf16x3", "fp32", "bf16x1")
+#: use the tcgen05 attention kernel when the shape allows (SNUFFY_B200_ATTN=simt forces the fp32 SIMT kernel)
+ATTN_TC = os.environ.get("SNUFFY_B200_ATTN", "tc") != "simt"
 
 
 def default_precision() -> str:
@@ -202,19 +204,27 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     row_map = ops.build_row_map(sel, N)
 
     # --- attention sub-layer: u = LN1(x); Q,V over all N rows; keys from the raw selected rows
+    attn_tc = False
     if precision == "fp32":
         u, _, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_f32=True, want_stats=save)
         qv = ops.gemm_f32(u, w.wqv, M=rows, N=2 * d, K=d, bias=w.bqv)
     else:
         _, up, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_planes=True, want_stats=save)
-        qv, _, _ = ops.gemm_tc(up, w.wqv_planes, M=rows, N=2 * d, K=d, passes=passes, bias=w.bqv)
+        attn_tc = ATTN_TC and ops.sparse_attn_tc_supported(B, N, Ksel, heads, d)
+        # the projection writes Q|V straight as the planes the tensor-core attention consumes (fp32 only if saved)
+        qv, _, qvp = ops.gemm_tc(up, w.wqv_planes, M=rows, N=2 * d, K=d, passes=passes, bias=w.bqv,
+                                 want_out=save or not attn_tc, want_planes=attn_tc)
     kp = ops.linear_f32(xs, w.wk, w.bk)
     drop = (0.0, 0, 0)
     if attn_dropout > 0.0:
         seed, offset = _RANDOM.next()
         drop = (attn_dropout, seed, offset)
-    o, probs, attn_stats = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, N, Ksel, heads, want_probs=want_probs,
-                                           want_stats=save, dropout_p=drop[0], seed=drop[1], offset=drop[2])
+    if attn_tc:
+        o, probs, attn_stats = ops.sparse_attn_tc(qvp, kp, B, N, Ksel, heads, d, want_probs=want_probs, want_stats=save,
+                                                  dropout_p=drop[0], seed=drop[1], offset=drop[2])
+    else:
+        o, probs, attn_stats = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, N, Ksel, heads, want_probs=want_probs,
+                                               want_stats=save, dropout_p=drop[0], seed=drop[1], offset=drop[2])
     xs_new = ops.linear_f32(o, w.wo, w.bo, resid=xs)                         # X_S' = X_S + W3 O + b3
 
     # --- feed-forward sub-layer over y = x with rows S replaced by X_S' (read through row_map)

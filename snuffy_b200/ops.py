@@ -237,6 +237,29 @@ def sparse_attn(q: torch.Tensor, v: torch.Tensor, kp: torch.Tensor, B: int, N: i
     return o, probs, stats
 
 
+def sparse_attn_tc_supported(B: int, N: int, Ksel: int, h: int, d: int) -> bool:
+    return d % 32 == 0 and lib.snuffy_sparse_attn_tc_workspace(B, N, Ksel, h, d) >= 0
+
+
+def sparse_attn_tc(qv_planes: Planes, kp: torch.Tensor, B: int, N: int, Ksel: int, h: int, d: int, *,
+                   want_probs: bool = True, want_stats: bool = False, dropout_p: float = 0.0, seed: int = 0,
+                   offset: int = 0):
+    """Tensor-core sparse attention on the Q|V planes written by the projection GEMM (planes over [B*N, 2d])."""
+    kp = _f32(kp, "kp")
+    dev = kp.device
+    ws_bytes = lib.snuffy_sparse_attn_tc_workspace(B, N, Ksel, h, d)
+    if ws_bytes < 0:
+        raise ValueError("shape not served by the tensor-core attention kernel")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    o = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
+    probs = torch.empty(B, h, N, Ksel, dtype=torch.float32, device=dev) if want_probs else None
+    stats = torch.empty(B, h, N, 2, dtype=torch.float32, device=dev) if want_stats else None
+    check(lib.snuffy_sparse_attn_tc_fwd(qv_planes.ptr, qv_planes.stride, qv_planes.K, 0, d, kp.data_ptr(), B, N, Ksel, h, d,
+                                        float(dropout_p), seed & _U64, offset & _U64, o.data_ptr(), _ptr(probs),
+                                        _ptr(stats), ws.data_ptr(), ws_bytes, _stream()), "snuffy_sparse_attn_tc_fwd")
+    return o, probs, stats
+
+
 # ------------------------------------------------------------------ a15: DSMIL pooling
 def dsmil_pool(q: torch.Tensor, q_max: torch.Tensor, v: torch.Tensor, w_fcc: torch.Tensor, b_fcc):
     """A[N,C], Bm[C,d], logits[C] (dsmil.py:83-91)."""

@@ -274,3 +274,51 @@ def test_dsmil_pool(ops):
     assert np.abs(a.cpu().numpy() - ra).max() < 1e-7
     assert np.abs(bm.cpu().numpy() - rb).max() < 1e-5
     assert np.abs(logits.cpu().numpy() - rl).max() < 1e-5
+
+
+# ------------------------------------------------------------------ a9 on the tensor cores (csrc/attn_tc.cu)
+@pytest.mark.parametrize("B,n,ks,h,d", [
+    (1, 1000, 200, 8, 512),     # cfg2 head shape (dk = 64, two 128-key MMA blocks)
+    (1, 128, 16, 1, 64),        # one tile, one head, minimal keys
+    (2, 333, 24, 4, 128),       # dk = 32, bags straddle row tiles
+    (3, 200, 100, 2, 128),      # dk = 64, three bags inside two tiles
+    (1, 700, 208, 8, 512),      # largest key count served at dk = 64
+    (1, 10000, 200, 8, 512),    # full cfg2 bag
+])
+def test_sparse_attention_tensor_core(ops, B, n, ks, h, d):
+    assert ops.sparse_attn_tc_supported(B, n, ks, h, d)
+    rs = np.random.RandomState(n + ks + B)
+    q = rs.standard_normal((B, n, d)).astype(np.float32)
+    v = rs.standard_normal((B, n, d)).astype(np.float32)
+    kp = rs.standard_normal((B, ks, d)).astype(np.float32)
+    qv = dev(np.concatenate([q, v], axis=-1).reshape(B * n, 2 * d))
+    _, planes, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    o, p, st = ops.sparse_attn_tc(planes, dev(kp.reshape(B * ks, d)), B, n, ks, h, d, want_probs=True, want_stats=True)
+    o2, p2, st2 = ops.sparse_attn(qv[:, :d], qv[:, d:], dev(kp.reshape(B * ks, d)), B, n, ks, h, want_probs=True,
+                                  want_stats=True)
+    o, p = o.cpu().numpy().reshape(B, ks, d), p.cpu().numpy()
+    for b in range(B if n <= 1000 else 0):
+        ro, rp = so.sparse_attention(q[b].astype(np.float64), kp[b].astype(np.float64), v[b].astype(np.float64), h)
+        assert np.abs(p[b] - rp).max() < 2e-5, np.abs(p[b] - rp).max()
+        assert np.abs(o[b] - ro).max() < 3e-5 * max(1.0, np.abs(ro).max()), np.abs(o[b] - ro).max()
+    # against the fp32 SIMT kernel (also covers the 10000-row case the numpy oracle is slow on)
+    assert (torch.from_numpy(p).cuda() - p2).abs().max() < 2e-5
+    assert (torch.from_numpy(o).cuda().view(B * ks, d) - o2).abs().max() < 3e-5 * max(1.0, o2.abs().max().item())
+    assert (st[..., 1] / st2[..., 1] - 1).abs().max() < 1e-4 and (st[..., 0] - st2[..., 0]).abs().max() < 1e-3
+
+
+def test_sparse_attention_tensor_core_dropout_matches_simt(ops):
+    B, n, ks, h, d = 1, 500, 64, 4, 256
+    rs = np.random.RandomState(1)
+    qv = dev(rs.standard_normal((n, 2 * d)).astype(np.float32))
+    kp = dev(rs.standard_normal((ks, d)).astype(np.float32))
+    _, planes, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    o1, _, _ = ops.sparse_attn_tc(planes, kp, B, n, ks, h, d, want_probs=False, dropout_p=0.3, seed=11, offset=4)
+    o2, _, _ = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, n, ks, h, want_probs=False, dropout_p=0.3, seed=11, offset=4)
+    assert (o1 - o2).abs().max() < 3e-5 * max(1.0, o2.abs().max().item())     # same counter-based mask in both kernels
+
+
+def test_sparse_attention_tensor_core_unsupported_shapes(ops):
+    assert not ops.sparse_attn_tc_supported(1, 256, 32, 1, 384)      # dk = 384
+    assert not ops.sparse_attn_tc_supported(1, 600, 392, 8, 768)     # dk = 96 with 392 keys does not fit
+    assert not ops.sparse_attn_tc_supported(1, 500, 256, 8, 512)     # 256 keys at dk = 64 exceed 227 KB
