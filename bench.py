@@ -178,18 +178,35 @@ def kernel_rooflines(model, batch, peaks, device):
     res.append(dict(kernel="gemm_tc FFN-down (+bias +residual)", bound="tensor", achieved=flops / t / 1e12,
                     peak=peaks["tf_burst"], unit="TFLOP/s", frac=flops / t / 1e12 / peaks["tf_burst"], traffic=None,
                     launch_ms=t * 1e3, passes=3))
-    qvs = [ops.gemm_tc(p, w.wqv_planes, M=rows, N=2 * d, K=d, passes=3, bias=w.bqv)[0] for p in planes]
+    def qv_proj():
+        it[0] ^= 1
+        ops.gemm_tc(planes[it[0]], w.wqv_planes, M=rows, N=2 * d, K=d, passes=3, bias=w.bqv, want_out=False, want_planes=True)
+    t = cuda_time(qv_proj, 10)
+    fl = 2.0 * rows * 2 * d * d
+    res.append(dict(kernel="gemm_tc Q|V projection (planes out)", bound="tensor", achieved=fl / t / 1e12,
+                    peak=peaks["tf_burst"], unit="TFLOP/s", frac=fl / t / 1e12 / peaks["tf_burst"], traffic=None,
+                    launch_ms=t * 1e3, passes=3))
+    qvp = [ops.gemm_tc(p, w.wqv_planes, M=rows, N=2 * d, K=d, passes=3, bias=w.bqv, want_out=False, want_planes=True)[2]
+           for p in planes]
     kp = torch.randn(batch * ks, d, device=device, generator=g)
 
     def attn():
         it[0] ^= 1
-        q = qvs[it[0]]
-        ops.sparse_attn(q[:, :d], q[:, d:], kp, batch, n, ks, h, want_probs=False)
+        ops.sparse_attn_tc(qvp[it[0]], kp, batch, n, ks, h, d, want_probs=False)
     t = cuda_time(attn, 10)
     byts = batch * (2.0 * n * d * 4 + 2.0 * ks * d * 4)
-    res.append(dict(kernel="sparse_attn (QK^T -> softmax -> P^T V, A not materialised)", bound="hbm",
+    res.append(dict(kernel="attn_tc (QK^T -> softmax -> P^T V on tcgen05, A not materialised) + fold", bound="hbm",
                     achieved=byts / t / 1e9, peak=peaks["hbm"], unit="GB/s", frac=byts / t / 1e9 / peaks["hbm"], traffic=None,
-                    launch_ms=t * 1e3, algorithmic_bytes_per_launch=byts))
+                    launch_ms=t * 1e3, algorithmic_bytes_per_launch=byts,
+                    useful_tflops=batch * 4.0 * n * ks * d / t / 1e12))
+    xs_sel = torch.randn(batch * ks, d, device=device, generator=g)
+
+    def small_proj():
+        ops.linear_f32(xs_sel, w.wk, w.bk)
+    t = cuda_time(small_proj, 10)
+    res.append(dict(kernel="gemm_simt key / output projection [B*Ksel, d] x [d, d]", bound="tensor",
+                    achieved=2.0 * batch * ks * d * d / t / 1e12, peak=peaks["tf_burst"], unit="TFLOP/s",
+                    frac=2.0 * batch * ks * d * d / t / 1e12 / peaks["tf_burst"], traffic=None, launch_ms=t * 1e3))
     wi = model.i_classifier.fc[0]
 
     def sc():

@@ -17,7 +17,7 @@
 // Work item = (bag, head, row-tile range).  Per 128-query tile:
 //   warp 0   bulk-copy producer: Q tile, V tile (single buffers, re-armed by tcgen05.commit)
 //   warp 1   MMA issuer:  S(t) = Q Kp^T  -> TMEM[0, KP);  O += P(t-1)^T V(t-1) -> TMEM[256, 256 + 2*dk)
-//   warps 2-5  one query row per thread: three passes over the TMEM row (max, sum, normalise), P -> smem,
+//   warps 2-9  one query row per thread (two warps per TMEM lane quadrant split the keys): three passes over the TMEM row (max, sum, normalise), P -> smem,
 //            at the end of the item O -> registers -> per-split partial (folded by fold_partials_kernel).
 #include "tc_ptx.cuh"
 
@@ -25,9 +25,15 @@ namespace snuffy {
 
 void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream);
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;          // producer + MMA issuer + 8 softmax warps
 constexpr int AT_TILE = 128;            // queries per tile (UMMA M)
 constexpr uint32_t AT_O_COL = 256;      // TMEM column of the O accumulators
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct AttnTcParams {
     const __nv_bfloat16* planes; int64_t plane_stride;   // Q|V planes over [rows, ldk], A layout, RC = 128
@@ -57,6 +63,7 @@ attn_tc_kernel(const AttnTcParams p) {
     unsigned char* sV = sQ + 2 * QV_PLANE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * QV_PLANE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* sRed = reinterpret_cast<float*>(bars + 10);       // [2 tile parities][max | sum][2 halves][128 rows]
     const uint32_t b0 = smem_u32(bars);
     const uint32_t q_full = b0, q_empty = b0 + 8, v_full = b0 + 16, v_empty = b0 + 24, s_full = b0 + 32,
                    s_empty = b0 + 40, p_full = b0 + 48, p_empty = b0 + 56, o_full = b0 + 64;
@@ -64,7 +71,7 @@ attn_tc_kernel(const AttnTcParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+        mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(p_empty, 1); mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -191,11 +198,14 @@ attn_tc_kernel(const AttnTcParams p) {
             if (lane == 0) tc_commit(o_full);
             __syncwarp();
         } else {
-            // ------------------------------------------------ softmax warps: thread = one query row of the tile
-            const int quad = warp & 3;
+            // ------------------------------------------------ softmax warps.  Thread = one query row of the tile;
+            // the two warps of a TMEM lane quadrant split the key chunks and exchange (max, sum) through smem.
+            const int quad = warp & 3, half = (warp - 2) >> 2;
             const int rr = quad * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
             const int nchunks = (KP + 31) / 32;
+            const int c_lo = half ? (nchunks + 1) / 2 : 0, c_hi = half ? nchunks : (nchunks + 1) / 2;
+            const uint32_t bar_id = 1 + quad;                       // named barrier of this quadrant's warp pair
             for (int t = 0; t < ntiles; ++t, ++it) {
                 const int64_t g = (t0 + t) * AT_TILE + rr;
                 const bool valid = g >= g_lo && g < g_hi;
@@ -203,34 +213,53 @@ attn_tc_kernel(const AttnTcParams p) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
                 float mx = -INFINITY;
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+                    if (c * 32 + 32 <= p.Ksel) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) mx = fmaxf(mx, v[e]);
+                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, v[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) mx = fmaxf(mx, v[e]);
+                    }
                 }
+                sRed[(it & 1) * 512 + half * 128 + rr] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                mx = fmaxf(mx, sRed[(it & 1) * 512 + (half ^ 1) * 128 + rr]);
                 if (!valid) mx = 0.f;                        // padding rows may hold anything, incl. NaN
                 const float mc = mx * p.c_log2;
                 float sum = 0.f;
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+                    if (c * 32 + 32 <= p.Ksel) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) sum += exp2f(fmaf(v[e], p.c_log2, -mc));
+                        for (int e = 0; e < 32; ++e) sum += ex2_approx(fmaf(v[e], p.c_log2, -mc));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) sum += ex2_approx(fmaf(v[e], p.c_log2, -mc));
+                    }
                 }
+                sRed[(it & 1) * 512 + 256 + half * 128 + rr] = sum;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                sum += sRed[(it & 1) * 512 + 256 + (half ^ 1) * 128 + rr];
                 const float inv = valid ? 1.f / sum : 0.f;
-                if (p.stats_out && valid) {
+                if (p.stats_out && valid && half == 0) {
                     float* so = p.stats_out + (((int64_t)b * p.h + j) * p.N + n) * 2;
                     so[0] = mx * (p.c_log2 * 0.69314718055994530942f);     // max of the scaled scores (natural units)
                     so[1] = inv;
                 }
                 mbar_wait(p_empty, (it & 1) ^ 1);            // MMA of the previous tile has consumed P
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+                    const bool full = c * 32 + 32 <= p.Ksel;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        v[e] = (valid && c * 32 + e < p.Ksel) ? exp2f(fmaf(v[e], p.c_log2, -mc)) * inv : 0.f;
+                    for (int e = 0; e < 32; ++e) {
+                        const float pe = ex2_approx(fmaf(v[e], p.c_log2, -mc)) * inv;
+                        v[e] = (full || c * 32 + e < p.Ksel) ? pe : 0.f;
+                    }
                     if (p.P_out && valid) {
                         float* po = p.P_out + (((int64_t)b * p.h + j) * p.N + n) * p.Ksel + c * 32;
 #pragma unroll
@@ -247,11 +276,18 @@ attn_tc_kernel(const AttnTcParams p) {
                     for (int u = 0; u < 4; ++u) {
                         const int kgp = c * 4 + u;
                         if (kgp * 8 < KP) {
-                            bf16x8 hi, lo;
+                            // hi = truncated bf16 (exact), lo = bf16 of the exact remainder: integer/FMA pipes only
+                            uint32_t hw[4], lw[4];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) split_bf16(v[u * 8 + e], hi.v[e], lo.v[e]);
-                            *reinterpret_cast<bf16x8*>(sP + (size_t)kgp * 2048 + rr * 16) = hi;
-                            *reinterpret_cast<bf16x8*>(sP + P_PLANE + (size_t)kgp * 2048 + rr * 16) = lo;
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t ua = __float_as_uint(v[u * 8 + 2 * q]), ub = __float_as_uint(v[u * 8 + 2 * q + 1]);
+                                const float la = v[u * 8 + 2 * q] - __uint_as_float(ua & 0xFFFF0000u);
+                                const float lb = v[u * 8 + 2 * q + 1] - __uint_as_float(ub & 0xFFFF0000u);
+                                hw[q] = __byte_perm(ua, ub, 0x7632);
+                                lw[q] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+                            }
+                            *reinterpret_cast<uint4*>(sP + (size_t)kgp * 2048 + rr * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4*>(sP + P_PLANE + (size_t)kgp * 2048 + rr * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                         }
                     }
                 }
@@ -260,10 +296,10 @@ attn_tc_kernel(const AttnTcParams p) {
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
             }
-            // ---- item epilogue: O (TMEM lane = key) -> this split's partial
+            // ---- item epilogue: O (TMEM lane = key) -> this split's partial; each half takes one 128-key block
             mbar_wait(o_full, item_no & 1);
             tc_fence_after();
-            for (int mb = 0; mb < mblocks; ++mb) {
+            for (int mb = half; mb < mblocks; mb += 2) {
                 const int key = mb * 128 + rr;
                 for (int c = 0; c < dk / 32; ++c) {
                     float v[32];
@@ -297,7 +333,7 @@ static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, in
     const int dk = (int)(d / h);
     if (dk % 32 || dk > 128 || Ksel < 1 || Ksel > 256) return pl;
     pl.KP = (int)((Ksel + 15) / 16 * 16);
-    pl.smem = (size_t)2 * pl.KP * 256 + (size_t)2 * pl.KP * dk * 2 + (size_t)4 * AT_TILE * dk * 2 + 128;
+    pl.smem = (size_t)2 * pl.KP * 256 + (size_t)2 * pl.KP * dk * 2 + (size_t)4 * AT_TILE * dk * 2 + 128 + 4096;
     if (pl.smem > 227 * 1024) return pl;
     // the second 128-key MMA block addresses 16 key groups from its base: must stay inside the CTA's window
     if (pl.KP > 128 && (size_t)(16 + 16) * 2048 + (size_t)pl.KP * 256 > pl.smem) return pl;

@@ -151,6 +151,8 @@ class LayerWeights:
     wqv_planes: Optional[Planes] = None
     w1_planes: Optional[Planes] = None
     w2_planes: Optional[Planes] = None
+    wk_planes: Optional[Planes] = None
+    wo_planes: Optional[Planes] = None
 
     def prepare(self, precision: str) -> None:
         if self.wqv is None:
@@ -161,6 +163,8 @@ class LayerWeights:
             self.wqv_planes = ops.weight_planes(self.wqv)
             self.w1_planes = ops.weight_planes(self.w1.detach())
             self.w2_planes = ops.weight_planes(self.w2.detach())
+            self.wk_planes = ops.weight_planes(self.wk.detach())
+            self.wo_planes = ops.weight_planes(self.wo.detach())
 
 
 @dataclass
@@ -214,7 +218,12 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         # the projection writes Q|V straight as the planes the tensor-core attention consumes (fp32 only if saved)
         qv, _, qvp = ops.gemm_tc(up, w.wqv_planes, M=rows, N=2 * d, K=d, passes=passes, bias=w.bqv,
                                  want_out=save or not attn_tc, want_planes=attn_tc)
-    kp = ops.linear_f32(xs, w.wk, w.bk)
+    small_tc = precision != "fp32" and B * Ksel >= 256          # [B*Ksel, d] projections: tensor cores once they fill tiles
+    if small_tc:
+        _, xsp, _ = ops.ln_rows(xs, None, None, apply_ln=False, want_planes=True)
+        kp, _, _ = ops.gemm_tc(xsp, w.wk_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bk)
+    else:
+        kp = ops.linear_f32(xs, w.wk, w.bk)
     drop = (0.0, 0, 0)
     if attn_dropout > 0.0:
         seed, offset = _RANDOM.next()
@@ -225,7 +234,11 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     else:
         o, probs, attn_stats = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, N, Ksel, heads, want_probs=want_probs,
                                                want_stats=save, dropout_p=drop[0], seed=drop[1], offset=drop[2])
-    xs_new = ops.linear_f32(o, w.wo, w.bo, resid=xs)                         # X_S' = X_S + W3 O + b3
+    if small_tc:                                                             # X_S' = X_S + W3 O + b3
+        _, opl, _ = ops.ln_rows(o, None, None, apply_ln=False, want_planes=True)
+        xs_new, _, _ = ops.gemm_tc(opl, w.wo_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bo, resid=xs)
+    else:
+        xs_new = ops.linear_f32(o, w.wo, w.bo, resid=xs)
 
     # --- feed-forward sub-layer over y = x with rows S replaced by X_S' (read through row_map)
     h_pre = None
