@@ -233,14 +233,17 @@ attn_tc_kernel(const AttnTcParams p) {
                 for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tc_ld32(lane_addr + (uint32_t)(c * 32), v);
-                    if (c * 32 + 32 <= p.Ksel) {
+                    // exp is evaluated ONCE per score (the XU pipe is the kernel's limiter) and parked in TMEM over S
+                    const bool full = c * 32 + 32 <= p.Ksel;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) sum += ex2_approx(fmaf(v[e], p.c_log2, -mc));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) sum += ex2_approx(fmaf(v[e], p.c_log2, -mc));
+                    for (int e = 0; e < 32; ++e) {
+                        const float ee = ex2_approx(fmaf(v[e], p.c_log2, -mc));
+                        v[e] = (full || c * 32 + e < p.Ksel) ? ee : 0.f;
+                        sum += v[e];
                     }
+                    tc_st32(lane_addr + (uint32_t)(c * 32), v);
                 }
+                tc_wait_st();
                 sRed[(it & 1) * 512 + 256 + half * 128 + rr] = sum;
                 asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
                 sum += sRed[(it & 1) * 512 + 256 + (half ^ 1) * 128 + rr];
@@ -254,12 +257,8 @@ attn_tc_kernel(const AttnTcParams p) {
                 for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tc_ld32(lane_addr + (uint32_t)(c * 32), v);
-                    const bool full = c * 32 + 32 <= p.Ksel;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float pe = ex2_approx(fmaf(v[e], p.c_log2, -mc)) * inv;
-                        v[e] = (full || c * 32 + e < p.Ksel) ? pe : 0.f;
-                    }
+                    for (int e = 0; e < 32; ++e) v[e] *= inv;           // exp(s - max) parked by the sum pass
                     if (p.P_out && valid) {
                         float* po = p.P_out + (((int64_t)b * p.h + j) * p.N + n) * p.Ksel + c * 32;
 #pragma unroll

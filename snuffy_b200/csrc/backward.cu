@@ -1,0 +1,286 @@
+// Backward kernels of the aggregator that are not plain contractions (train.py:259 `loss.backward()` runs through
+// the drop-in modules; the contractions themselves go through snuffy_gemm_f32 / snuffy_gemm_f32_batched):
+//   ln_rows_bwd        LayerNorm backward (snuffy.py:107,110,86) incl. dgamma / dbeta, optional residual-gradient add,
+//                      optional broadcast upstream gradient (the mean-pool of snuffy.py:71 sends the same row to all N)
+//   act_bwd            dh = da * dropout_mask * act'(h_pre), a = dropout(act(h_pre))   (snuffy.py:216-225)
+//   colsum             out[c, :] = sum_rows w[row, c] * X[row, :]   (bias grads, instance-classifier grad)
+//   softmax recompute / dS   the row-local pieces of the attention backward (snuffy.py:160-168)
+//   scatter_add_rows   dx[S] += dxs  (backward of the raw-row gather snuffy.py:131,145-147)
+#include "common.cuh"
+
+namespace snuffy {
+
+void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream);
+
+
+// ------------------------------------------------------------------ LayerNorm backward
+// warp per row; per-warp dgamma/dbeta accumulators in shared memory (fixed summation order -> deterministic);
+// each CTA writes one partial [2][d] that fold_partials sums.
+__global__ void __launch_bounds__(256)
+ln_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy_bcast, int64_t rows_per_bag, float bscale,
+                   const float* __restrict__ x, const int32_t* __restrict__ row_map, const float* __restrict__ alt,
+                   const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ add,
+                   int64_t rows, int d, float* __restrict__ dx, float* __restrict__ partials) {
+    extern __shared__ __align__(16) float lb_smem[];        // [warps][2][d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float* accg = lb_smem + (size_t)warp * 2 * d;
+    float* accb = accg + d;
+    for (int e = lane; e < d; e += 32) { accg[e] = 0.f; accb[e] = 0.f; }
+    __syncwarp();
+    const float inv_d = 1.f / (float)d;
+    for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += (int64_t)gridDim.x * nwarps) {
+        const float* src = x + row * (int64_t)d;
+        if (row_map) { const int32_t slot = row_map[row]; if (slot >= 0) src = alt + (int64_t)slot * d; }
+        const float* g = dy ? dy + row * (int64_t)d : dy_bcast + (row / rows_per_bag) * (int64_t)d;
+        const float gs = dy ? 1.f : bscale;
+        const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+        float s1 = 0.f, s2 = 0.f;
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(src + e));
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(g + e));
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + e));
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gg[4] = {gv.x * gs, gv.y * gs, gv.z * gs, gv.w * gs};
+            const float gm[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float z = (xs[j] - mean) * rstd, t = gg[j] * gm[j];
+                s1 += t; s2 = fmaf(t, z, s2);
+                accg[e + j] = fmaf(gg[j], z, accg[e + j]);
+                accb[e + j] += gg[j];
+            }
+        }
+        s1 = warp_sum(s1) * inv_d; s2 = warp_sum(s2) * inv_d;
+        if (dx) {
+            for (int e = lane * 4; e < d; e += 128) {
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(src + e));
+                const float4 gv = __ldg(reinterpret_cast<const float4*>(g + e));
+                const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + e));
+                float4 o;
+                o.x = rstd * (gv.x * gs * ga.x - s1 - (xv.x - mean) * rstd * s2);
+                o.y = rstd * (gv.y * gs * ga.y - s1 - (xv.y - mean) * rstd * s2);
+                o.z = rstd * (gv.z * gs * ga.z - s1 - (xv.z - mean) * rstd * s2);
+                o.w = rstd * (gv.w * gs * ga.w - s1 - (xv.w - mean) * rstd * s2);
+                if (add) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(add + row * (int64_t)d + e));
+                    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                }
+                *reinterpret_cast<float4*>(dx + row * (int64_t)d + e) = o;
+            }
+        }
+    }
+    __syncthreads();
+    float* part = partials + (int64_t)blockIdx.x * 2 * d;
+    for (int e = threadIdx.x; e < 2 * d; e += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarps; ++w) s += lb_smem[(size_t)w * 2 * d + e];
+        part[e] = s;
+    }
+}
+
+// ------------------------------------------------------------------ activation / dropout backward (elementwise)
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float* __restrict__ hpre, const float* __restrict__ da, int act, float drop_p, uint64_t seed,
+               uint64_t offset, int64_t total4, float* __restrict__ dh, float* __restrict__ a_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        float h[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (hpre) { const float4 v = __ldg(reinterpret_cast<const float4*>(hpre) + i); h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w; }
+        if (da) { const float4 v = __ldg(reinterpret_cast<const float4*>(da) + i); g[0] = v.x; g[1] = v.y; g[2] = v.z; g[3] = v.w; }
+        float od[4], oa[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float m = drop_p > 0.f ? drop_keep_scale(seed, offset, (uint64_t)(i * 4 + j), drop_p) : 1.f;
+            od[j] = g[j] * m * (hpre ? act_grad(act, h[j]) : 1.f);
+            oa[j] = (hpre ? act_apply(act, h[j]) : 0.f) * m;
+        }
+        if (dh) reinterpret_cast<float4*>(dh)[i] = make_float4(od[0], od[1], od[2], od[3]);
+        if (a_out) reinterpret_cast<float4*>(a_out)[i] = make_float4(oa[0], oa[1], oa[2], oa[3]);
+    }
+}
+
+// ------------------------------------------------------------------ weighted column sums
+// partial[chunk][c][e] = sum_{rows in chunk} w[row*C + c] * X[row*ldx + e]   (w == null -> weight 1, C = 1)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, int64_t rows, int d, int C,
+              int64_t rows_per_chunk, float* __restrict__ partials) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+    for (int c = 0; c < C; ++c) {
+        for (int e0 = 0; e0 < d; e0 += 32) {
+            const int e = e0 + lane;
+            float acc = 0.f;
+            if (e < d)
+                for (int64_t r = r0 + warp; r < r1; r += 8) acc = fmaf(w ? __ldg(w + r * C + c) : 1.f, __ldg(X + r * ldx + e), acc);
+            red[warp][lane] = acc;
+            __syncthreads();
+            if (warp == 0 && e < d) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s += red[k][lane];
+                partials[((int64_t)blockIdx.x * C + c) * d + e] = s;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fold_scalar_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += __ldcg(part + (int64_t)s * n + i);
+    out[i] = acc;
+}
+
+// ------------------------------------------------------------------ attention backward, row-local pieces
+// S holds the scaled scores Q Kp^T / sqrt(dk) of every (bag, head): [B*h*N, Ksel] rows; stats [B*h*N, 2] = (max, 1/sum).
+//   mode 0:  Pd[r, k] = exp(S - max) / sum * dropout_mask            (P~, the operand of dV = P~ dO)
+//   mode 1:  G[r, k] <- (P~ G - P * sum_k(P~ G)) / sqrt(dk)          with G = V dO^T on entry: dS on exit
+// warp per row.
+__global__ void __launch_bounds__(256)
+attn_rows_bwd_kernel(const float* __restrict__ S, const float* __restrict__ stats, int64_t nrows, int Ksel, int64_t N,
+                     int mode, float inv_scale, float drop_p, uint64_t seed, uint64_t offset, float* __restrict__ Pd,
+                     float* __restrict__ G) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const float m = stats[row * 2], inv = stats[row * 2 + 1];
+    const float* s = S + row * (int64_t)Ksel;
+    // dropout index of element (b, j, n, key) = ((b*h + j)*N + n)*Ksel + key = row*Ksel + key  (matches the forward)
+    const uint64_t base = (uint64_t)row * (uint64_t)Ksel;
+    if (mode == 0) {
+        for (int k = lane; k < Ksel; k += 32) {
+            float p = expf(s[k] - m) * inv;
+            if (drop_p > 0.f) p *= drop_keep_scale(seed, offset, base + k, drop_p);
+            Pd[row * (int64_t)Ksel + k] = p;
+        }
+        return;
+    }
+    float* g = G + row * (int64_t)Ksel;
+    float delta = 0.f;
+    for (int k = lane; k < Ksel; k += 32) {
+        float p = expf(s[k] - m) * inv;
+        if (drop_p > 0.f) p *= drop_keep_scale(seed, offset, base + k, drop_p);
+        delta = fmaf(p, g[k], delta);
+    }
+    delta = warp_sum(delta);
+    for (int k = lane; k < Ksel; k += 32) {
+        const float p = expf(s[k] - m) * inv;
+        const float mk = drop_p > 0.f ? drop_keep_scale(seed, offset, base + k, drop_p) : 1.f;
+        g[k] = p * (mk * g[k] - delta) * inv_scale;
+    }
+}
+
+// ------------------------------------------------------------------ dx[b, idx[b,k], :] += src[b*K + k, :]
+__global__ void __launch_bounds__(128)
+scatter_add_rows_kernel(float* __restrict__ dx, const int64_t* __restrict__ idx, const float* __restrict__ src, int64_t N,
+                        int64_t K, int d) {
+    const int64_t slot = blockIdx.x;
+    const int64_t b = slot / K;
+    const int64_t r = idx[slot];
+    if (r < 0 || r >= N) return;
+    float* dst = dx + (b * N + r) * (int64_t)d;
+    const float* s = src + slot * (int64_t)d;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) dst[e] += s[e];
+}
+
+}  // namespace snuffy
+
+using namespace snuffy;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+// CTAs (= partial rows) snuffy_ln_rows_bwd uses; partials needs blocks * 2 * d floats
+int64_t snuffy_ln_rows_bwd_blocks(int64_t rows) {
+    int64_t b = (rows + 7) / 8;
+    const int64_t cap = 4 * (int64_t)sm_count();
+    if (b > cap) b = cap;
+    return b < 1 ? 1 : b;
+}
+
+// LayerNorm backward over rows of y = (row_map ? x with mapped rows from alt : x) with saved stats [rows, 2]:
+//   dx[row] = add[row] + rstd * (g - mean(g) - z * mean(g z)),  g = dy * gamma, z = (y - mean) * rstd
+//   dgamma_dbeta[0:d] = sum_rows dy * z,  dgamma_dbeta[d:2d] = sum_rows dy
+// Upstream gradient: dy [rows, d], or (dy == null) the broadcast dy_bcast[row / rows_per_bag, :] * bscale.
+int snuffy_ln_rows_bwd(const float* dy, const float* dy_bcast, int64_t rows_per_bag, float bscale, const float* x,
+                       const int32_t* row_map, const float* alt, const float* stats, const float* gamma,
+                       const float* add, int64_t rows, int64_t d, float* dx, float* dgamma_dbeta, float* partials,
+                       cudaStream_t stream) {
+    SNUFFY_REQUIRE((dy || dy_bcast) && x && stats && gamma && dgamma_dbeta && partials, "snuffy_ln_rows_bwd: null pointer");
+    SNUFFY_REQUIRE(!row_map || alt, "snuffy_ln_rows_bwd: row_map given without the replacement rows");
+    SNUFFY_REQUIRE(d % 4 == 0 && d >= 4 && rows >= 1 && (dy || rows_per_bag >= 1), "snuffy_ln_rows_bwd: needs d %% 4 == 0 (d=%lld)",
+                   (long long)d);
+    SNUFFY_REQUIRE((uintptr_t)x % 16 == 0 && (!dy || (uintptr_t)dy % 16 == 0) && (!dy_bcast || (uintptr_t)dy_bcast % 16 == 0) &&
+                       (!alt || (uintptr_t)alt % 16 == 0) && (!add || (uintptr_t)add % 16 == 0) &&
+                       (!dx || (uintptr_t)dx % 16 == 0) && (uintptr_t)gamma % 16 == 0,
+                   "snuffy_ln_rows_bwd: pointers must be 16-byte aligned");
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 2 * d * 4 > 200 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 2 * d * 4;
+    SNUFFY_REQUIRE(smem <= 200 * 1024, "snuffy_ln_rows_bwd: d=%lld too large", (long long)d);
+    if (smem > 48 * 1024)
+        SNUFFY_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t blocks = snuffy_ln_rows_bwd_blocks(rows);
+    ln_rows_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(dy, dy_bcast, rows_per_bag, bscale, x, row_map, alt,
+                                                                      stats, gamma, add, rows, (int)d, dx, partials);
+    launch_fold_partials(partials, (int)blocks, 2 * d / 4, dgamma_dbeta, stream);
+    return check_launch("snuffy_ln_rows_bwd", 2);
+}
+
+// dh = da * mask * act'(hpre) and/or a_out = act(hpre) * mask over `total` contiguous elements (total % 4 == 0).
+// hpre == null: plain dropout-mask application (act = identity).  The mask of element i is the one the forward GEMM
+// epilogue drew for flat index i with the same (p, seed, offset).
+int snuffy_act_bwd(const float* hpre, const float* da, int act, float dropout_p, uint64_t seed, uint64_t offset,
+                   int64_t total, float* dh, float* a_out, cudaStream_t stream) {
+    SNUFFY_REQUIRE((dh || a_out) && (!dh || da) && (!a_out || hpre), "snuffy_act_bwd: inconsistent pointers");
+    SNUFFY_REQUIRE(total % 4 == 0, "snuffy_act_bwd: element count must be a multiple of 4");
+    if (total == 0) return 0;
+    const int64_t t4 = total / 4;
+    int64_t blocks = (t4 + 255) / 256;
+    const int64_t cap = 16 * (int64_t)sm_count();
+    if (blocks > cap) blocks = cap;
+    act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(hpre, da, act, dropout_p, seed, offset, t4, dh, a_out);
+    return check_launch("snuffy_act_bwd");
+}
+
+int64_t snuffy_colsum_chunks(int64_t rows) {
+    int64_t c = (rows + 63) / 64;
+    const int64_t cap = 2 * (int64_t)sm_count();
+    if (c > cap) c = cap;
+    return c < 1 ? 1 : c;
+}
+
+// out[c, e] = sum_rows w[row, c] * X[row, e]  (w == null: plain column sums, C must be 1).  partials: chunks*C*d floats.
+int snuffy_colsum(const float* X, int64_t ldx, const float* w, int64_t rows, int64_t d, int64_t C, float* out,
+                  float* partials, cudaStream_t stream) {
+    SNUFFY_REQUIRE(X && out && partials && rows >= 1 && d >= 1 && C >= 1 && (w || C == 1), "snuffy_colsum: bad arguments");
+    const int64_t chunks = snuffy_colsum_chunks(rows);
+    const int64_t rpc = (rows + chunks - 1) / chunks;
+    colsum_kernel<<<(unsigned)chunks, 256, 0, stream>>>(X, ldx, w, rows, (int)d, (int)C, rpc, partials);
+    const int64_t n = C * d;
+    fold_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(partials, (int)chunks, n, out);
+    return check_launch("snuffy_colsum", 2);
+}
+
+// Row-local pieces of the sparse-attention backward on materialised [B*h*N, Ksel] score matrices (see kernel comment).
+int snuffy_attn_rows_bwd(const float* S, const float* stats, int64_t nrows, int64_t Ksel, int64_t N, int mode, float scale,
+                         float dropout_p, uint64_t seed, uint64_t offset, float* Pd, float* G, cudaStream_t stream) {
+    SNUFFY_REQUIRE(S && stats && nrows >= 1 && Ksel >= 1 && (mode == 0 ? Pd != nullptr : G != nullptr),
+                   "snuffy_attn_rows_bwd: bad arguments");
+    attn_rows_bwd_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, stream>>>(S, stats, nrows, (int)Ksel, N, mode, 1.f / scale,
+                                                                         dropout_p, seed, offset, Pd, G);
+    return check_launch("snuffy_attn_rows_bwd");
+}
+
+int snuffy_scatter_add_rows(float* dx, const int64_t* idx, const float* src, int64_t B, int64_t N, int64_t K, int64_t d,
+                            cudaStream_t stream) {
+    SNUFFY_REQUIRE(dx && idx && src && B >= 1 && N >= 1 && K >= 0 && d >= 1, "snuffy_scatter_add_rows: bad arguments");
+    if (K == 0) return 0;
+    scatter_add_rows_kernel<<<(unsigned)(B * K), 128, 0, stream>>>(dx, idx, src, N, K, (int)d);
+    return check_launch("snuffy_scatter_add_rows");
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

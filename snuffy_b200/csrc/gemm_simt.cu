@@ -24,6 +24,18 @@ struct SimtEpilogue {
     float drop_p; uint64_t seed, offset;   // dropout on the activated value (before the residual)
 };
 
+// Batched / split-K extension (backward contractions): blockIdx.z = batch * ksplit + split, batch = (outer, inner)
+// with separate element strides per operand (e.g. outer = bag, inner = head slice of a [rows, d] matrix).  With
+// ksplit > 1 every split writes its raw alpha-scaled partial to a dense [ksplit][nbatch][M][N] workspace that
+// splitk_fold_kernel sums in a fixed order (deterministic), so long contractions over the N patches (dW = dY^T X,
+// dKp = dS^T Q) fill the machine instead of a handful of CTAs.
+struct SimtBatch {
+    int nb_inner, ksplit;
+    int64_t sa_o, sa_i, sb_o, sb_i, sc_o, sc_i;
+    int64_t k_per_split;
+    float* part;
+};
+
 // K_CONTIG: the operand's k stride is 1 (row-major [rows, K]); otherwise its row stride is 1.
 template <bool K_CONTIG>
 __device__ __forceinline__ void load_tile(const float* __restrict__ P, int64_t s_row, int64_t s_k, int64_t row0,
@@ -86,11 +98,18 @@ template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbn,
                  int64_t sbk, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, bool vecA,
-                 bool vecB, SimtEpilogue ep) {
+                 bool vecB, SimtEpilogue ep, SimtBatch bt) {
     __shared__ __align__(16) float As[2][SG_BK][SG_BM + SG_PAD];
     __shared__ __align__(16) float Bs[2][SG_BK][SG_BN + SG_PAD];
     const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
     const int64_t m0 = (int64_t)blockIdx.y * SG_BM, n0 = (int64_t)blockIdx.x * SG_BN;
+    const int split = (int)(blockIdx.z % bt.ksplit), zb = (int)(blockIdx.z / bt.ksplit);
+    const int zo = zb / bt.nb_inner, zi = zb % bt.nb_inner;
+    A += zo * bt.sa_o + zi * bt.sa_i;
+    B += zo * bt.sb_o + zi * bt.sb_i;
+    C += zo * bt.sc_o + zi * bt.sc_i;
+    const int64_t k_begin = (int64_t)split * bt.k_per_split;
+    if (bt.ksplit > 1) K = min(K, k_begin + bt.k_per_split);
 
     float acc[8][8];
 #pragma unroll
@@ -99,18 +118,18 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const fl
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
     float ra[8], rb[8];
-    load_tile<A_KC>(A, sam, sak, m0, M, 0, K, vecA, ra);
-    load_tile<B_KC>(B, sbn, sbk, n0, N, 0, K, vecB, rb);
+    load_tile<A_KC>(A, sam, sak, m0, M, k_begin, K, vecA, ra);
+    load_tile<B_KC>(B, sbn, sbk, n0, N, k_begin, K, vecB, rb);
     store_tile<A_KC>(As[0], ra);
     store_tile<B_KC>(Bs[0], rb);
     __syncthreads();
 
-    const int64_t ktiles = (K + SG_BK - 1) / SG_BK;
+    const int64_t ktiles = K > k_begin ? (K - k_begin + SG_BK - 1) / SG_BK : 0;
     for (int64_t kt = 0; kt < ktiles; ++kt) {
         const int cur = (int)(kt & 1);
         if (kt + 1 < ktiles) {
-            load_tile<A_KC>(A, sam, sak, m0, M, (kt + 1) * SG_BK, K, vecA, ra);
-            load_tile<B_KC>(B, sbn, sbk, n0, N, (kt + 1) * SG_BK, K, vecB, rb);
+            load_tile<A_KC>(A, sam, sak, m0, M, k_begin + (kt + 1) * SG_BK, K, vecA, ra);
+            load_tile<B_KC>(B, sbn, sbk, n0, N, k_begin + (kt + 1) * SG_BK, K, vecB, rb);
         }
 #pragma unroll
         for (int k = 0; k < SG_BK; ++k) {
@@ -132,6 +151,23 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const fl
         __syncthreads();
     }
 
+    if (bt.ksplit > 1) {
+        // raw partial: part[split][batch][m][n]
+        float* P = bt.part + ((int64_t)split * (gridDim.z / bt.ksplit) + zb) * M * N;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (m >= M) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t n = n0 + h * 64 + tx * 4 + j;
+                    if (n < N) P[m * N + n] = acc[i][h * 4 + j] * ep.alpha;
+                }
+        }
+        return;
+    }
     const bool vec_out = (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0) &&
                          (!ep.resid || ((ep.ldr % 4 == 0) && ((uintptr_t)ep.resid % 16 == 0) &&
                                         (!ep.resid_alt || (uintptr_t)ep.resid_alt % 16 == 0))) &&
@@ -184,12 +220,47 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const fl
     }
 }
 
+// C[batch][m][n] (strided) = sum_split part[split][batch][m][n] + bias[n]
+__global__ void __launch_bounds__(256)
+splitk_fold_kernel(const float* __restrict__ part, int ksplit, int nbatch, int64_t M, int64_t N, float* __restrict__ C,
+                   int64_t ldc, int nb_inner, int64_t sc_o, int64_t sc_i, const float* __restrict__ bias) {
+    const int64_t total = (int64_t)nbatch * M * N;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float acc = 0.f;
+    for (int s = 0; s < ksplit; ++s) acc += __ldcg(part + (int64_t)s * total + i);
+    const int64_t n = i % N, m = (i / N) % M;
+    const int zb = (int)(i / (M * N));
+    if (bias) acc += bias[n];
+    C[(zb / nb_inner) * sc_o + (zb % nb_inner) * sc_i + m * ldc + n] = acc;
+}
+
 }  // namespace snuffy
 
 using namespace snuffy;
 
 #pragma GCC visibility push(default)
 extern "C" {
+
+static int launch_gemm_f32(const float* A, int64_t lda, int a_kc, const float* B, int64_t ldb, int b_kc, float* C,
+                           int64_t ldc, int64_t M, int64_t N, int64_t K, const SimtEpilogue& ep, const SimtBatch& bt,
+                           int nbatch, cudaStream_t stream, const char* who) {
+    const int64_t sam = a_kc ? lda : 1, sak = a_kc ? 1 : lda;
+    const int64_t sbn = b_kc ? ldb : 1, sbk = b_kc ? 1 : ldb;
+    const bool vecA = (lda % 4 == 0) && ((uintptr_t)A % 16 == 0) && bt.sa_o % 4 == 0 && bt.sa_i % 4 == 0;
+    const bool vecB = (ldb % 4 == 0) && ((uintptr_t)B % 16 == 0) && bt.sb_o % 4 == 0 && bt.sb_i % 4 == 0;
+    dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM), (unsigned)(nbatch * bt.ksplit));
+    SNUFFY_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "%s: M=%lld / batch too large for one launch", who, (long long)M);
+    if (a_kc && b_kc)
+        gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep, bt);
+    else if (a_kc && !b_kc)
+        gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep, bt);
+    else if (!a_kc && b_kc)
+        gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep, bt);
+    else
+        gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep, bt);
+    return 0;
+}
 
 // C[M,N] (ldc) = dropout(act(alpha * A.B^T + bias)) + resid.   a_kc / b_kc: 1 when the operand is stored [rows, K]
 // row-major with leading dimension lda/ldb, 0 when it is stored [K, rows] row-major (i.e. transposed).
@@ -202,21 +273,56 @@ int snuffy_gemm_f32(const float* A, int64_t lda, int a_kc, const float* B, int64
     SNUFFY_REQUIRE(!row_map || (resid && resid_alt), "snuffy_gemm_f32: row_map needs resid and resid_alt");
     if (M == 0 || N == 0) return 0;
     SimtEpilogue ep{bias, act, resid, row_map, resid_alt, ldr, preact, alpha, dropout_p, seed, offset};
-    const int64_t sam = a_kc ? lda : 1, sak = a_kc ? 1 : lda;
-    const int64_t sbn = b_kc ? ldb : 1, sbk = b_kc ? 1 : ldb;
-    const bool vecA = (lda % 4 == 0) && ((uintptr_t)A % 16 == 0);
-    const bool vecB = (ldb % 4 == 0) && ((uintptr_t)B % 16 == 0);
-    dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
-    SNUFFY_REQUIRE(grid.y <= 65535, "snuffy_gemm_f32: M=%lld too large for one launch", (long long)M);
-    if (a_kc && b_kc)
-        gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep);
-    else if (a_kc && !b_kc)
-        gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep);
-    else if (!a_kc && b_kc)
-        gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep);
-    else
-        gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, C, ldc, M, N, K, vecA, vecB, ep);
+    SimtBatch bt{1, 1, 0, 0, 0, 0, 0, 0, 0, nullptr};
+    if (int rc = launch_gemm_f32(A, lda, a_kc, B, ldb, b_kc, C, ldc, M, N, K, ep, bt, 1, stream, "snuffy_gemm_f32")) return rc;
     return check_launch("snuffy_gemm_f32");
+}
+
+// Batched / split-K form used by the backward pass: for batch z = (zo, zi), zo < nb_outer, zi < nb_inner
+//   C_z[M,N] = alpha * A_z . B_z^T (+ bias),   X_z = X + zo * s?_o + zi * s?_i   (element strides)
+// ksplit > 1 splits the contraction over K across CTAs; `workspace` then needs snuffy_gemm_f32_batched_workspace bytes.
+int64_t snuffy_gemm_f32_batched_workspace(int64_t nbatch, int64_t M, int64_t N, int64_t ksplit) {
+    return ksplit > 1 ? nbatch * M * N * ksplit * 4 + 16 : 0;
+}
+
+// a ksplit that fills ~2 waves of the machine for this problem (1 when the grid is already large or K is short)
+int64_t snuffy_gemm_f32_auto_ksplit(int64_t nbatch, int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = nbatch * ((M + SG_BM - 1) / SG_BM) * ((N + SG_BN - 1) / SG_BN);
+    if (tiles <= 0) return 1;
+    int64_t ks = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+    const int64_t max_ks = K / 256;                        // at least 256 k per split
+    if (ks > max_ks) ks = max_ks;
+    if (ks > 64) ks = 64;
+    return ks < 1 ? 1 : ks;
+}
+
+int snuffy_gemm_f32_batched(const float* A, int64_t lda, int a_kc, const float* B, int64_t ldb, int b_kc, float* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha, const float* bias,
+                            int64_t nb_outer, int64_t nb_inner, int64_t sa_o, int64_t sa_i, int64_t sb_o, int64_t sb_i,
+                            int64_t sc_o, int64_t sc_i, int64_t ksplit, void* workspace, int64_t workspace_bytes,
+                            cudaStream_t stream) {
+    SNUFFY_REQUIRE(A && B && C, "snuffy_gemm_f32_batched: null pointer");
+    SNUFFY_REQUIRE(M >= 0 && N >= 0 && K >= 0 && nb_outer >= 1 && nb_inner >= 1 && ksplit >= 1,
+                   "snuffy_gemm_f32_batched: bad dimensions");
+    if (M == 0 || N == 0) return 0;
+    const int64_t nbatch = nb_outer * nb_inner;
+    SNUFFY_REQUIRE(ksplit == 1 || (workspace && workspace_bytes >= snuffy_gemm_f32_batched_workspace(nbatch, M, N, ksplit)),
+                   "snuffy_gemm_f32_batched: split-K needs a workspace");
+    SimtEpilogue ep{ksplit == 1 ? bias : nullptr, ACT_NONE, nullptr, nullptr, nullptr, 0, nullptr, alpha, 0.f, 0, 0};
+    SimtBatch bt{(int)nb_inner, (int)ksplit, sa_o, sa_i, sb_o, sb_i, sc_o, sc_i, 0, reinterpret_cast<float*>(workspace)};
+    if (ksplit > 1) {
+        int64_t kps = (K + ksplit - 1) / ksplit;
+        bt.k_per_split = (kps + SG_BK - 1) / SG_BK * SG_BK;
+    }
+    if (int rc = launch_gemm_f32(A, lda, a_kc, B, ldb, b_kc, C, ldc, M, N, K, ep, bt, (int)nbatch, stream,
+                                 "snuffy_gemm_f32_batched")) return rc;
+    if (ksplit > 1) {
+        const int64_t total = nbatch * M * N;
+        splitk_fold_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(bt.part, (int)ksplit, (int)nbatch, M, N, C, ldc,
+                                                                               (int)nb_inner, sc_o, sc_i, bias);
+        return check_launch("snuffy_gemm_f32_batched", 2);
+    }
+    return check_launch("snuffy_gemm_f32_batched");
 }
 
 }  // extern "C"
