@@ -123,6 +123,45 @@ int snuffy_dsmil_pool_fwd(const float* Q, const float* qmax, const float* V, con
                           float* Bm, float* logits, float* stats_out, void* workspace,
                           int64_t workspace_bytes, snuffy_stream_t stream);
 
+/* ---- backward (train.py:259 loss.backward() through the drop-in modules; autograd only sequences these)   */
+/* Batched / split-K form of snuffy_gemm_f32 (no epilogue but alpha and bias): batch z = (zo, zi) offsets the
+ * operands by zo*s?_o + zi*s?_i elements (outer = bag, inner = head slice); ksplit > 1 splits the contraction
+ * over CTAs with a deterministic fold (dW = dY^T X and dKp = dS^T Q contract over all N patches).            */
+int64_t snuffy_gemm_f32_batched_workspace(int64_t nbatch, int64_t M, int64_t N, int64_t ksplit);
+int64_t snuffy_gemm_f32_auto_ksplit(int64_t nbatch, int64_t M, int64_t N, int64_t K);
+int snuffy_gemm_f32_batched(const float* A, int64_t lda, int a_kc, const float* B, int64_t ldb, int b_kc,
+                            float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha,
+                            const float* bias, int64_t nb_outer, int64_t nb_inner, int64_t sa_o, int64_t sa_i,
+                            int64_t sb_o, int64_t sb_i, int64_t sc_o, int64_t sc_i, int64_t ksplit,
+                            void* workspace, int64_t workspace_bytes, snuffy_stream_t stream);
+/* LayerNorm backward (autograd of nn.LayerNorm at snuffy.py:107,110,86) with saved (mean, rstd):
+ * dx = add + LN'(dy), dgamma_dbeta [2, d].  dy == null: upstream is dy_bcast[row / rows_per_bag] * bscale
+ * (the mean-pool of snuffy.py:71).  partials: snuffy_ln_rows_bwd_blocks(rows) * 2 * d floats.               */
+int64_t snuffy_ln_rows_bwd_blocks(int64_t rows);
+int snuffy_ln_rows_bwd(const float* dy, const float* dy_bcast, int64_t rows_per_bag, float bscale,
+                       const float* x, const int32_t* row_map, const float* alt, const float* stats,
+                       const float* gamma, const float* add, int64_t rows, int64_t d, float* dx,
+                       float* dgamma_dbeta, float* partials, snuffy_stream_t stream);
+/* dh = da * dropout_mask * act'(hpre), a_out = act(hpre) * dropout_mask   (snuffy.py:216-225 backward)      */
+int snuffy_act_bwd(const float* hpre, const float* da, int act, float dropout_p, uint64_t seed,
+                   uint64_t offset, int64_t total, float* dh, float* a_out, snuffy_stream_t stream);
+/* out[c, :] = sum_rows w[row, c] * X[row, :]  (bias grads; FCLayer weight grad snuffy.py:37)                 */
+int64_t snuffy_colsum_chunks(int64_t rows);
+int snuffy_colsum(const float* X, int64_t ldx, const float* w, int64_t rows, int64_t d, int64_t C, float* out,
+                  float* partials, snuffy_stream_t stream);
+/* row-local pieces of the attention backward (snuffy.py:160-168) on materialised [B*h*N, Ksel] scores:
+ * mode 0: Pd = softmax(S) * dropout_mask;  mode 1: G (= V dO^T on entry) <- dS                               */
+int snuffy_attn_rows_bwd(const float* S, const float* stats, int64_t nrows, int64_t Ksel, int64_t N, int mode,
+                         float scale, float dropout_p, uint64_t seed, uint64_t offset, float* Pd, float* G,
+                         snuffy_stream_t stream);
+/* dx[b, idx[b,k], :] += src[b*K + k, :]   (backward of the raw-row gather, snuffy.py:131,145-147)            */
+int snuffy_scatter_add_rows(float* dx, const int64_t* idx, const float* src, int64_t B, int64_t N, int64_t K,
+                            int64_t d, snuffy_stream_t stream);
+
+/* DSMIL: backward of A = softmax over the N instances (dsmil.py:86): dS = A (dA - sum_n A dA) / scale          */
+int snuffy_softmax_cols_bwd(const float* A, const float* dA, int64_t N, int64_t C, float scale, float* dS,
+                            snuffy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

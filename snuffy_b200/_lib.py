@@ -44,6 +44,17 @@ _SIGNATURES = {
     "snuffy_sparse_attn_tc_fwd": (c_int, [P, I, I, I, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
     "snuffy_dsmil_workspace": (c_int64, [I, I, I]),
     "snuffy_dsmil_pool_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P, P, P, P, P, I, P]),
+    "snuffy_gemm_f32_batched_workspace": (c_int64, [I, I, I, I]),
+    "snuffy_gemm_f32_auto_ksplit": (c_int64, [I, I, I, I]),
+    "snuffy_gemm_f32_batched": (c_int, [P, I, c_int, P, I, c_int, P, I, I, I, I, c_float, P, I, I, I, I, I, I, I, I, I, P, I, P]),
+    "snuffy_ln_rows_bwd_blocks": (c_int64, [I]),
+    "snuffy_ln_rows_bwd": (c_int, [P, P, I, c_float, P, P, P, P, P, P, I, I, P, P, P, P]),
+    "snuffy_act_bwd": (c_int, [P, P, c_int, c_float, c_uint64, c_uint64, I, P, P, P]),
+    "snuffy_colsum_chunks": (c_int64, [I]),
+    "snuffy_colsum": (c_int, [P, I, P, I, I, I, P, P, P]),
+    "snuffy_attn_rows_bwd": (c_int, [P, P, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P]),
+    "snuffy_scatter_add_rows": (c_int, [P, P, P, I, I, I, I, P]),
+    "snuffy_softmax_cols_bwd": (c_int, [P, P, I, I, c_float, P, P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -57,10 +57,9 @@ def encoder_layer_fn(layer, x: torch.Tensor, sel: torch.Tensor):
     if _needs_grad(x, *layer._params()):
         from .backward import EncoderLayerFunction
         return EncoderLayerFunction.apply(layer, x, sel, *layer._params())
-    if p_enc > 0.0 or p_ff > 0.0:
-        raise NotImplementedError("encoder / feed-forward dropout in train mode needs the autograd path")
     w = layer.layer_weights()
     xc = x.detach().contiguous().view(B * N, d)
     x_next, probs, _ = engine.encoder_layer_forward(xc, B, N, sel, w, heads, act, precision,
-                                                    want_probs=layer.return_attn, attn_dropout=p_attn)
+                                                    want_probs=layer.return_attn, attn_dropout=p_attn,
+                                                    enc_dropout=p_enc, ff_dropout=p_ff)
     return x_next.view(B, N, d), probs

@@ -1,0 +1,281 @@
+"""Backward passes of the drop-in modules (train.py:259 ``loss.backward()``).
+
+Every ``torch.autograd.Function`` here runs its forward AND backward in ``libsnuffy_b200.so``: PyTorch's autograd
+engine only sequences them and owns the buffers.  The gradient math follows SURVEY.md Appendix A differentiated by
+hand; ``tests/test_gpu_backward.py`` checks it against autograd of the CPU port of the reference.
+
+Per encoder layer (snuffy.py:126-157), with y = x-with-rows-S-replaced, g the upstream gradient of x_next:
+  FFN       x_next = y + D2(W2 a + b2), a = Dff(act(h)), h = W1 LN2(y) + b1
+  attention xs_new = xs + D1(Wo O + bo), O_j = D_attn(softmax_keys(Q_j Kp_j^T / sqrt(dk)))^T V_j,
+            Q|V = Wqv LN1(x) + bqv (all N rows), Kp = Wk xs + bk, xs = x[S] raw rows
+  scatter   y[S] = xs_new, y[not S] = x
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import engine, ops
+
+
+def _flat(t: torch.Tensor, d: int) -> torch.Tensor:
+    return t.contiguous().view(-1, d)
+
+
+# ------------------------------------------------------------------ instance scores (snuffy.py:39-41)
+class ScoresFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, weight, bias):
+        ctx.save_for_backward(feats, weight)
+        ctx.has_bias = bias is not None
+        return ops.scores(feats.detach(), weight.detach(), None if bias is None else bias.detach())
+
+    @staticmethod
+    def backward(ctx, dc):
+        feats, weight = ctx.saved_tensors
+        d = feats.shape[-1]
+        C = weight.shape[0]
+        x2 = _flat(feats.detach(), d)
+        dc2 = dc.contiguous().view(-1, C)
+        d_feats = d_w = d_b = None
+        if ctx.needs_input_grad[1]:
+            d_w = ops.colsum(x2, dc2)                                    # [C, d]: only the arg-max rows are non-zero
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            d_b = ops.colsum(dc2).view(C)
+        if ctx.needs_input_grad[0]:
+            d_feats = ops.matmul_nn(dc2, weight.detach()).view(feats.shape)
+        return d_feats, d_w, d_b
+
+
+# ------------------------------------------------------------------ LayerNorm (Encoder.forward's final norm, snuffy.py:86)
+class LayerNormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        d = x.shape[-1]
+        out, _, stats = ops.ln_rows(_flat(x.detach(), d), gamma.detach(), beta.detach(), want_f32=True, want_stats=True)
+        ctx.save_for_backward(x, gamma, stats)
+        return out.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, stats = ctx.saved_tensors
+        d = x.shape[-1]
+        dx, dg, db = ops.ln_rows_bwd(_flat(x.detach(), d), stats, gamma.detach(), dy=_flat(g, d),
+                                     want_dx=ctx.needs_input_grad[0])
+        return (dx.view(x.shape) if dx is not None else None), dg, db
+
+
+# ------------------------------------------------------------------ final LN + mean + head (snuffy.py:86,71)
+class LnMeanHeadFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, w_head, b_head):
+        bag, stats, pooled = ops.ln_mean_head(x.detach(), gamma.detach(), beta.detach(), w_head.detach(),
+                                              None if b_head is None else b_head.detach(), want_stats=True, want_pooled=True)
+        ctx.save_for_backward(x, gamma, w_head, stats, pooled)
+        ctx.has_bias = b_head is not None
+        return bag
+
+    @staticmethod
+    def backward(ctx, dbag):
+        x, gamma, w_head, stats, pooled = ctx.saved_tensors
+        B, N, d = x.shape
+        C = w_head.shape[0]
+        dbag = dbag.contiguous().view(B, C)
+        d_wh = ops.matmul_tn(dbag, pooled)                               # [C, d]
+        d_bh = ops.colsum(dbag).view(C) if ctx.has_bias else None
+        dpooled = ops.matmul_nn(dbag, w_head.detach())                   # [B, d]; every row of bag b receives dpooled[b] / N
+        dx, dg, db = ops.ln_rows_bwd(_flat(x.detach(), d), stats, gamma.detach(), dy_bcast=dpooled, rows_per_bag=N,
+                                     bscale=1.0 / N, want_dx=ctx.needs_input_grad[0])
+        return (dx.view(B, N, d) if dx is not None else None), dg, db, d_wh, d_bh
+
+
+# ------------------------------------------------------------------ one encoder layer (snuffy.py:126-157)
+class EncoderLayerFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layer, x, sel, *params):
+        B, N, d = x.shape
+        training = layer.training
+        w = layer.layer_weights()
+        xc = x.detach().contiguous().view(B * N, d)
+        x_next, probs, tape = engine.encoder_layer_forward(
+            xc, B, N, sel, w, layer.self_attn.h, layer.feed_forward.activation_name, layer._effective_precision(),
+            want_probs=layer.return_attn, save=True,
+            attn_dropout=float(layer.self_attn.dropout.p) if training else 0.0,
+            enc_dropout=float(layer.sublayer[0].dropout.p) if training else 0.0,
+            ff_dropout=float(layer.feed_forward.dropout.p) if training else 0.0)
+        ctx.tape, ctx.w = tape, w
+        ctx.meta = (B, N, d, layer.self_attn.h, layer.feed_forward.activation_name)
+        x_next = x_next.view(B, N, d)
+        if probs is None:
+            return x_next, None
+        ctx.mark_non_differentiable(probs)       # nobody differentiates through A
+        return x_next, probs
+
+    @staticmethod
+    def backward(ctx, g_out, _g_probs=None):
+        t, w = ctx.tape, ctx.w
+        B, N, d, heads, act = ctx.meta
+        rows, ksel = B * N, t.sel.shape[1]
+        need = ctx.needs_input_grad
+        g = _flat(g_out, d)
+
+        # ---- feed-forward sub-layer
+        gf = ops.act_bwd(None, g, drop=t.drop_enc2)[0] if t.drop_enc2[0] > 0 else g
+        d_b2 = ops.colsum(gf).view(-1)
+        da = ops.matmul_nn(gf, w.w2)                                              # [rows, dff]
+        dh, a = ops.act_bwd(t.h_pre, da, act, t.drop_ff, want_dh=True, want_a=True)
+        del da
+        d_w2 = ops.matmul_tn(gf, a)                                               # [d, dff]
+        del a
+        d_b1 = ops.colsum(dh).view(-1)
+        u2, _, _ = ops.ln_rows(t.x_in, w.g2, w.be2, row_map=t.row_map, alt=t.xs_new, want_f32=True)
+        d_w1 = ops.matmul_tn(dh, u2)                                              # [dff, d]
+        del u2
+        du2 = ops.matmul_nn(dh, w.w1)                                             # [rows, d]
+        del dh
+        dy, d_g2, d_be2 = ops.ln_rows_bwd(t.x_in, t.ln2_stats, w.g2, dy=du2, row_map=t.row_map, alt=t.xs_new, add=g)
+        del du2
+
+        # ---- attention sub-layer: the selected rows of y are xs_new = xs + D1(Wo O + bo)
+        dxs_new = ops.gather_rows(dy.view(B, N, d), t.sel).view(B * ksel, d)
+        dz = ops.act_bwd(None, dxs_new, drop=t.drop_enc1)[0] if t.drop_enc1[0] > 0 else dxs_new
+        d_bo = ops.colsum(dz).view(-1)
+        d_wo = ops.matmul_tn(dz, t.o)
+        d_o = ops.matmul_nn(dz, w.wo)                                             # [B*Ksel, d]
+        q, v = t.qv[:, :d], t.qv[:, d:]
+        dq, dv, dkp = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)
+        d_bk = ops.colsum(dkp).view(-1)                                           # == 0 up to rounding (App. B-16)
+        d_wk = ops.matmul_tn(dkp, t.xs)
+        u1, _, _ = ops.ln_rows(t.x_in, w.g1, w.be1, want_f32=True)
+        d_wq, d_wv = ops.matmul_tn(dq, u1), ops.matmul_tn(dv, u1)
+        del u1
+        d_bq, d_bv = ops.colsum(dq).view(-1), ops.colsum(dv).view(-1)
+        du1 = ops.matmul_nn(dv, w.wv, resid=ops.matmul_nn(dq, w.wq))              # [rows, d]
+        dx, d_g1, d_be1 = ops.ln_rows_bwd(t.x_in, t.ln1_stats, w.g1, dy=du1, add=dy, want_dx=need[1])
+        if dx is not None:
+            # raw selected rows also feed the key projection: dx[S] += dKp Wk  (the xs residual is already in `add`)
+            ops.scatter_add_rows(dx.view(B, N, d), t.sel, ops.matmul_nn(dkp, w.wk))
+            dx = dx.view(B, N, d)
+        ctx.tape = None
+        return (None, dx, None, d_wq, d_bq, d_wk, d_bk, d_wv, d_bv, d_wo, d_bo, d_w1, d_b1, d_w2, d_b2,
+                d_g1, d_be1, d_g2, d_be2)
+
+
+# ------------------------------------------------------------------ DSMIL bag classifier (dsmil.py:72-92)
+def _dsmil_params(mod):
+    import torch.nn as nn
+    if isinstance(mod.q, nn.Sequential):
+        qp = [mod.q[0].weight, mod.q[0].bias, mod.q[2].weight, mod.q[2].bias]
+    else:
+        qp = [mod.q.weight, mod.q.bias]
+    vp = [mod.v[1].weight, mod.v[1].bias] if isinstance(mod.v, nn.Sequential) else []
+    return qp, vp, [mod.fcc.weight, mod.fcc.bias]
+
+
+class _QMlp:
+    """q(.) of dsmil.py:56-60 with saved pre-activations, and its backward."""
+
+    def __init__(self, qp):
+        self.p = [t.detach() for t in qp]
+        self.nonlinear = len(qp) == 4
+
+    def forward(self, inp):
+        if not self.nonlinear:
+            return ops.linear_f32(inp, self.p[0], self.p[1]), (inp,)
+        M = inp.shape[0]
+        a1, h1 = ops.gemm_f32(inp, self.p[0], M=M, N=self.p[0].shape[0], K=inp.shape[1], bias=self.p[1], act="relu",
+                              want_preact=True)
+        out, h2 = ops.gemm_f32(a1, self.p[2], M=M, N=self.p[2].shape[0], K=a1.shape[1], bias=self.p[3], act="tanh",
+                               want_preact=True)
+        return out, (inp, h1, a1, h2)
+
+    def backward(self, saved, d_out, want_dinp):
+        """-> (grads of the q parameters in order, d_inp or None)"""
+        if not self.nonlinear:
+            (inp,) = saved
+            d_inp = ops.matmul_nn(d_out, self.p[0]) if want_dinp else None
+            return [ops.matmul_tn(d_out, inp), ops.colsum(d_out).view(-1)], d_inp
+        inp, h1, a1, h2 = saved
+        dh2, _ = ops.act_bwd(h2, d_out, "tanh")
+        dh1, _ = ops.act_bwd(h1, ops.matmul_nn(dh2, self.p[2]), "relu")
+        d_inp = ops.matmul_nn(dh1, self.p[0]) if want_dinp else None
+        return [ops.matmul_tn(dh1, inp), ops.colsum(dh1).view(-1), ops.matmul_tn(dh2, a1), ops.colsum(dh2).view(-1)], d_inp
+
+
+class DsmilBClassifierFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, feats, c, *params):
+        import torch.nn as nn
+        qp, vp, fp = _dsmil_params(mod)
+        feats_d = feats.detach().contiguous()
+        n, d = feats_d.shape
+        ncls = c.shape[1]
+        drop = (0.0, 0, 0)
+        v_saved = None
+        if vp:
+            p = float(mod.v[0].p) if mod.training else 0.0
+            if p > 0:
+                drop = (p,) + engine._RANDOM.next()
+            a0 = ops.act_bwd(None, feats_d, drop=drop)[0] if p > 0 else feats_d      # nn.Dropout on the input (dsmil.py:64)
+            v, hv = ops.gemm_f32(a0, vp[0].detach(), M=n, N=d, K=d, bias=vp[1].detach(), act="relu", want_preact=True)
+            v_saved = (a0, hv)
+        else:
+            v = feats_d
+        mlp = _QMlp(qp)
+        q, q_saved = mlp.forward(feats_d)
+        crit = ops.select_topk(c.detach().contiguous().view(1, n, ncls), 1).view(1, ncls)   # dsmil.py:78-81
+        m_feats = ops.gather_rows(feats_d.view(1, n, d), crit).view(ncls, d)
+        q_max, qm_saved = mlp.forward(m_feats)
+        a, bm, logits = ops.dsmil_pool(q, q_max, v, fp[0].detach(), fp[1].detach())
+        ctx.mlp, ctx.saved = mlp, (feats_d, v, v_saved, q, q_saved, q_max, qm_saved, crit, a, bm, drop)
+        ctx.nq, ctx.nv = len(qp), len(vp)
+        ctx.vw = vp[0].detach() if vp else None
+        ctx.fw = fp[0].detach()
+        ctx.mark_non_differentiable(crit)
+        return logits.view(1, -1), a, bm.view(1, ncls, d)
+
+    @staticmethod
+    def backward(ctx, d_logits, d_a_up, d_b_up):
+        feats, v, v_saved, q, q_saved, q_max, qm_saved, crit, a, bm, drop = ctx.saved
+        n, d = feats.shape
+        ncls = a.shape[1]
+        dq_dim = q.shape[1]
+        want_dfeats = ctx.needs_input_grad[1]
+        fw = ctx.fw.view(ncls, ncls * d)
+        dl = (d_logits if d_logits is not None else torch.zeros(1, ncls, device=feats.device)).contiguous().view(1, ncls)
+        d_fw = ops.matmul_tn(dl, bm.view(1, ncls * d)).view(ncls, ncls, d)           # Conv1d(C, C, kernel = d) weight
+        d_fb = dl.view(ncls).clone()
+        d_bm = ops.matmul_nn(dl, fw).view(ncls, d)
+        if d_b_up is not None:
+            d_bm = d_bm + d_b_up.view(ncls, d)
+        d_v = ops.matmul_nn(a, d_bm)                                                 # [N, d]
+        d_a = ops.matmul_nt(v, d_bm)                                                 # [N, C]
+        if d_a_up is not None:
+            d_a = d_a + d_a_up
+        d_s = ops.softmax_cols_bwd(a, d_a, float(torch.sqrt(torch.tensor(dq_dim, dtype=torch.float32))))
+        d_q = ops.matmul_nn(d_s, q_max)                                              # [N, 128]
+        d_qmax = ops.matmul_tn(d_s, q)                                               # [C, 128]
+        gq, d_feats = ctx.mlp.backward(q_saved, d_q, want_dfeats)
+        gqm, d_mfeats = ctx.mlp.backward(qm_saved, d_qmax, want_dfeats)
+        q_grads = [g1 + g2 for g1, g2 in zip(gq, gqm)]
+        v_grads = []
+        if ctx.nv:
+            a0, hv = v_saved
+            dhv, _ = ops.act_bwd(hv, d_v, "relu")
+            v_grads = [ops.matmul_tn(dhv, a0), ops.colsum(dhv).view(-1)]
+            if want_dfeats:
+                dfv = ops.matmul_nn(dhv, ctx.vw)
+                d_feats = d_feats + (ops.act_bwd(None, dfv, drop=drop)[0] if drop[0] > 0 else dfv)
+        elif want_dfeats:
+            d_feats = d_feats + d_v
+        if want_dfeats:
+            d_feats = d_feats.contiguous()
+            ops.scatter_add_rows(d_feats.view(1, n, d), crit, d_mfeats)
+        ctx.saved = None
+        return (None, d_feats if want_dfeats else None, None, *q_grads, *v_grads, d_fw, d_fb)
+
+
+def dsmil_bclassifier_fn(mod, feats, c):
+    qp, vp, fp = _dsmil_params(mod)
+    return DsmilBClassifierFunction.apply(mod, feats, c, *qp, *vp, *fp)

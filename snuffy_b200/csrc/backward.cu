@@ -284,3 +284,39 @@ int snuffy_scatter_add_rows(float* dx, const int64_t* idx, const float* src, int
 
 }  // extern "C"
 #pragma GCC visibility pop
+
+// ------------------------------------------------------------------ DSMIL: softmax over instances, backward
+// A [N, C] = softmax over n (dsmil.py:86).  dS[n, c] = A[n, c] * (dA[n, c] - sum_n' A[n', c] dA[n', c]) / scale.
+// One CTA per class (C is 1..3 and this is N*C elements: latency-sized).
+namespace snuffy {
+__global__ void __launch_bounds__(1024)
+softmax_cols_bwd_kernel(const float* __restrict__ A, const float* __restrict__ dA, int64_t N, int C, float inv_scale,
+                        float* __restrict__ dS) {
+    __shared__ float red[32];
+    __shared__ float s_delta;
+    const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.f;
+    for (int64_t n = threadIdx.x; n < N; n += blockDim.x) acc = fmaf(A[n * C + c], dA[n * C + c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        float v = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) s_delta = v;
+    }
+    __syncthreads();
+    const float delta = s_delta;
+    for (int64_t n = threadIdx.x; n < N; n += blockDim.x)
+        dS[n * C + c] = A[n * C + c] * (dA[n * C + c] - delta) * inv_scale;
+}
+}  // namespace snuffy
+
+#pragma GCC visibility push(default)
+extern "C" int snuffy_softmax_cols_bwd(const float* A, const float* dA, int64_t N, int64_t C, float scale, float* dS,
+                                       cudaStream_t stream) {
+    SNUFFY_REQUIRE(A && dA && dS && N >= 1 && C >= 1 && scale > 0.f, "snuffy_softmax_cols_bwd: bad arguments");
+    snuffy::softmax_cols_bwd_kernel<<<(unsigned)C, 1024, 0, stream>>>(A, dA, N, (int)C, 1.f / scale, dS);
+    return snuffy::check_launch("snuffy_softmax_cols_bwd");
+}
+#pragma GCC visibility pop

@@ -182,7 +182,10 @@ class LayerTape:
     attn_stats: torch.Tensor
     h_pre: torch.Tensor
     x_in: torch.Tensor
-    drop: Tuple[float, int, int]
+    drop: Tuple[float, int, int]                 # attention dropout (p, seed, offset)   snuffy.py:166-167
+    drop_enc1: Tuple[float, int, int] = (0.0, 0, 0)   # sublayer[0] dropout on the attention output   snuffy.py:108
+    drop_ff: Tuple[float, int, int] = (0.0, 0, 0)     # feed-forward hidden dropout                     snuffy.py:225
+    drop_enc2: Tuple[float, int, int] = (0.0, 0, 0)   # sublayer[1] dropout on the FFN output           snuffy.py:110
 
 
 def tc_supported(d: int) -> bool:
@@ -191,11 +194,13 @@ def tc_supported(d: int) -> bool:
 
 def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w: LayerWeights, heads: int,
                           activation: str, precision: str, want_probs: bool, save: bool = False,
-                          attn_dropout: float = 0.0) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[LayerTape]]:
+                          attn_dropout: float = 0.0, enc_dropout: float = 0.0, ff_dropout: float = 0.0
+                          ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[LayerTape]]:
     """One EncoderLayer (snuffy.py:126-157) on x [B*N, d] with the selection sel [B, Ksel].
 
-    Eval-mode semantics except for the attention dropout (train mode, snuffy.py:166-167).  Returns
-    (x_next [B*N, d], P [B, h, N, Ksel] or None, tape or None)."""
+    The three dropout rates are 0 in eval mode; in train mode they are the reference's (attention probabilities
+    snuffy.py:166-167, both sublayer outputs 108/110, FFN hidden 225), drawn from counter-based masks that the backward
+    regenerates.  Returns (x_next [B*N, d], P [B, h, N, Ksel] or None, tape or None)."""
     d = x.shape[1]
     rows = B * N
     Ksel = sel.shape[1]
@@ -224,10 +229,9 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         kp, _, _ = ops.gemm_tc(xsp, w.wk_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bk)
     else:
         kp = ops.linear_f32(xs, w.wk, w.bk)
-    drop = (0.0, 0, 0)
-    if attn_dropout > 0.0:
-        seed, offset = _RANDOM.next()
-        drop = (attn_dropout, seed, offset)
+    def draw(p):
+        return (float(p),) + _RANDOM.next() if p > 0.0 else (0.0, 0, 0)
+    drop, drop_enc1, drop_ff, drop_enc2 = draw(attn_dropout), draw(enc_dropout), draw(ff_dropout), draw(enc_dropout)
     if attn_tc:
         o, probs, attn_stats = ops.sparse_attn_tc(qvp, kp, B, N, Ksel, heads, d, want_probs=want_probs, want_stats=save,
                                                   dropout_p=drop[0], seed=drop[1], offset=drop[2])
@@ -236,27 +240,30 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
                                                want_stats=save, dropout_p=drop[0], seed=drop[1], offset=drop[2])
     if small_tc:                                                             # X_S' = X_S + W3 O + b3
         _, opl, _ = ops.ln_rows(o, None, None, apply_ln=False, want_planes=True)
-        xs_new, _, _ = ops.gemm_tc(opl, w.wo_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bo, resid=xs)
+        xs_new, _, _ = ops.gemm_tc(opl, w.wo_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bo, resid=xs,
+                                   drop=drop_enc1)
     else:
-        xs_new = ops.linear_f32(o, w.wo, w.bo, resid=xs)
+        xs_new = ops.linear_f32(o, w.wo, w.bo, resid=xs, drop=drop_enc1)
 
     # --- feed-forward sub-layer over y = x with rows S replaced by X_S' (read through row_map)
     h_pre = None
     if precision == "fp32":
         u2, _, ln2_stats = ops.ln_rows(x, w.g2, w.be2, row_map=row_map, alt=xs_new, want_f32=True, want_stats=save)
-        res = ops.gemm_f32(u2, w.w1, M=rows, N=w.w1.shape[0], K=d, bias=w.b1, act=activation, want_preact=save)
+        res = ops.gemm_f32(u2, w.w1, M=rows, N=w.w1.shape[0], K=d, bias=w.b1, act=activation, want_preact=save,
+                           drop=drop_ff)
         hdn, h_pre = res if save else (res, None)
         x_next = ops.gemm_f32(hdn, w.w2, M=rows, N=d, K=w.w1.shape[0], bias=w.b2, resid=x, row_map=row_map,
-                              resid_alt=xs_new)
+                              resid_alt=xs_new, drop=drop_enc2)
     else:
         _, yp, ln2_stats = ops.ln_rows(x, w.g2, w.be2, row_map=row_map, alt=xs_new, want_planes=True, want_stats=save)
         dff = w.w1.shape[0]
         _, h_pre, hp = ops.gemm_tc(yp, w.w1_planes, M=rows, N=dff, K=d, passes=passes, bias=w.b1, act=activation,
-                                   want_out=False, want_preact=save, want_planes=True)
+                                   want_out=False, want_preact=save, want_planes=True, drop=drop_ff)
         x_next, _, _ = ops.gemm_tc(hp, w.w2_planes, M=rows, N=d, K=dff, passes=passes, bias=w.b2, resid=x,
-                                   row_map=row_map, resid_alt=xs_new)
+                                   row_map=row_map, resid_alt=xs_new, drop=drop_enc2)
     tape = None
     if save:
         tape = LayerTape(sel=sel, row_map=row_map, xs=xs, xs_new=xs_new, kp=kp, qv=qv, o=o, ln1_stats=ln1_stats,
-                         ln2_stats=ln2_stats, attn_stats=attn_stats, h_pre=h_pre, x_in=x, drop=drop)
+                         ln2_stats=ln2_stats, attn_stats=attn_stats, h_pre=h_pre, x_in=x, drop=drop, drop_enc1=drop_enc1,
+                         drop_ff=drop_ff, drop_enc2=drop_enc2)
     return x_next, probs, tape

@@ -277,3 +277,159 @@ def dsmil_pool(q: torch.Tensor, q_max: torch.Tensor, v: torch.Tensor, w_fcc: tor
                                     C, A.data_ptr(), Bm.data_ptr(), logits.data_ptr(), None, ws.data_ptr(), ws_bytes,
                                     _stream()), "snuffy_dsmil_pool_fwd")
     return A, Bm, logits
+
+
+# ------------------------------------------------------------------ backward kernels (csrc/backward.cu, gemm_simt.cu)
+def gemm_f32_batched(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int,
+                     ldc: int, a_kc: bool = True, b_kc: bool = True, alpha: float = 1.0, bias=None, nb_outer: int = 1,
+                     nb_inner: int = 1, sa=(0, 0), sb=(0, 0), sc=(0, 0), ksplit: Optional[int] = None) -> torch.Tensor:
+    """c_z[M, N] = alpha * a_z . b_z^T (+ bias) for every batch z = (outer, inner); operands are addressed from the
+    tensors' data pointers with element strides (outer, inner).  ksplit None = pick one that fills the machine."""
+    nbatch = nb_outer * nb_inner
+    if ksplit is None:
+        ksplit = lib.snuffy_gemm_f32_auto_ksplit(nbatch, M, N, K)
+    ws_bytes = lib.snuffy_gemm_f32_batched_workspace(nbatch, M, N, ksplit)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device) if ws_bytes else None
+    check(lib.snuffy_gemm_f32_batched(a.data_ptr(), lda, 1 if a_kc else 0, b.data_ptr(), ldb, 1 if b_kc else 0, c.data_ptr(),
+                                      ldc, M, N, K, alpha, _ptr(bias), nb_outer, nb_inner, sa[0], sa[1], sb[0], sb[1], sc[0],
+                                      sc[1], ksplit, _ptr(ws), ws_bytes, _stream()), "snuffy_gemm_f32_batched")
+    return c
+
+
+def matmul_nt(a: torch.Tensor, b: torch.Tensor, *, resid=None, alpha: float = 1.0) -> torch.Tensor:
+    """a [M, K] . b [N, K]^T -> [M, N]  (dX = dY . W uses matmul_nn)."""
+    M, K = a.shape
+    return gemm_f32(a, b, M=M, N=b.shape[0], K=K, resid=resid, alpha=alpha)
+
+
+def matmul_nn(a: torch.Tensor, b: torch.Tensor, *, resid=None) -> torch.Tensor:
+    """a [M, K] . b [K, N] -> [M, N]   (dX = dY . W with W = nn.Linear.weight [out, in])."""
+    M, K = a.shape
+    return gemm_f32(a, b, M=M, N=b.shape[1], K=K, b_kc=False, resid=resid)
+
+
+def matmul_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a [R, M]^T . b [R, N] -> [M, N], split over the long R axis   (dW = dY^T X)."""
+    a, b = _f32(a, "a"), _f32(b, "b")
+    R, M = a.shape
+    N = b.shape[1]
+    c = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    return gemm_f32_batched(a, b, c, M=M, N=N, K=R, lda=M, ldb=N, ldc=N, a_kc=False, b_kc=False)
+
+
+def ln_rows_bwd(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, *, dy: Optional[torch.Tensor] = None,
+                dy_bcast: Optional[torch.Tensor] = None, rows_per_bag: int = 1, bscale: float = 1.0, row_map=None,
+                alt=None, add=None, want_dx: bool = True):
+    """LayerNorm backward.  Returns (dx [rows, d] or None, dgamma [d], dbeta [d])."""
+    x = _f32(x, "x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    dev = x.device
+    dx = torch.empty(rows, d, dtype=torch.float32, device=dev) if want_dx else None
+    gb = torch.empty(2, d, dtype=torch.float32, device=dev)
+    blocks = lib.snuffy_ln_rows_bwd_blocks(rows)
+    partials = torch.empty(blocks * 2 * d, dtype=torch.float32, device=dev)
+    if dy is not None:
+        dy = _f32(dy, "dy")
+    if dy_bcast is not None:
+        dy_bcast = _f32(dy_bcast, "dy_bcast")
+    if add is not None:
+        add = _f32(add, "add")
+    check(lib.snuffy_ln_rows_bwd(_ptr(dy), _ptr(dy_bcast), rows_per_bag, float(bscale), x.data_ptr(), _ptr(row_map), _ptr(alt),
+                                 stats.data_ptr(), gamma.data_ptr(), _ptr(add), rows, d, _ptr(dx), gb.data_ptr(),
+                                 partials.data_ptr(), _stream()), "snuffy_ln_rows_bwd")
+    return dx, gb[0], gb[1]
+
+
+def act_bwd(hpre: Optional[torch.Tensor], da: Optional[torch.Tensor], act: str = "none",
+            drop: Tuple[float, int, int] = (0.0, 0, 0), want_dh: bool = True, want_a: bool = False):
+    """(dh, a): dh = da * mask * act'(hpre); a = act(hpre) * mask.  hpre None = dropout mask only."""
+    ref = hpre if hpre is not None else da
+    ref = _f32(ref, "hpre/da")
+    dh = torch.empty_like(ref) if want_dh else None
+    a = torch.empty_like(ref) if want_a else None
+    check(lib.snuffy_act_bwd(_ptr(hpre), _ptr(da), ACT_IDS[act], float(drop[0]), drop[1] & _U64, drop[2] & _U64, ref.numel(),
+                             _ptr(dh), _ptr(a), _stream()), "snuffy_act_bwd")
+    return dh, a
+
+
+def colsum(x: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [rows, d] (row stride allowed), w [rows, C] or None -> [C, d]: out[c] = sum_rows w[row, c] * x[row]."""
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.reshape(-1, x.shape[-1]).contiguous()
+    rows, d = x.shape
+    C = 1 if w is None else w.shape[-1]
+    if w is not None:
+        w = _f32(w.reshape(rows, C), "w")
+    out = torch.empty(C, d, dtype=torch.float32, device=x.device)
+    partials = torch.empty(lib.snuffy_colsum_chunks(rows) * C * d, dtype=torch.float32, device=x.device)
+    check(lib.snuffy_colsum(x.data_ptr(), x.stride(0), _ptr(w), rows, d, C, out.data_ptr(), partials.data_ptr(), _stream()),
+          "snuffy_colsum")
+    return out
+
+
+def attn_rows_bwd(s: torch.Tensor, stats: torch.Tensor, N: int, mode: int, scale: float,
+                  drop: Tuple[float, int, int] = (0.0, 0, 0), pd: Optional[torch.Tensor] = None,
+                  g: Optional[torch.Tensor] = None) -> None:
+    nrows, ksel = s.shape
+    check(lib.snuffy_attn_rows_bwd(s.data_ptr(), stats.data_ptr(), nrows, ksel, N, mode, float(scale), float(drop[0]),
+                                   drop[1] & _U64, drop[2] & _U64, _ptr(pd), _ptr(g), _stream()), "snuffy_attn_rows_bwd")
+
+
+def scatter_add_rows(dx: torch.Tensor, idx: torch.Tensor, src: torch.Tensor) -> None:
+    """dx [B, N, d] (in place) += src [B*K, d] at rows idx [B, K]."""
+    B, N, d = dx.shape
+    K = idx.shape[1]
+    check(lib.snuffy_scatter_add_rows(dx.data_ptr(), idx.data_ptr(), src.data_ptr(), B, N, K, d, _stream()),
+          "snuffy_scatter_add_rows")
+
+
+def sparse_attn_bwd(q: torch.Tensor, v: torch.Tensor, kp: torch.Tensor, d_o: torch.Tensor, stats: torch.Tensor, B: int,
+                    N: int, Ksel: int, h: int, drop: Tuple[float, int, int] = (0.0, 0, 0)):
+    """Backward of O_j = softmax_keys(Q_j Kp_j^T / sqrt(dk))^T V_j  (snuffy.py:160-168).
+
+    q, v: [B*N, d] (row-strided views allowed); kp, d_o: [B*Ksel, d]; stats [B, h, N, 2] from the forward.
+    Returns (dQ [B*N, d], dV [B*N, d], dKp [B*Ksel, d]).  The [B, h, N, Ksel] score tensors are materialised here
+    (recompute, never saved by the forward) and every contraction is one head-batched SIMT GEMM launch."""
+    q, v = _rows_view(q, "q"), _rows_view(v, "v")
+    kp, d_o = _f32(kp, "kp"), _f32(d_o, "d_o")
+    d = kp.shape[-1]
+    dk = d // h
+    dev = q.device
+    ldq, ldv = q.stride(0), v.stride(0)
+    scale = math.sqrt(dk)
+    S = torch.empty(B * h * N, Ksel, dtype=torch.float32, device=dev)
+    Pd = torch.empty_like(S)
+    G = torch.empty_like(S)
+    dq = torch.empty(B * N, d, dtype=torch.float32, device=dev)
+    dv = torch.empty(B * N, d, dtype=torch.float32, device=dev)
+    dkp = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
+    hb = dict(nb_outer=B, nb_inner=h)
+    s_str = (h * N * Ksel, N * Ksel)                    # [B, h, N, Ksel] matrices
+    # S = Q_j Kp_j^T / sqrt(dk)
+    gemm_f32_batched(q, kp, S, M=N, N=Ksel, K=dk, lda=ldq, ldb=d, ldc=Ksel, alpha=1.0 / scale,
+                     sa=(N * ldq, dk), sb=(Ksel * d, dk), sc=s_str, ksplit=1, **hb)
+    attn_rows_bwd(S, stats, N, 0, scale, drop, pd=Pd)
+    # dV_j = P~_j dO_j          [N, dk]   (B operand dO_j stored [key, c]: k-major rows)
+    gemm_f32_batched(Pd, d_o, dv, M=N, N=dk, K=Ksel, lda=Ksel, ldb=d, ldc=d, b_kc=False,
+                     sa=s_str, sb=(Ksel * d, dk), sc=(N * d, dk), ksplit=1, **hb)
+    # G = V_j dO_j^T            [N, Ksel]
+    gemm_f32_batched(v, d_o, G, M=N, N=Ksel, K=dk, lda=ldv, ldb=d, ldc=Ksel,
+                     sa=(N * ldv, dk), sb=(Ksel * d, dk), sc=s_str, ksplit=1, **hb)
+    attn_rows_bwd(S, stats, N, 1, scale, drop, g=G)     # G <- dS
+    # dQ_j = dS_j Kp_j          [N, dk]
+    gemm_f32_batched(G, kp, dq, M=N, N=dk, K=Ksel, lda=Ksel, ldb=d, ldc=d, b_kc=False,
+                     sa=s_str, sb=(Ksel * d, dk), sc=(N * d, dk), ksplit=1, **hb)
+    # dKp_j = dS_j^T Q_j        [Ksel, dk], contraction over the N patches -> split-K
+    gemm_f32_batched(G, q, dkp, M=Ksel, N=dk, K=N, lda=Ksel, ldb=ldq, ldc=d, a_kc=False, b_kc=False,
+                     sa=s_str, sb=(N * ldq, dk), sc=(Ksel * d, dk), **hb)
+    return dq, dv, dkp
+
+
+def softmax_cols_bwd(a: torch.Tensor, da: torch.Tensor, scale: float) -> torch.Tensor:
+    """dS for A = softmax over dim 0 of S / scale (dsmil.py:83-86).  a, da [N, C]."""
+    a, da = _f32(a, "a"), _f32(da, "da")
+    ds = torch.empty_like(a)
+    check(lib.snuffy_softmax_cols_bwd(a.data_ptr(), da.data_ptr(), a.shape[0], a.shape[1], float(scale), ds.data_ptr(),
+                                      _stream()), "snuffy_softmax_cols_bwd")
+    return ds

@@ -53,7 +53,7 @@ def forward_bags(milnet: MILNet, x: torch.Tensor):
     for layer in enc.layers:
         sel = layer.forced_selection if layer.forced_selection is not None else layer.select(classes, state)
         from .autograd import encoder_layer_fn
-        h, attn = encoder_layer_fn(layer, h, sel.to(torch.int64).contiguous())
+        h, attn = encoder_layer_fn(layer, h, sel.to(device=h.device, dtype=torch.int64).contiguous())
     from .autograd import ln_mean_head_fn
     b = milnet.b_classifier
     bag = ln_mean_head_fn(h, enc.norm.weight, enc.norm.bias, b.linear.weight, b.linear.bias)
