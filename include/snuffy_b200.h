@@ -162,6 +162,20 @@ int snuffy_scatter_add_rows(float* dx, const int64_t* idx, const float* src, int
 int snuffy_softmax_cols_bwd(const float* A, const float* dA, int64_t N, int64_t C, float scale, float* dS,
                             snuffy_stream_t stream);
 
+/* ---- training-loop glue on the device (caller side of the path: train.py:828-846, 468-473)                  */
+/* loss = w BCEwL(bag, y) + (1 - w) BCEwL(max_n classes, y), its gradients and the mixed prediction in one launch.
+ * terms: 2*B*C floats, ticket: one zeroed uint32; loss[3] = (mixed, bag term, max term).                        */
+int snuffy_mil_loss(const float* classes, const float* bag, const float* label, const float* weight,
+                    int64_t B, int64_t N, int64_t C, float w, float gscale, float* terms, uint32_t* ticket,
+                    float* loss, float* pred, float* dclasses, float* dbag, snuffy_stream_t stream);
+int64_t snuffy_sumsq_blocks(int64_t n);
+int snuffy_sumsq(const float* x, int64_t n, float* partials, float* out, snuffy_stream_t stream);
+/* torch.optim.AdamW step over flat fp32 buffers (train.py:809-826), gradient pre-scale and optional global-norm
+ * clip (train.py:469-470) folded in.                                                                            */
+int snuffy_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int64_t step, float gscale,
+                      const float* gnorm_sq, float max_norm, snuffy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,10 @@ _SIGNATURES = {
     "snuffy_attn_rows_bwd": (c_int, [P, P, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P]),
     "snuffy_scatter_add_rows": (c_int, [P, P, P, I, I, I, I, P]),
     "snuffy_softmax_cols_bwd": (c_int, [P, P, I, I, c_float, P, P]),
+    "snuffy_mil_loss": (c_int, [P, P, P, P, I, I, I, c_float, c_float, P, P, P, P, P, P, P]),
+    "snuffy_sumsq_blocks": (c_int64, [I]),
+    "snuffy_sumsq": (c_int, [P, I, P, P, P]),
+    "snuffy_adamw_flat": (c_int, [P, P, P, P, I, c_float, c_float, c_float, c_float, c_float, I, c_float, P, c_float, P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

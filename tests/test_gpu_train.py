@@ -1,0 +1,155 @@
+"""Training-loop glue and the data-parallel trainer on the GPU (reference caller
+train.py:828-846, 468-473, 809-826): fused loss vs torch, flat AdamW vs torch.optim.AdamW, the world-1 trajectory vs the
+reference op sequence trained on the CPU in float64, and (when 2 GPUs are visible) NCCL data parallelism."""
+import copy
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import build_snuffy, force_selections, load_golden, load_params, set_precision, snuffy_inputs
+from test_gpu_backward import _params64, mil_loss as ref_mil_loss, ref_forward
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,N,C", [(1, 257, 1), (3, 1000, 2), (2, 10, 3)])
+def test_fused_mil_loss_matches_torch(B, N, C):
+    from snuffy_b200 import dp
+    g = torch.Generator(device="cuda").manual_seed(N)
+    classes = (torch.randn(B, N, C, device="cuda", generator=g) * 2).requires_grad_(True)
+    bag = torch.randn(B, C, device="cuda", generator=g).requires_grad_(True)
+    label = (torch.rand(B, C, device="cuda", generator=g) > 0.5).float()
+    weight = torch.rand(C, device="cuda", generator=g) + 0.5
+    for w, wt in [(0.5, None), (0.3, weight)]:
+        classes.grad = bag.grad = None
+        loss, pred, terms = dp.mil_loss(classes, bag, label, w, wt)
+        (loss * 1.7).backward()
+        c64 = classes.detach().double().requires_grad_(True)
+        b64 = bag.detach().double().requires_grad_(True)
+        wt64 = None if wt is None else wt.double()
+        mx = c64.max(dim=1)[0]
+        lb = F.binary_cross_entropy_with_logits(b64, label.double(), weight=wt64)
+        lm = F.binary_cross_entropy_with_logits(mx, label.double(), weight=wt64)
+        ref = w * lb + (1 - w) * lm
+        (ref * 1.7).backward()
+        assert abs(float(loss) - float(ref)) < 1e-5
+        assert abs(float(terms[0]) - float(lb)) < 1e-5 and abs(float(terms[1]) - float(lm)) < 1e-5
+        assert (classes.grad.double() - c64.grad).abs().max() < 1e-6
+        assert (bag.grad.double() - b64.grad).abs().max() < 1e-6
+        ref_pred = (1 - w) * torch.sigmoid(mx) + w * torch.sigmoid(b64)
+        assert (pred.double() - ref_pred).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("clip", [None, 0.05])
+def test_flat_adamw_matches_torch(clip):
+    from snuffy_b200 import dp
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(37, 29), torch.nn.LayerNorm(29), torch.nn.Linear(29, 3)).cuda()
+    ref = copy.deepcopy(model)
+    flat = dp.FlatBuffers(model.parameters())
+    opt = dp.FlatAdamW(flat, lr=2e-3, betas=(0.5, 0.9), weight_decay=5e-3, clip_grad=clip)
+    ropt = torch.optim.AdamW(ref.parameters(), lr=2e-3, betas=(0.5, 0.9), weight_decay=5e-3)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for step in range(5):
+        x = torch.randn(16, 37, device="cuda", generator=g)
+        flat.zero_grad(); ropt.zero_grad()
+        model(x).square().sum().backward()
+        ref(x).square().sum().backward()
+        if clip is not None:
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=clip)
+        opt.step(); ropt.step()
+        for p, q in zip(model.parameters(), ref.parameters()):
+            assert (p - q).abs().max() < 2e-6, (step, (p - q).abs().max())
+
+
+def test_world1_trainer_follows_the_reference_trajectory():
+    """4 optimizer steps of the reference loop (one bag per step, AdamW lr 2e-4 betas (0.5, 0.9) wd 5e-3: train.py
+    defaults 58, 61, 110) on the CPU in float64 vs DataParallelTrainer at world size 1."""
+    from snuffy_b200 import dp, snuffy
+    z, c = load_golden("bin_rand_gelu")
+    params, _ = snuffy_inputs(c)
+    model = load_params(build_snuffy(snuffy, c), params)
+    for m in model.modules():                       # dropout 0 (train mode would draw the reference's default 0.1)
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    set_precision(model, "fp32")
+    rs = np.random.RandomState(5)
+    n, d = c["n"], c["d"]
+    ksel = len(z["ref32_sel"][0])
+    bags = rs.standard_normal((4, 1, n, d)).astype(np.float32)
+    labels = np.array([1.0, 0.0, 0.0, 1.0], dtype=np.float32)
+    sels = [[rs.permutation(n)[:ksel][None] for _ in range(c["depth"])] for _ in range(4)]
+    trainer = dp.DataParallelTrainer(model, lr=2e-3, betas=(0.5, 0.9), weight_decay=5e-3)
+    P64 = _params64(params)
+    ropt = torch.optim.AdamW(list(P64.values()), lr=2e-3, betas=(0.5, 0.9), weight_decay=5e-3)
+    for i in range(4):
+        force_selections(model, sels[i])
+        loss = trainer.train_step(torch.from_numpy(bags[i]).cuda(), torch.tensor([[labels[i]]]))
+        ropt.zero_grad()
+        c64, bag64 = ref_forward(torch.from_numpy(bags[i]).double(), P64, c["heads"], c["depth"], c["act"],
+                                 [torch.from_numpy(s) for s in sels[i]])
+        rl = ref_mil_loss(c64, bag64, torch.tensor([[labels[i]]]).double())
+        rl.backward()
+        ropt.step()
+        assert abs(float(loss) - float(rl)) < 2e-4, (i, float(loss), float(rl))
+    for name, p in model.named_parameters():
+        assert (p.detach().double().cpu() - P64[name].detach()).abs().max() < 5e-4, name
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from snuffy_b200 import dp, snuffy
+        z, c = load_golden("bin_tiny_relu")
+        params, _ = snuffy_inputs(c)
+        model = load_params(build_snuffy(snuffy, c), params, device=f"cuda:{rank}")
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        set_precision(model, "fp32")
+        trainer = dp.DataParallelTrainer(model, lr=1e-3)
+        rs = np.random.RandomState(11)
+        bags = rs.standard_normal((4, 1, c["n"], c["d"])).astype(np.float32)
+        labels = [1.0, 0.0, 1.0, 0.0]
+        for step in range(2):
+            i = dp.shard_slides(4, rank, world)[step]
+            trainer.train_step(torch.from_numpy(bags[i]).cuda(), torch.tensor([[labels[i]]]))
+        out[rank] = trainer.flat.flat_param.detach().cpu()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_data_parallel_equals_gradient_averaging():
+    """2 ranks x 1 bag per step == one process averaging the two bags' gradients (the DP extension of §8e)."""
+    import torch.multiprocessing as mp
+    from snuffy_b200 import dp, snuffy
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert torch.equal(out[0], out[1])                                  # replicas stay bit-identical
+    z, c = load_golden("bin_tiny_relu")
+    params, _ = snuffy_inputs(c)
+    model = load_params(build_snuffy(snuffy, c), params)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    set_precision(model, "fp32")
+    trainer = dp.DataParallelTrainer(model, lr=1e-3)
+    rs = np.random.RandomState(11)
+    bags = rs.standard_normal((4, 1, c["n"], c["d"])).astype(np.float32)
+    labels = [1.0, 0.0, 1.0, 0.0]
+    for step in range(2):                                               # both bags of a step in ONE process: mean loss over 2
+        ids = [dp.shard_slides(4, r, 2)[step] for r in range(2)]
+        x = torch.from_numpy(np.concatenate([bags[i] for i in ids])).cuda()
+        trainer.train_step(x, torch.tensor([[labels[i]] for i in ids]))
+    assert (trainer.flat.flat_param.cpu() - out[0]).abs().max() < 1e-5
