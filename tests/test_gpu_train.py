@@ -118,10 +118,12 @@ def _dp_worker(rank, world, port, out):
         rs = np.random.RandomState(11)
         bags = rs.standard_normal((4, 1, c["n"], c["d"])).astype(np.float32)
         labels = [1.0, 0.0, 1.0, 0.0]
+        grads = []
         for step in range(2):
             i = dp.shard_slides(4, rank, world)[step]
             trainer.train_step(torch.from_numpy(bags[i]).cuda(), torch.tensor([[labels[i]]]))
-        out[rank] = trainer.flat.flat_param.detach().cpu()
+            grads.append(trainer.flat.flat_grad.detach().cpu() / world)      # after the all-reduce: sum over ranks
+        out[rank] = (trainer.flat.flat_param.detach().cpu(), grads[0])
     finally:
         dist.destroy_process_group()
 
@@ -136,7 +138,7 @@ def test_two_gpu_data_parallel_equals_gradient_averaging():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
-    assert torch.equal(out[0], out[1])                                  # replicas stay bit-identical
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])      # replicas stay bit-identical
     z, c = load_golden("bin_tiny_relu")
     params, _ = snuffy_inputs(c)
     model = load_params(build_snuffy(snuffy, c), params)
@@ -148,8 +150,10 @@ def test_two_gpu_data_parallel_equals_gradient_averaging():
     rs = np.random.RandomState(11)
     bags = rs.standard_normal((4, 1, c["n"], c["d"])).astype(np.float32)
     labels = [1.0, 0.0, 1.0, 0.0]
-    for step in range(2):                                               # both bags of a step in ONE process: mean loss over 2
-        ids = [dp.shard_slides(4, r, 2)[step] for r in range(2)]
-        x = torch.from_numpy(np.concatenate([bags[i] for i in ids])).cuda()
-        trainer.train_step(x, torch.tensor([[labels[i]] for i in ids]))
-    assert (trainer.flat.flat_param.cpu() - out[0]).abs().max() < 1e-5
+    # both bags of step 0 in ONE process (mean loss over the 2 bags) give the averaged gradient.  Parameters after Adam
+    # are not compared: Adam normalises noise-level gradients (e.g. the key-projection bias, identically 0) to +-lr.
+    ids = [dp.shard_slides(4, r, 2)[0] for r in range(2)]
+    x = torch.from_numpy(np.concatenate([bags[i] for i in ids])).cuda()
+    trainer.train_step(x, torch.tensor([[labels[i]] for i in ids]))
+    g1, g2 = trainer.flat.flat_grad.cpu(), out[0][1]
+    assert (g1 - g2).abs().max() < 1e-5 * max(1.0, float(g2.abs().max())), float((g1 - g2).abs().max())
