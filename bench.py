@@ -237,6 +237,33 @@ def kernel_rooflines(model, batch, peaks, device):
     return res
 
 
+# ------------------------------------------------------------------ training step (configs[4]: DP training loop)
+def train_throughput(device, world, steps=6, warm=2):
+    """Train-mode step of the reference loop (train.py:249-264: one bag per optimizer step per process) at cfg2:
+    forward (bf16x3) + fused loss + backward (fp32 SIMT) + one all-reduce of the flat gradient + AdamW.  slides/s over
+    all ranks; CUDA events, max over ranks done by the caller."""
+    from snuffy_b200 import dp
+    model, _ = build_model(device)
+    for layer in model.b_classifier.encoder.layers:
+        layer.return_attn = False
+    trainer = dp.DataParallelTrainer(model, lr=2e-4, betas=(0.5, 0.9), weight_decay=5e-3)     # train.py:58,61,110
+    c = CFG
+    g = torch.Generator(device=device).manual_seed(4321 + int(os.environ.get("RANK", 0)))
+    bags = [torch.randn(1, c["n"], c["d"], device=device, generator=g) for _ in range(8)]      # 8 x 20.5 MB > L2
+    labels = [torch.full((1, c["C"]), float(i & 1), device=device) for i in range(8)]
+    for i in range(warm):
+        trainer.train_step(bags[i & 7], labels[i & 7])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = trainer.train_step(bags[i & 7], labels[i & 7])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return ms, steps, float(loss), trainer.flat.numel * 4
+
+
 # ------------------------------------------------------------------ CPU baseline (port of the reference forward)
 def cpu_baseline(params, max_seconds=25.0, min_slides=2):
     from oracle import torch_port
@@ -303,6 +330,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kernels", action="store_true")
+    ap.add_argument("--skip-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -441,6 +469,20 @@ def main():
            "how": "pinned host bags -> cudaMemcpyAsync on a copy stream -> snuffy.forward_bags -> D2H predictions; "
                   "two buffers, copy of step i+1 overlaps compute of step i; wall clock around the loop"}
 
+    train = None
+    if not args.skip_train:
+        lc0 = lib.snuffy_launch_count()
+        t_ms, t_steps, t_loss, grad_bytes = train_throughput(device, world)
+        if world > 1:
+            t = torch.tensor([t_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        train = {"value": world * t_steps / (t_ms * 1e-3), "unit": "slides/s", "ms_per_step": t_ms / t_steps,
+                 "bags_per_step_per_gpu": 1, "steps": t_steps, "final_loss": t_loss,
+                 "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+                 "launches_per_step": int((lib.snuffy_launch_count() - lc0) / (t_steps + 2)),
+                 "what": "train.py-style step at cfg2 (train mode, attention dropout 0.1): forward bf16x3 + fused MIL loss "
+                         "+ backward (fp32 SIMT) + one flat-gradient all-reduce + flat AdamW"}
     kernels = [] if (args.skip_kernels or rank != 0) else kernel_rooflines(model, B, peaks, device)
     if world > 1:
         dist.barrier()
@@ -459,6 +501,8 @@ def main():
             "clocks": clocks,
             "end_to_end_tensor_frac": (value / world) * F / 1e12 / peaks["tf_sustained"],
         }
+        if train:
+            line["train_step"] = train
         if kernels:
             line["roofline"] = {k: kernels[0][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
             line["roofline"]["kernel"] = kernels[0]["kernel"]

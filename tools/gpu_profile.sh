@@ -2,7 +2,7 @@
 # ncu evidence for one round (B200_PROFILING.md recipe): launch list of a short bench + full captures of the top kernels.
 mkdir -p gpurun_out
 R=${1:-r01}
-BENCH="python bench.py --steps 2 --warmup 3 --no-graph --skip-cpu --skip-kernels"
+BENCH="python bench.py --steps 2 --warmup 3 --no-graph --skip-cpu --skip-kernels --skip-train"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$R.csv $BENCH > gpurun_out/ncu_launch_$R.log 2>&1
 echo "launch list exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 6 -c 3 -f -o gpurun_out/prof_gemm_tc_$R $BENCH > gpurun_out/ncu_gemm_$R.log 2>&1
