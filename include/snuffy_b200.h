@@ -67,6 +67,12 @@ int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt,
                        const float* beta, int64_t rows, int64_t d, int apply_ln, float* out_f32,
                        void* planes, int64_t plane_stride, int plane_rc, float* stats,
                        snuffy_stream_t stream);
+/* Overwrite plane rows b*N + idx[b,k] with split(LN(src[b*K+k])): LN1 and LN2 (snuffy.py:107,110) share one set
+ * of normalised planes, only the Ksel rows changed by the attention sub-layer (snuffy.py:152-155) are redone.
+ * apply_ln everywhere: 0 = convert (optional per-column gain gamma), 1 = LN with affine, 2 = normalise only.     */
+int snuffy_ln_rows_scatter_planes(const float* src, const int64_t* idx, int64_t B, int64_t N, int64_t K,
+                                  int64_t d, const float* gamma, const float* beta, int apply_ln, void* planes,
+                                  int64_t plane_stride, snuffy_stream_t stream);
 /* bag[B,C] = head(mean_n LN_f(x[b,n,:]))   (Encoder.norm + BClassifier: snuffy.py:86 + 71) in one pass.
  * partials: B*chunks*d floats (chunks = snuffy_ln_mean_head_chunks); tickets: B uint32 zeroed once.     */
 int64_t snuffy_ln_mean_head_chunks(int64_t B, int64_t N);

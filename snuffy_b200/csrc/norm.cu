@@ -52,6 +52,8 @@ ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map,
             for (int j = 0; j < 8; ++j) v[it][j] = 0.f;
         }
     }
+    // apply_ln: 0 = plain convert (optionally scaled per column by gamma: folds a LayerNorm gain into a weight),
+    //           1 = LayerNorm with affine, 2 = normalise only (z = (y - mean) * rstd; the affine lives in the weights)
     float mean = 0.f, rstd = 1.f;
     if (apply_ln) {
         mean = warp_sum(sum) / (float)d;
@@ -74,7 +76,7 @@ ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map,
         if (unit < nunits) {
             float u[8];
             if (live && e < d) {
-                if (apply_ln) {
+                if (apply_ln == 1) {
                     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
                     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e + 4));
                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + e));
@@ -83,6 +85,15 @@ ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map,
                     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) u[j] = (v[it][j] - mean) * rstd * g[j] + bb[j];
+                } else if (apply_ln == 2) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u[j] = (v[it][j] - mean) * rstd;
+                } else if (gamma) {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e));
+                    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e + 4));
+                    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u[j] = v[it][j] * g[j];
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) u[j] = v[it][j];
@@ -138,52 +149,72 @@ ln_rows_scalar_kernel(const float* __restrict__ x, const int32_t* __restrict__ r
         if (stats && lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
     }
     for (int e = lane; e < d; e += 32)
-        out_f32[row * (int64_t)d + e] = apply_ln ? (src[e] - mean) * rstd * gamma[e] + beta[e] : src[e];
+        out_f32[row * (int64_t)d + e] = apply_ln == 1 ? (src[e] - mean) * rstd * gamma[e] + beta[e]
+                                      : apply_ln == 2 ? (src[e] - mean) * rstd : (gamma ? src[e] * gamma[e] : src[e]);
+}
+
+// Re-normalise K scattered rows in place inside an existing plane set: row k of `src` [B*K, d] (the updated selected
+// rows X_S') goes to plane row b*N + idx[b, k].  Lets LN1 and LN2 share one set of z planes: only the Ksel rows the
+// attention sub-layer changed are rewritten (snuffy.py:152-155 + 110) instead of a second pass over all N rows.
+__global__ void __launch_bounds__(256)
+ln_rows_scatter_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t N, int64_t K, int64_t total,
+                       int d, const float* __restrict__ gamma, const float* __restrict__ beta, int apply_ln,
+                       __nv_bfloat16* __restrict__ planes, int64_t plane_stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t slot = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (slot >= total) return;
+    const int64_t r = idx[slot];
+    if (r < 0 || r >= N) return;
+    const int64_t dst = (slot / K) * N + r;
+    const float* s = src + slot * (int64_t)d;
+    float mean = 0.f, rstd = 1.f;
+    if (apply_ln) {
+        float sum = 0.f;
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(s + e));
+            sum += (a.x + a.y) + (a.z + a.w);
+        }
+        mean = warp_sum(sum) / (float)d;
+        float sq = 0.f;
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(s + e));
+            const float t0 = a.x - mean, t1 = a.y - mean, t2 = a.z - mean, t3 = a.w - mean;
+            sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+        }
+        rstd = rsqrtf(warp_sum(sq) / (float)d + LN_EPS);
+    }
+    const int nunits = (int)plane_kblocks(d) * 4;
+    for (int unit = lane; unit < nunits; unit += 32) {
+        const int e = unit * 8;
+        bf16x8 h, l;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float u = 0.f;
+            if (e + j < d) {
+                u = s[e + j];
+                if (apply_ln) u = (u - mean) * rstd;
+                if (apply_ln == 1) u = u * gamma[e + j] + beta[e + j];
+            }
+            split_bf16(u, h.v[j], l.v[j]);
+        }
+        const int64_t off = plane_unit_offset(dst, e, d, 128);
+        *reinterpret_cast<bf16x8*>(planes + off) = h;
+        *reinterpret_cast<bf16x8*>(planes + plane_stride + off) = l;
+    }
 }
 
 // ------------------------------------------------------------------ final LN + mean + head
 // grid (chunks, B).  Each CTA normalises its rows (warp per row), sums the normalised rows,
 // writes one partial [d] and takes a ticket; the last CTA of the bag folds the partials in a
 // fixed order, applies the affine (mean(z*g+b) = g*mean(z)+b), divides by N and runs the C x d head.
-__global__ void __launch_bounds__(256)
-ln_mean_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const float* __restrict__ Wh, const float* __restrict__ bh, int64_t N, int d, int C,
-                    float* __restrict__ partials, unsigned int* __restrict__ tickets, float* __restrict__ stats,
-                    float* __restrict__ pooled, float* __restrict__ bag_out) {
-    extern __shared__ __align__(16) float hs[];            // [8 warps][d] then reused
+// tail shared by both variants: write this CTA's partial, take a ticket, the last CTA of the bag folds + runs the head
+__device__ __forceinline__ void ln_mean_head_tail(float* hs, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  const float* __restrict__ Wh, const float* __restrict__ bh, int64_t N, int d,
+                                                  int C, float* __restrict__ partials, unsigned int* __restrict__ tickets,
+                                                  float* __restrict__ pooled, float* __restrict__ bag_out) {
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = gridDim.x, chunk = blockIdx.x, bag = blockIdx.y;
-    const int64_t per = (N + chunks - 1) / chunks;
-    const int64_t r0 = chunk * per, r1 = min(N, r0 + per);
-    const float* xb = x + (int64_t)bag * N * d;
-    float* wacc = hs + (size_t)warp * d;
-    for (int e = lane; e < d; e += 32) wacc[e] = 0.f;
-    for (int64_t r = r0 + warp; r < r1; r += 8) {
-        const float* src = xb + r * d;
-        float sum = 0.f;
-        for (int e = lane * 4; e < d; e += 128) {
-            const float4 a = ld_stream(reinterpret_cast<const float4*>(src + e));
-            sum += (a.x + a.y) + (a.z + a.w);
-        }
-        const float mean = warp_sum(sum) / (float)d;
-        float sq = 0.f;
-        for (int e = lane * 4; e < d; e += 128) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));   // L1/L2 hit
-            const float t0 = a.x - mean, t1 = a.y - mean, t2 = a.z - mean, t3 = a.w - mean;
-            sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
-        }
-        const float rstd = rsqrtf(warp_sum(sq) / (float)d + LN_EPS);
-        if (stats && lane == 0) { stats[((int64_t)bag * N + r) * 2] = mean; stats[((int64_t)bag * N + r) * 2 + 1] = rstd; }
-        for (int e = lane * 4; e < d; e += 128) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));
-            float4 w = *reinterpret_cast<float4*>(wacc + e);
-            w.x += (a.x - mean) * rstd; w.y += (a.y - mean) * rstd;
-            w.z += (a.z - mean) * rstd; w.w += (a.w - mean) * rstd;
-            *reinterpret_cast<float4*>(wacc + e) = w;
-        }
-    }
-    __syncthreads();
     float* part = partials + ((int64_t)bag * chunks + chunk) * d;
     for (int e = threadIdx.x; e < d; e += blockDim.x) {
         float s = 0.f;
@@ -218,6 +249,112 @@ ln_mean_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma
     }
 }
 
+// d <= MAXIT * 128: the row and the column accumulators live in registers (one 128-bit load per element, two rows in
+// flight per warp); the generic kernel below re-reads the row from L1 and accumulates in shared memory.
+template <int MAXIT>
+__global__ void __launch_bounds__(256)
+ln_mean_head_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const float* __restrict__ Wh, const float* __restrict__ bh, int64_t N, int d, int C,
+                        float* __restrict__ partials, unsigned int* __restrict__ tickets, float* __restrict__ stats,
+                        float* __restrict__ pooled, float* __restrict__ bag_out) {
+    extern __shared__ __align__(16) float hs[];            // [8 warps][d]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = gridDim.x, chunk = blockIdx.x, bag = blockIdx.y;
+    const int64_t per = (N + chunks - 1) / chunks;
+    const int64_t r0 = chunk * per, r1 = min(N, r0 + per);
+    const float* xb = x + (int64_t)bag * N * d;
+    const float inv_d = 1.f / (float)d;
+    float4 acc[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + warp; r < r1; r += 16) {
+        const bool two = r + 8 < r1;
+        float4 a[MAXIT], b[MAXIT];
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int e = (it * 32 + lane) * 4;
+            a[it] = e < d ? ld_stream(reinterpret_cast<const float4*>(xb + r * d + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            b[it] = (two && e < d) ? ld_stream(reinterpret_cast<const float4*>(xb + (r + 8) * d + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            sa += (a[it].x + a[it].y) + (a[it].z + a[it].w);
+            sb += (b[it].x + b[it].y) + (b[it].z + b[it].w);
+        }
+        const float ma = warp_sum(sa) * inv_d, mb = warp_sum(sb) * inv_d;
+        float qa = 0.f, qb = 0.f;
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            if ((it * 32 + lane) * 4 < d) {
+                a[it].x -= ma; a[it].y -= ma; a[it].z -= ma; a[it].w -= ma;
+                b[it].x -= mb; b[it].y -= mb; b[it].z -= mb; b[it].w -= mb;
+                qa += (a[it].x * a[it].x + a[it].y * a[it].y) + (a[it].z * a[it].z + a[it].w * a[it].w);
+                qb += (b[it].x * b[it].x + b[it].y * b[it].y) + (b[it].z * b[it].z + b[it].w * b[it].w);
+            }
+        }
+        const float ra = rsqrtf(warp_sum(qa) * inv_d + LN_EPS);
+        const float rb = two ? rsqrtf(warp_sum(qb) * inv_d + LN_EPS) : 0.f;
+        if (stats && lane == 0) {
+            stats[((int64_t)bag * N + r) * 2] = ma; stats[((int64_t)bag * N + r) * 2 + 1] = ra;
+            if (two) { stats[((int64_t)bag * N + r + 8) * 2] = mb; stats[((int64_t)bag * N + r + 8) * 2 + 1] = rb; }
+        }
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            acc[it].x += a[it].x * ra + b[it].x * rb; acc[it].y += a[it].y * ra + b[it].y * rb;
+            acc[it].z += a[it].z * ra + b[it].z * rb; acc[it].w += a[it].w * ra + b[it].w * rb;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+        const int e = (it * 32 + lane) * 4;
+        if (e < d) *reinterpret_cast<float4*>(hs + (size_t)warp * d + e) = acc[it];
+    }
+    __syncthreads();
+    ln_mean_head_tail(hs, gamma, beta, Wh, bh, N, d, C, partials, tickets, pooled, bag_out);
+}
+
+__global__ void __launch_bounds__(256)
+ln_mean_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ Wh, const float* __restrict__ bh, int64_t N, int d, int C,
+                    float* __restrict__ partials, unsigned int* __restrict__ tickets, float* __restrict__ stats,
+                    float* __restrict__ pooled, float* __restrict__ bag_out) {
+    extern __shared__ __align__(16) float hs[];            // [8 warps][d] then reused
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = gridDim.x, chunk = blockIdx.x, bag = blockIdx.y;
+    const int64_t per = (N + chunks - 1) / chunks;
+    const int64_t r0 = chunk * per, r1 = min(N, r0 + per);
+    const float* xb = x + (int64_t)bag * N * d;
+    float* wacc = hs + (size_t)warp * d;
+    for (int e = lane; e < d; e += 32) wacc[e] = 0.f;
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+        const float* src = xb + r * d;
+        float sum = 0.f;
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = ld_stream(reinterpret_cast<const float4*>(src + e));
+            sum += (a.x + a.y) + (a.z + a.w);
+        }
+        const float mean = warp_sum(sum) / (float)d;
+        float sq = 0.f;
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));   // L1/L2 hit
+            const float t0 = a.x - mean, t1 = a.y - mean, t2 = a.z - mean, t3 = a.w - mean;
+            sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)d + LN_EPS);
+        if (stats && lane == 0) { stats[((int64_t)bag * N + r) * 2] = mean; stats[((int64_t)bag * N + r) * 2 + 1] = rstd; }
+        for (int e = lane * 4; e < d; e += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + e));
+            float4 w = *reinterpret_cast<float4*>(wacc + e);
+            w.x += (a.x - mean) * rstd; w.y += (a.y - mean) * rstd;
+            w.z += (a.z - mean) * rstd; w.w += (a.w - mean) * rstd;
+            *reinterpret_cast<float4*>(wacc + e) = w;
+        }
+    }
+    __syncthreads();
+    ln_mean_head_tail(hs, gamma, beta, Wh, bh, N, d, C, partials, tickets, pooled, bag_out);
+}
+
 }  // namespace snuffy
 
 using namespace snuffy;
@@ -233,7 +370,8 @@ int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt,
                        const float* beta, int64_t rows, int64_t d, int apply_ln, float* out_f32, void* planes,
                        int64_t plane_stride, int plane_rc, float* stats, cudaStream_t stream) {
     SNUFFY_REQUIRE(x && rows >= 0 && d > 0, "snuffy_ln_rows_fwd: bad arguments");
-    SNUFFY_REQUIRE(!apply_ln || (gamma && beta), "snuffy_ln_rows_fwd: LayerNorm needs gamma and beta");
+    SNUFFY_REQUIRE(apply_ln >= 0 && apply_ln <= 2, "snuffy_ln_rows_fwd: apply_ln must be 0, 1 or 2");
+    SNUFFY_REQUIRE(apply_ln != 1 || (gamma && beta), "snuffy_ln_rows_fwd: LayerNorm needs gamma and beta");
     SNUFFY_REQUIRE(!row_map || alt, "snuffy_ln_rows_fwd: row_map given without the replacement rows");
     SNUFFY_REQUIRE(!planes || plane_rc == 128 || plane_rc == 256, "snuffy_ln_rows_fwd: plane_rc must be 128 or 256");
     if (rows == 0) return 0;
@@ -267,6 +405,22 @@ int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt,
     return check_launch("snuffy_ln_rows_fwd");
 }
 
+// planes rows b*N + idx[b,k] <- split(LN(src[b*K + k]))   (apply_ln as in snuffy_ln_rows_fwd; A-operand planes, RC = 128)
+int snuffy_ln_rows_scatter_planes(const float* src, const int64_t* idx, int64_t B, int64_t N, int64_t K, int64_t d,
+                                  const float* gamma, const float* beta, int apply_ln, void* planes, int64_t plane_stride,
+                                  cudaStream_t stream) {
+    SNUFFY_REQUIRE(src && idx && planes && B >= 1 && N >= 1 && K >= 0, "snuffy_ln_rows_scatter_planes: bad arguments");
+    SNUFFY_REQUIRE(d % 8 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)planes % 16 == 0 && plane_stride % 8 == 0,
+                   "snuffy_ln_rows_scatter_planes: needs d %% 8 == 0 and 16-byte aligned buffers");
+    SNUFFY_REQUIRE(apply_ln >= 0 && apply_ln <= 2 && (apply_ln != 1 || (gamma && beta)),
+                   "snuffy_ln_rows_scatter_planes: bad LayerNorm mode");
+    if (K == 0) return 0;
+    const int64_t total = B * K;
+    ln_rows_scatter_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(
+        src, idx, N, K, total, (int)d, gamma, beta, apply_ln, reinterpret_cast<__nv_bfloat16*>(planes), plane_stride);
+    return check_launch("snuffy_ln_rows_scatter_planes");
+}
+
 // workspace floats needed by snuffy_ln_mean_head_fwd (partials) -- tickets are B uint32 (zeroed once by the caller)
 int64_t snuffy_ln_mean_head_chunks(int64_t B, int64_t N) {
     int64_t chunks = (2 * (int64_t)sm_count() + B - 1) / (B > 0 ? B : 1);
@@ -289,8 +443,20 @@ int snuffy_ln_mean_head_fwd(const float* x, const float* gamma, const float* bet
     if (smem > 48 * 1024)
         SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)chunks, (unsigned)B);
-    ln_mean_head_kernel<<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
-                                                     stats, pooled, bag_out);
+    if (d <= 512) {
+        if (smem > 48 * 1024)
+            SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_reg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ln_mean_head_reg_kernel<4><<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
+                                                                stats, pooled, bag_out);
+    } else if (d <= 1024) {
+        if (smem > 48 * 1024)
+            SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ln_mean_head_reg_kernel<8><<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
+                                                                stats, pooled, bag_out);
+    } else {
+        ln_mean_head_kernel<<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
+                                                         stats, pooled, bag_out);
+    }
     return check_launch("snuffy_ln_mean_head_fwd");
 }
 

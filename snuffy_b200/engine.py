@@ -27,6 +27,8 @@ from .ops import Planes
 PRECISIONS = ("bf16x3", "fp32", "bf16x1")
 #: use the tcgen05 attention kernel when the shape allows (SNUFFY_B200_ATTN=simt forces the fp32 SIMT kernel)
 ATTN_TC = os.environ.get("SNUFFY_B200_ATTN", "tc") != "simt"
+#: share one set of normalised operand planes between LN1 and LN2 in inference (SNUFFY_B200_SHARE_Z=0 disables)
+SHARE_Z = os.environ.get("SNUFFY_B200_SHARE_Z", "1") != "0"
 
 
 def default_precision() -> str:
@@ -153,6 +155,11 @@ class LayerWeights:
     w2_planes: Optional[Planes] = None
     wk_planes: Optional[Planes] = None
     wo_planes: Optional[Planes] = None
+    # LayerNorm affine folded into the consumers of the shared z planes:  LN(y) W^T + b = z (W * gamma)^T + (b + W beta)
+    wqv_fold_planes: Optional[Planes] = None
+    bqv_fold: Optional[torch.Tensor] = None
+    w1_fold_planes: Optional[Planes] = None
+    b1_fold: Optional[torch.Tensor] = None
 
     def prepare(self, precision: str) -> None:
         if self.wqv is None:
@@ -165,6 +172,15 @@ class LayerWeights:
             self.w2_planes = ops.weight_planes(self.w2.detach())
             self.wk_planes = ops.weight_planes(self.wk.detach())
             self.wo_planes = ops.weight_planes(self.wo.detach())
+
+    def prepare_folded(self) -> None:
+        if self.wqv_fold_planes is None:
+            d = self.wq.shape[1]
+            self.wqv_fold_planes = ops.weight_planes(self.wqv, col_gain=self.g1)
+            self.bqv_fold = ops.gemm_f32(self.be1.view(1, d), self.wqv, M=1, N=self.wqv.shape[0], K=d, bias=self.bqv).view(-1)
+            self.w1_fold_planes = ops.weight_planes(self.w1.detach(), col_gain=self.g2)
+            self.b1_fold = ops.gemm_f32(self.be2.view(1, d), self.w1.detach(), M=1, N=self.w1.shape[0], K=d,
+                                        bias=self.b1).view(-1)
 
 
 @dataclass
@@ -208,6 +224,9 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         precision = "fp32"                                   # tcgen05 planes need d % 8 == 0; still the CUDA path
     w.prepare(precision)
     passes = 1 if precision == "bf16x1" else 3
+    # Inference shares ONE set of normalised planes z = (x - mean) * rstd between LN1 and LN2 (their affines are folded
+    # into the weights); the training tape keeps the two LayerNorms separate (their statistics are saved per sub-layer).
+    share_z = SHARE_Z and precision != "fp32" and not save
 
     xs = ops.gather_rows(x.view(B, N, d), sel).view(B * Ksel, d)            # raw keys (App. B-1)
     row_map = ops.build_row_map(sel, N)
@@ -218,10 +237,16 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         u, _, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_f32=True, want_stats=save)
         qv = ops.gemm_f32(u, w.wqv, M=rows, N=2 * d, K=d, bias=w.bqv)
     else:
-        _, up, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_planes=True, want_stats=save)
+        if share_z:
+            w.prepare_folded()
+            _, up, ln1_stats = ops.ln_rows(x, None, None, want_planes=True, affine=False)
+            wqv_p, bqv = w.wqv_fold_planes, w.bqv_fold
+        else:
+            _, up, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_planes=True, want_stats=save)
+            wqv_p, bqv = w.wqv_planes, w.bqv
         attn_tc = ATTN_TC and ops.sparse_attn_tc_supported(B, N, Ksel, heads, d)
         # the projection writes Q|V straight as the planes the tensor-core attention consumes (fp32 only if saved)
-        qv, _, qvp = ops.gemm_tc(up, w.wqv_planes, M=rows, N=2 * d, K=d, passes=passes, bias=w.bqv,
+        qv, _, qvp = ops.gemm_tc(up, wqv_p, M=rows, N=2 * d, K=d, passes=passes, bias=bqv,
                                  want_out=save or not attn_tc, want_planes=attn_tc)
     small_tc = precision != "fp32" and B * Ksel >= 256          # [B*Ksel, d] projections: tensor cores once they fill tiles
     if small_tc:
@@ -255,9 +280,14 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         x_next = ops.gemm_f32(hdn, w.w2, M=rows, N=d, K=w.w1.shape[0], bias=w.b2, resid=x, row_map=row_map,
                               resid_alt=xs_new, drop=drop_enc2)
     else:
-        _, yp, ln2_stats = ops.ln_rows(x, w.g2, w.be2, row_map=row_map, alt=xs_new, want_planes=True, want_stats=save)
+        if share_z:
+            ops.ln_rows_scatter_planes(xs_new, sel, N, up)          # only the Ksel rows changed: y[S] = X_S'
+            yp, w1_p, b1, ln2_stats = up, w.w1_fold_planes, w.b1_fold, None
+        else:
+            _, yp, ln2_stats = ops.ln_rows(x, w.g2, w.be2, row_map=row_map, alt=xs_new, want_planes=True, want_stats=save)
+            w1_p, b1 = w.w1_planes, w.b1
         dff = w.w1.shape[0]
-        _, h_pre, hp = ops.gemm_tc(yp, w.w1_planes, M=rows, N=dff, K=d, passes=passes, bias=w.b1, act=activation,
+        _, h_pre, hp = ops.gemm_tc(yp, w1_p, M=rows, N=dff, K=d, passes=passes, bias=b1, act=activation,
                                    want_out=False, want_preact=save, want_planes=True, drop=drop_ff)
         x_next, _, _ = ops.gemm_tc(hp, w.w2_planes, M=rows, N=d, K=dff, passes=passes, bias=w.b2, resid=x,
                                    row_map=row_map, resid_alt=xs_new, drop=drop_enc2)

@@ -117,8 +117,9 @@ def build_row_map(idx: torch.Tensor, N: int) -> torch.Tensor:
 def ln_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], *,
             row_map: Optional[torch.Tensor] = None, alt: Optional[torch.Tensor] = None, apply_ln: bool = True,
             want_f32: bool = False, want_planes: bool = False, plane_rc: int = 128, want_stats: bool = False,
-            zero_planes: bool = False):
-    """LN over the rows of y = x-with-mapped-rows-replaced.  Returns (fp32 or None, Planes or None, stats or None)."""
+            zero_planes: bool = False, affine: bool = True):
+    """LN over the rows of y = x-with-mapped-rows-replaced.  Returns (fp32 or None, Planes or None, stats or None).
+    apply_ln=False: plain convert (a given `gamma` scales the columns); affine=False: normalise only (z)."""
     x = _f32(x, "x")
     d = x.shape[-1]
     rows = x.numel() // d
@@ -126,9 +127,19 @@ def ln_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch
     planes = Planes(rows, d, plane_rc, x.device, zero=zero_planes) if want_planes else None
     stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device) if want_stats else None
     check(lib.snuffy_ln_rows_fwd(x.data_ptr(), _ptr(row_map), _ptr(alt), _ptr(gamma), _ptr(beta), rows, d,
-                                 1 if apply_ln else 0, _ptr(out), planes.ptr if planes else None,
+                                 (1 if affine else 2) if apply_ln else 0, _ptr(out), planes.ptr if planes else None,
                                  planes.stride if planes else 0, plane_rc, _ptr(stats), _stream()), "snuffy_ln_rows_fwd")
     return out, planes, stats
+
+
+def ln_rows_scatter_planes(src: torch.Tensor, idx: torch.Tensor, N: int, planes: Planes, gamma=None, beta=None,
+                           apply_ln: bool = True, affine: bool = False) -> None:
+    """planes rows b*N + idx[b, k] <- split(LN(src[b*K + k]))  (in place; src [B*K, d], idx [B, K])."""
+    src = _f32(src, "src")
+    B, K = idx.shape
+    mode = (1 if affine else 2) if apply_ln else 0
+    check(lib.snuffy_ln_rows_scatter_planes(src.data_ptr(), idx.data_ptr(), B, N, K, src.shape[-1], _ptr(gamma), _ptr(beta),
+                                            mode, planes.ptr, planes.stride, _stream()), "snuffy_ln_rows_scatter_planes")
 
 
 _HEAD_WS = {}
@@ -180,12 +191,13 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias=None, act: str = "non
     return gemm_f32(x, weight, M=rows, N=weight.shape[0], K=K, bias=bias, act=act, resid=resid, drop=drop)
 
 
-def weight_planes(weight: torch.Tensor) -> Planes:
-    """Split an nn.Linear weight [N, K] into B-operand planes (zero padded to the kernel's BLOCK_N)."""
+def weight_planes(weight: torch.Tensor, col_gain: Optional[torch.Tensor] = None) -> Planes:
+    """Split an nn.Linear weight [N, K] into B-operand planes (zero padded to the kernel's BLOCK_N).  `col_gain` [K]
+    scales the columns first (W * gamma: a LayerNorm gain folded into the weight that consumes the normalised rows)."""
     weight = _f32(weight, "weight")
     n = weight.shape[0]
     rc = lib.snuffy_gemm_tc_block_n(n)
-    _, planes, _ = ln_rows(weight, None, None, apply_ln=False, want_planes=True, plane_rc=rc, zero_planes=True)
+    _, planes, _ = ln_rows(weight, col_gain, None, apply_ln=False, want_planes=True, plane_rc=rc, zero_planes=True)
     return planes
 
 
