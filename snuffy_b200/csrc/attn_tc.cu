@@ -42,6 +42,8 @@ struct AttnTcParams {
     const float* Kp;                  // [B*Ksel, d]
     int B, N, Ksel, KP, h, dk, d;
     int splits, tiles_per_split;
+    int nkc, KC;                      // key chunks per (bag, head) and keys per chunk (KC % 16 == 0; KP = padded chunk size)
+    float* stats_part;                // [nkc][B, h, N, 2] per-chunk (row max of raw scores, sum of exp2): MODE 1 -> MODE 2
     float c_log2;                     // log2(e) / sqrt(dk)
     float* O_part;                    // [splits, B*Ksel, d]
     float* P_out;                     // [B, h, N, Ksel] or null (pre-dropout)
@@ -49,6 +51,10 @@ struct AttnTcParams {
     float drop_p; uint64_t seed, offset;
 };
 
+// MODE 0: all keys of a head fit one chunk (Ksel <= 256): scores, softmax and P^T V fused in one pass.
+// MODE 1: several key chunks, pass 1: per-chunk row statistics only (no P, no V, no O).
+// MODE 2: several key chunks, pass 2: merge the chunk statistics, P for this chunk, O[chunk keys] += P^T V.
+template <int MODE>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const AttnTcParams p) {
     extern __shared__ __align__(1024) unsigned char at_smem[];
@@ -88,14 +94,17 @@ attn_tc_kernel(const AttnTcParams p) {
     const int ksteps = dk / 16;
     const int chunks_per_head = dk / PLANE_KB;
     const int64_t chunk_elems = (int64_t)AT_TILE * PLANE_KB;
-    const int items = p.B * p.h * p.splits;
+    const int items = p.B * p.h * p.nkc * p.splits;
     uint32_t it = 0;          // tiles processed by this CTA so far (every role counts the same sequence)
     uint32_t item_no = 0;
 
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_no) {
         const int split = item % p.splits;
-        const int j = (item / p.splits) % p.h;
-        const int b = item / (p.splits * p.h);
+        const int kc = (item / p.splits) % p.nkc;
+        const int j = (item / (p.splits * p.nkc)) % p.h;
+        const int b = item / (p.splits * p.nkc * p.h);
+        const int key0 = kc * p.KC;                                         // first key of this chunk
+        const int kvalid = min(p.KC, p.Ksel - key0);                        // keys of this chunk (the rest of KP is padding)
         const int64_t g_lo = (int64_t)b * p.N, g_hi = g_lo + p.N;           // global rows of this bag
         const int64_t t_first = g_lo / AT_TILE, t_last = (g_hi + AT_TILE - 1) / AT_TILE;
         const int64_t t0 = t_first + (int64_t)split * p.tiles_per_split;
@@ -109,8 +118,8 @@ attn_tc_kernel(const AttnTcParams p) {
             for (int idx = threadIdx.x - 64; idx < units; idx += AT_THREADS - 64) {
                 const int key = idx % KP, kg = idx / KP;
                 bf16x8 hi, lo;
-                if (key < p.Ksel) {
-                    const float* src = p.Kp + ((int64_t)b * p.Ksel + key) * p.d + j * dk + kg * 8;
+                if (key < kvalid) {
+                    const float* src = p.Kp + ((int64_t)b * p.Ksel + key0 + key) * p.d + j * dk + kg * 8;
                     const float4 a = __ldg(reinterpret_cast<const float4*>(src));
                     const float4 c = __ldg(reinterpret_cast<const float4*>(src + 4));
                     const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
@@ -139,11 +148,13 @@ attn_tc_kernel(const AttnTcParams p) {
                     bulk_g2s(smem_u32(sQ), qsrc, QV_PLANE, q_full);
                     bulk_g2s(smem_u32(sQ) + QV_PLANE, qsrc + p.plane_stride, QV_PLANE, q_full);
                 }
-                mbar_wait(v_empty, (it & 1) ^ 1);
-                if (lane == 0) {
-                    mbar_expect_tx(v_full, 2 * QV_PLANE);
-                    bulk_g2s(smem_u32(sV), vsrc, QV_PLANE, v_full);
-                    bulk_g2s(smem_u32(sV) + QV_PLANE, vsrc + p.plane_stride, QV_PLANE, v_full);
+                if (MODE != 1) {
+                    mbar_wait(v_empty, (it & 1) ^ 1);
+                    if (lane == 0) {
+                        mbar_expect_tx(v_full, 2 * QV_PLANE);
+                        bulk_g2s(smem_u32(sV), vsrc, QV_PLANE, v_full);
+                        bulk_g2s(smem_u32(sV) + QV_PLANE, vsrc + p.plane_stride, QV_PLANE, v_full);
+                    }
                 }
                 __syncwarp();
             }
@@ -192,11 +203,13 @@ attn_tc_kernel(const AttnTcParams p) {
                     tc_commit(s_full);
                 }
                 __syncwarp();
-                if (t > 0) mma2(it - 1, t == 1);
+                if (MODE != 1 && t > 0) mma2(it - 1, t == 1);
             }
-            if (ntiles > 0) mma2(it - 1, ntiles == 1);
-            if (lane == 0) tc_commit(o_full);
-            __syncwarp();
+            if (MODE != 1) {
+                if (ntiles > 0) mma2(it - 1, ntiles == 1);
+                if (lane == 0) tc_commit(o_full);
+                __syncwarp();
+            }
         } else {
             // ------------------------------------------------ softmax warps.  Thread = one query row of the tile;
             // the two warps of a TMEM lane quadrant split the key chunks and exchange (max, sum) through smem.
@@ -210,46 +223,76 @@ attn_tc_kernel(const AttnTcParams p) {
                 const int64_t g = (t0 + t) * AT_TILE + rr;
                 const bool valid = g >= g_lo && g < g_hi;
                 const int n = (int)(g - g_lo);
+                const int64_t srow = ((int64_t)b * p.h + j) * p.N + n;      // row of the [B, h, N, *] statistics
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
-                float mx = -INFINITY;
-                for (int c = c_lo; c < c_hi; ++c) {
-                    float v[32];
-                    tc_ld32(lane_addr + (uint32_t)(c * 32), v);
-                    if (c * 32 + 32 <= p.Ksel) {
+                float mx = -INFINITY, inv = 0.f, mc = 0.f;
+                if (MODE != 2) {
+                    // ---- pass 1: row max over this warp's key chunks
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        float v[32];
+                        tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+                        if (c * 32 + 32 <= kvalid) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) mx = fmaxf(mx, v[e]);
+                            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, v[e]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) mx = fmaxf(mx, v[e]);
+                        }
+                    }
+                    sRed[(it & 1) * 512 + half * 128 + rr] = mx;
+                    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                    mx = fmaxf(mx, sRed[(it & 1) * 512 + (half ^ 1) * 128 + rr]);
+                    if (!valid) mx = 0.f;
+                    // rows of a neighbouring bag / padding: exp2(s*c - inf) = 0 -> P = 0 exactly (never inf * 0 = NaN)
+                    mc = valid ? mx * p.c_log2 : INFINITY;
+                    // ---- pass 2: exp ONCE per score (the XU pipe is the limiter); MODE 0 parks it in TMEM over S
+                    float sum = 0.f;
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        float v[32];
+                        tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+                        const bool full = c * 32 + 32 <= kvalid;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const float ee = ex2_approx(fmaf(v[e], p.c_log2, -mc));
+                            v[e] = (full || c * 32 + e < kvalid) ? ee : 0.f;
+                            sum += v[e];
+                        }
+                        if (MODE == 0) tc_st32(lane_addr + (uint32_t)(c * 32), v);
+                    }
+                    if (MODE == 0) tc_wait_st();
+                    sRed[(it & 1) * 512 + 256 + half * 128 + rr] = sum;
+                    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                    sum += sRed[(it & 1) * 512 + 256 + (half ^ 1) * 128 + rr];
+                    if (MODE == 1) {
+                        // per-chunk partial statistics for pass 2 (raw-score max, sum of exp2 relative to it)
+                        if (valid && half == 0) {
+                            float* sp = p.stats_part + ((int64_t)kc * p.B * p.h * p.N + srow) * 2;
+                            sp[0] = mx; sp[1] = sum;
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(s_empty);
+                        continue;
+                    }
+                    inv = valid ? 1.f / sum : 0.f;
+                } else {
+                    // ---- merge the chunk statistics of this row (written by the MODE 1 launch)
+                    float lsum = 0.f;
+                    if (valid) {
+                        const float* sp = p.stats_part + srow * 2;
+                        const int64_t cs = (int64_t)p.B * p.h * p.N * 2;
+                        for (int c2 = 0; c2 < p.nkc; ++c2) mx = fmaxf(mx, __ldcg(sp + c2 * cs));
+                        for (int c2 = 0; c2 < p.nkc; ++c2)
+                            lsum += __ldcg(sp + c2 * cs + 1) * ex2_approx((__ldcg(sp + c2 * cs) - mx) * p.c_log2);
+                        inv = 1.f / lsum;
                     } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) mx = fmaxf(mx, v[e]);
+                        mx = 0.f;
                     }
+                    mc = valid ? mx * p.c_log2 : INFINITY;
                 }
-                sRed[(it & 1) * 512 + half * 128 + rr] = mx;
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                mx = fmaxf(mx, sRed[(it & 1) * 512 + (half ^ 1) * 128 + rr]);
-                if (!valid) mx = 0.f;                        // padding rows may hold anything, incl. NaN
-                const float mc = mx * p.c_log2;
-                float sum = 0.f;
-                for (int c = c_lo; c < c_hi; ++c) {
-                    float v[32];
-                    tc_ld32(lane_addr + (uint32_t)(c * 32), v);
-                    // exp is evaluated ONCE per score (the XU pipe is the kernel's limiter) and parked in TMEM over S
-                    const bool full = c * 32 + 32 <= p.Ksel;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const float ee = ex2_approx(fmaf(v[e], p.c_log2, -mc));
-                        v[e] = (full || c * 32 + e < p.Ksel) ? ee : 0.f;
-                        sum += v[e];
-                    }
-                    tc_st32(lane_addr + (uint32_t)(c * 32), v);
-                }
-                tc_wait_st();
-                sRed[(it & 1) * 512 + 256 + half * 128 + rr] = sum;
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                sum += sRed[(it & 1) * 512 + 256 + (half ^ 1) * 128 + rr];
-                const float inv = valid ? 1.f / sum : 0.f;
-                if (p.stats_out && valid && half == 0) {
-                    float* so = p.stats_out + (((int64_t)b * p.h + j) * p.N + n) * 2;
+                if (p.stats_out && valid && half == 0 && kc == 0) {
+                    float* so = p.stats_out + srow * 2;
                     so[0] = mx * (p.c_log2 * 0.69314718055994530942f);     // max of the scaled scores (natural units)
                     so[1] = inv;
                 }
@@ -257,17 +300,26 @@ attn_tc_kernel(const AttnTcParams p) {
                 for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tc_ld32(lane_addr + (uint32_t)(c * 32), v);
+                    if (MODE == 0) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] *= inv;           // exp(s - max) parked by the sum pass
+                        for (int e = 0; e < 32; ++e) v[e] *= inv;       // exp(s - max) parked by the sum pass
+                    } else {
+                        const bool full = c * 32 + 32 <= kvalid;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const float pe = ex2_approx(fmaf(v[e], p.c_log2, -mc)) * inv;
+                            v[e] = (full || c * 32 + e < kvalid) ? pe : 0.f;
+                        }
+                    }
                     if (p.P_out && valid) {
-                        float* po = p.P_out + (((int64_t)b * p.h + j) * p.N + n) * p.Ksel + c * 32;
+                        float* po = p.P_out + srow * p.Ksel + key0 + c * 32;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) if (c * 32 + e < p.Ksel) po[e] = v[e];
+                        for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) po[e] = v[e];
                     }
                     if (p.drop_p > 0.f && valid) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            const uint64_t idx = (((uint64_t)(b * p.h + j) * p.N + n) * p.Ksel + c * 32 + e);
+                            const uint64_t idx = ((uint64_t)srow * p.Ksel + key0 + c * 32 + e);
                             v[e] *= drop_keep_scale(p.seed, p.offset, idx, p.drop_p);
                         }
                     }
@@ -295,20 +347,22 @@ attn_tc_kernel(const AttnTcParams p) {
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
             }
-            // ---- item epilogue: O (TMEM lane = key) -> this split's partial; each half takes one 128-key block
-            mbar_wait(o_full, item_no & 1);
-            tc_fence_after();
-            for (int mb = half; mb < mblocks; mb += 2) {
-                const int key = mb * 128 + rr;
-                for (int c = 0; c < dk / 32; ++c) {
-                    float v[32];
-                    tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * dk + c * 32), v);
-                    if (key < p.Ksel) {
-                        float* o = p.O_part + (((int64_t)split * p.B + b) * p.Ksel + key) * p.d + j * dk + c * 32;
+            if (MODE != 1) {
+                // ---- item epilogue: O (TMEM lane = key) -> this split's partial; each half takes one 128-key block
+                mbar_wait(o_full, item_no & 1);
+                tc_fence_after();
+                for (int mb = half; mb < mblocks; mb += 2) {
+                    const int key = mb * 128 + rr;
+                    for (int c = 0; c < dk / 32; ++c) {
+                        float v[32];
+                        tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * dk + c * 32), v);
+                        if (key < kvalid) {
+                            float* o = p.O_part + (((int64_t)split * p.B + b) * p.Ksel + key0 + key) * p.d + j * dk + c * 32;
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            float4 w = ntiles > 0 ? make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            *reinterpret_cast<float4*>(o + e) = w;
+                            for (int e = 0; e < 32; e += 4) {
+                                float4 w = ntiles > 0 ? make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                *reinterpret_cast<float4*>(o + e) = w;
+                            }
                         }
                     }
                 }
@@ -324,26 +378,39 @@ attn_tc_kernel(const AttnTcParams p) {
     }
 }
 
-struct AttnTcPlan { int KP, splits, tiles_per_split, grid; size_t smem; bool ok; };
+struct AttnTcPlan { int KP, KC, nkc, splits, tiles_per_split, grid; size_t smem; bool ok; };
+
+static size_t attn_tc_smem(int KP, int dk) {
+    return (size_t)2 * KP * 256 + (size_t)2 * KP * dk * 2 + (size_t)4 * AT_TILE * dk * 2 + 128 + 4096;
+}
 
 static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d) {
     AttnTcPlan pl{};
     if (h <= 0 || d % h) return pl;
     const int dk = (int)(d / h);
-    if (dk % 32 || dk > 128 || Ksel < 1 || Ksel > 256) return pl;
-    pl.KP = (int)((Ksel + 15) / 16 * 16);
-    pl.smem = (size_t)2 * pl.KP * 256 + (size_t)2 * pl.KP * dk * 2 + (size_t)4 * AT_TILE * dk * 2 + 128 + 4096;
-    if (pl.smem > 227 * 1024) return pl;
-    // the second 128-key MMA block addresses 16 key groups from its base: must stay inside the CTA's window
-    if (pl.KP > 128 && (size_t)(16 + 16) * 2048 + (size_t)pl.KP * 256 > pl.smem) return pl;
+    if (dk % 32 || dk > 128 || Ksel < 1 || Ksel > 65536) return pl;
+    // fewest key chunks such that a chunk fits TMEM (S: KP <= 256 columns next to the O accumulators) and the operand
+    // tiles fit 227 KB of shared memory
+    for (int nkc = 1; nkc <= 512; ++nkc) {
+        const int KC = (int)(((Ksel + nkc - 1) / nkc + 15) / 16 * 16);
+        if (KC > 256) continue;
+        const size_t smem = attn_tc_smem(KC, dk);
+        if (smem > 227 * 1024) continue;
+        // the second 128-key MMA block addresses 16 key groups from its base: must stay inside the CTA's window
+        if (KC > 128 && (size_t)(16 + 16) * 2048 + (size_t)KC * 256 > smem) continue;
+        pl.nkc = (int)((Ksel + KC - 1) / KC); pl.KC = KC; pl.KP = KC; pl.smem = smem;
+        break;
+    }
+    if (pl.nkc == 0) return pl;
     const int64_t tiles = (N + AT_TILE - 1) / AT_TILE + 1;         // a bag may straddle one extra row tile
-    const int64_t target = (B * h >= 32 ? 4 : 2) * (int64_t)sm_count();
-    int64_t splits = (target + B * h - 1) / (B * h);
+    const int64_t per = B * h * pl.nkc;
+    const int64_t target = (per >= 32 ? 4 : 2) * (int64_t)sm_count();
+    int64_t splits = (target + per - 1) / per;
     if (splits > tiles) splits = tiles;
     if (splits < 1) splits = 1;
     pl.tiles_per_split = (int)((tiles + splits - 1) / splits);
     pl.splits = (int)((tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
-    const int64_t items = B * h * pl.splits;
+    const int64_t items = per * pl.splits;
     pl.grid = (int)(items < sm_count() ? items : sm_count());
     pl.ok = true;
     return pl;
@@ -357,11 +424,14 @@ using namespace snuffy;
 extern "C" {
 
 // bytes of workspace for snuffy_sparse_attn_tc_fwd, or -1 when the shape is not served by the tensor-core kernel
-// (needs dk % 32 == 0, dk <= 128, Ksel <= 256 and the operand tiles to fit 227 KB) -> use snuffy_sparse_attn_fwd.
+// (needs dk % 32 == 0 and dk <= 128) -> use snuffy_sparse_attn_fwd.  Ksel > 256 (or a head too wide for one chunk) runs as
+// two launches over key chunks: per-chunk row statistics, then P and P^T V per chunk with the merged statistics.
 int64_t snuffy_sparse_attn_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d) {
     const AttnTcPlan pl = plan_attn_tc(B, N, Ksel, h, d);
     if (!pl.ok) return -1;
-    return (int64_t)pl.splits * B * Ksel * d * 4 + 256;
+    int64_t bytes = (int64_t)pl.splits * B * Ksel * d * 4 + 256;
+    if (pl.nkc > 1) bytes += (int64_t)pl.nkc * B * h * N * 2 * 4;
+    return bytes;
 }
 
 // Same contract as snuffy_sparse_attn_fwd, but Q and V arrive as the split-bf16 planes the Q|V projection wrote
@@ -386,14 +456,23 @@ int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64
     p.nkb = (int)(ldk / 32); p.q_kb0 = (int)(q_col0 / 32); p.v_kb0 = (int)(v_col0 / 32);
     p.Kp = Kp; p.B = (int)B; p.N = (int)N; p.Ksel = (int)Ksel; p.KP = pl.KP; p.h = (int)h; p.dk = (int)(d / h); p.d = (int)d;
     p.splits = pl.splits; p.tiles_per_split = pl.tiles_per_split;
+    p.nkc = pl.nkc; p.KC = pl.KC;
     p.c_log2 = (float)(1.4426950408889634 / sqrt((double)p.dk));
     p.O_part = reinterpret_cast<float*>(workspace);
+    p.stats_part = p.O_part + (int64_t)pl.splits * B * Ksel * d;
     p.P_out = P_out; p.stats_out = stats_out;
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
-    SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    attn_tc_kernel<<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
+    if (pl.nkc == 1) {
+        SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        attn_tc_kernel<0><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
+    } else {
+        SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        attn_tc_kernel<1><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
+        attn_tc_kernel<2><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
+    }
     launch_fold_partials(p.O_part, pl.splits, B * Ksel * d / 4, O, stream);
-    return check_launch("snuffy_sparse_attn_tc_fwd", 2);
+    return check_launch("snuffy_sparse_attn_tc_fwd", pl.nkc == 1 ? 2 : 3);
 }
 
 }  // extern "C"

@@ -284,6 +284,10 @@ def test_dsmil_pool(ops):
     (3, 200, 100, 2, 128),      # dk = 64, three bags inside two tiles
     (1, 700, 208, 8, 512),      # largest key count served at dk = 64
     (1, 10000, 200, 8, 512),    # full cfg2 bag
+    (1, 600, 392, 8, 768),      # cfg3 head shape: dk = 96, 392 keys -> 4 key chunks (statistics pass + P^T V pass)
+    (2, 900, 256, 8, 512),      # 256 keys at dk = 64 -> 2 chunks, two bags straddling tiles
+    (1, 2000, 1024, 8, 512),    # cfg4 k-sweep upper end: 1024 keys -> 5 chunks
+    (1, 300, 513, 4, 128),      # dk = 32, ragged last chunk
 ])
 def test_sparse_attention_tensor_core(ops, B, n, ks, h, d):
     assert ops.sparse_attn_tc_supported(B, n, ks, h, d)
@@ -318,7 +322,24 @@ def test_sparse_attention_tensor_core_dropout_matches_simt(ops):
     assert (o1 - o2).abs().max() < 3e-5 * max(1.0, o2.abs().max().item())     # same counter-based mask in both kernels
 
 
+def test_sparse_attention_tensor_core_saturated_logits_across_bags(ops):
+    """Un-normalised keys make the logits saturate in deep layers, and bags straddle 128-row tiles:
+    rows of the neighbouring bag inside a tile must contribute exactly 0 (never inf * 0)."""
+    B, n, ks, h, d = 3, 200, 40, 2, 128
+    rs = np.random.RandomState(5)
+    qv = dev((rs.standard_normal((B * n, 2 * d)) * 30).astype(np.float32))
+    kp = dev((rs.standard_normal((B * ks, d)) * 30).astype(np.float32))
+    _, planes, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    o1, p1, _ = ops.sparse_attn_tc(planes, kp, B, n, ks, h, d, want_probs=True)
+    o2, p2, _ = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, n, ks, h, want_probs=True)
+    assert torch.isfinite(o1).all() and torch.isfinite(p1).all()
+    assert (p1.sum(-1) - 1).abs().max() < 1e-4
+    assert (p1 - p2).abs().max() < 2e-2                 # one-hot rows: a logit gap of ~1e-3 moves P by ~1e-3
+    assert (o1 - o2).abs().max() < 2e-2 * o2.abs().max().item()
+
+
 def test_sparse_attention_tensor_core_unsupported_shapes(ops):
-    assert not ops.sparse_attn_tc_supported(1, 256, 32, 1, 384)      # dk = 384
-    assert not ops.sparse_attn_tc_supported(1, 600, 392, 8, 768)     # dk = 96 with 392 keys does not fit
-    assert not ops.sparse_attn_tc_supported(1, 500, 256, 8, 512)     # 256 keys at dk = 64 exceed 227 KB
+    assert not ops.sparse_attn_tc_supported(1, 256, 32, 1, 384)      # dk = 384 > 128
+    assert not ops.sparse_attn_tc_supported(1, 256, 32, 8, 320)      # dk = 40 is not a multiple of 32
+    assert ops.sparse_attn_tc_supported(1, 600, 392, 8, 768)         # served in key chunks since round 1c
+    assert ops.sparse_attn_tc_supported(1, 50000, 1024, 8, 512)
