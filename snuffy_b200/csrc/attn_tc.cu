@@ -35,6 +35,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+#ifdef ATTN_DEBUG_TIMING
+// Per-phase clock64 stamps of CTA 0 (tools/attn_timeline.py): [role 0 softmax | 1 mma | 2 producer][tile < 64][8 stamps]
+__device__ long long g_attn_dbg[3 * 64 * 8];
+#define DBG_STAMP(role, t, k) do { if (blockIdx.x == 0 && (t) < 64) g_attn_dbg[((role) * 64 + (t)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(role, t, k) do { } while (0)
+#endif
+
 struct AttnTcParams {
     const __nv_bfloat16* planes; int64_t plane_stride;   // Q|V planes over [rows, ldk], A layout, RC = 128
     int nkb;                          // k-blocks (of 32 columns) per row tile of the planes = ldk / 32
@@ -142,7 +150,9 @@ attn_tc_kernel(const AttnTcParams p) {
                 const int64_t rt = t0 + t;
                 const __nv_bfloat16* qsrc = p.planes + (rt * p.nkb + p.q_kb0 + j * chunks_per_head) * chunk_elems;
                 const __nv_bfloat16* vsrc = p.planes + (rt * p.nkb + p.v_kb0 + j * chunks_per_head) * chunk_elems;
+                if (lane == 0) DBG_STAMP(2, it, 0);
                 mbar_wait(q_empty, (it & 1) ^ 1);
+                if (lane == 0) DBG_STAMP(2, it, 1);
                 if (lane == 0) {
                     mbar_expect_tx(q_full, 2 * QV_PLANE);
                     bulk_g2s(smem_u32(sQ), qsrc, QV_PLANE, q_full);
@@ -150,6 +160,7 @@ attn_tc_kernel(const AttnTcParams p) {
                 }
                 if (MODE != 1) {
                     mbar_wait(v_empty, (it & 1) ^ 1);
+                    if (lane == 0) DBG_STAMP(2, it, 2);
                     if (lane == 0) {
                         mbar_expect_tx(v_full, 2 * QV_PLANE);
                         bulk_g2s(smem_u32(sV), vsrc, QV_PLANE, v_full);
@@ -166,8 +177,11 @@ attn_tc_kernel(const AttnTcParams p) {
             const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP), aV = smem_u32(sV);
             auto mma2 = [&](uint32_t itp, bool first) {
                 // O[mblk] (+)= P(t)^T V(t): A = P planes (MN-major, M = key), B = V planes (MN-major, N = dv)
+                if (lane == 0) DBG_STAMP(1, itp, 4);
                 mbar_wait(p_full, itp & 1);
+                if (lane == 0) DBG_STAMP(1, itp, 5);
                 mbar_wait(v_full, itp & 1);
+                if (lane == 0) DBG_STAMP(1, itp, 6);
                 tc_fence_after();
                 if (lane == 0) {
                     for (int mb = 0; mb < mblocks; ++mb) {
@@ -183,12 +197,16 @@ attn_tc_kernel(const AttnTcParams p) {
                     }
                     tc_commit(p_empty);
                     tc_commit(v_empty);
+                    DBG_STAMP(1, itp, 7);
                 }
                 __syncwarp();
             };
             for (int t = 0; t < ntiles; ++t, ++it) {
+                if (lane == 0) DBG_STAMP(1, it, 0);
                 mbar_wait(q_full, it & 1);
+                if (lane == 0) DBG_STAMP(1, it, 1);
                 mbar_wait(s_empty, (it & 1) ^ 1);
+                if (lane == 0) DBG_STAMP(1, it, 2);
                 tc_fence_after();
                 if (lane == 0) {
                     for (int ks = 0; ks < ksteps; ++ks) {
@@ -201,6 +219,7 @@ attn_tc_kernel(const AttnTcParams p) {
                     }
                     tc_commit(q_empty);
                     tc_commit(s_full);
+                    DBG_STAMP(1, it, 3);
                 }
                 __syncwarp();
                 if (MODE != 1 && t > 0) mma2(it - 1, t == 1);
@@ -224,7 +243,10 @@ attn_tc_kernel(const AttnTcParams p) {
                 const bool valid = g >= g_lo && g < g_hi;
                 const int n = (int)(g - g_lo);
                 const int64_t srow = ((int64_t)b * p.h + j) * p.N + n;      // row of the [B, h, N, *] statistics
+                const bool stamp = warp == 2 && lane == 0;
+                if (stamp) DBG_STAMP(0, it, 0);
                 mbar_wait(s_full, it & 1);
+                if (stamp) DBG_STAMP(0, it, 1);
                 tc_fence_after();
                 float mx = -INFINITY, inv = 0.f, mc = 0.f;
                 if (MODE != 2) {
@@ -243,6 +265,7 @@ attn_tc_kernel(const AttnTcParams p) {
                     sRed[(it & 1) * 512 + half * 128 + rr] = mx;
                     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
                     mx = fmaxf(mx, sRed[(it & 1) * 512 + (half ^ 1) * 128 + rr]);
+                    if (stamp) DBG_STAMP(0, it, 2);
                     if (!valid) mx = 0.f;
                     // rows of a neighbouring bag / padding: exp2(s*c - inf) = 0 -> P = 0 exactly (never inf * 0 = NaN)
                     mc = valid ? mx * p.c_log2 : INFINITY;
@@ -264,6 +287,7 @@ attn_tc_kernel(const AttnTcParams p) {
                     sRed[(it & 1) * 512 + 256 + half * 128 + rr] = sum;
                     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
                     sum += sRed[(it & 1) * 512 + 256 + (half ^ 1) * 128 + rr];
+                    if (stamp) DBG_STAMP(0, it, 3);
                     if (MODE == 1) {
                         // per-chunk partial statistics for pass 2 (raw-score max, sum of exp2 relative to it)
                         if (valid && half == 0) {
@@ -296,7 +320,9 @@ attn_tc_kernel(const AttnTcParams p) {
                     so[0] = mx * (p.c_log2 * 0.69314718055994530942f);     // max of the scaled scores (natural units)
                     so[1] = inv;
                 }
+                if (stamp) DBG_STAMP(0, it, 4);
                 mbar_wait(p_empty, (it & 1) ^ 1);            // MMA of the previous tile has consumed P
+                if (stamp) DBG_STAMP(0, it, 5);
                 for (int c = c_lo; c < c_hi; ++c) {
                     float v[32];
                     tc_ld32(lane_addr + (uint32_t)(c * 32), v);
@@ -345,6 +371,7 @@ attn_tc_kernel(const AttnTcParams p) {
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
+                if (stamp) DBG_STAMP(0, it, 6);
                 if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
             }
             if (MODE != 1) {
@@ -474,6 +501,12 @@ int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64
     launch_fold_partials(p.O_part, pl.splits, B * Ksel * d / 4, O, stream);
     return check_launch("snuffy_sparse_attn_tc_fwd", pl.nkc == 1 ? 2 : 3);
 }
+
+#ifdef ATTN_DEBUG_TIMING
+int snuffy_attn_debug_read(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_attn_dbg, sizeof(g_attn_dbg)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // extern "C"
 #pragma GCC visibility pop
