@@ -102,6 +102,21 @@ int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_p
                    int64_t out_plane_stride, float dropout_p, uint64_t seed, uint64_t offset,
                    snuffy_stream_t stream);
 
+/* Split-K form for weight gradients dW[M,N] = A B^T contracting over all patches (few output tiles, long K):
+ * ksplit <= 0 = automatic; workspace: snuffy_gemm_tc_splitk_workspace(M, N, ksplit) bytes (deterministic fold).     */
+int64_t snuffy_gemm_tc_auto_ksplit(int64_t M, int64_t N, int64_t K);
+int64_t snuffy_gemm_tc_splitk_workspace(int64_t M, int64_t N, int64_t ksplit);
+int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const void* B_planes,
+                          int64_t b_plane_stride, int64_t M, int64_t N, int64_t K, int passes, int64_t ksplit,
+                          float* out, void* workspace, int64_t workspace_bytes, snuffy_stream_t stream);
+/* Operand planes of X^T for fp32 X [R, C] (plane row = column of X, k = row of X) with an optional prologue:
+ * mode 0 plain, 1 LayerNorm from saved (mean, rstd) through row_map, 2 dropout(act(x)).  Feeds the transposed
+ * operands of dW = dY^T X (autograd of nn.Linear at snuffy.py:188, 225) to snuffy_gemm_tc_splitk.                   */
+int snuffy_planes_t_fwd(const float* x, int64_t ldx, int64_t R, int64_t C, int plane_rc, int mode,
+                        const float* stats, const float* gamma, const float* beta, const int32_t* row_map,
+                        const float* alt, int act, float dropout_p, uint64_t seed, uint64_t offset, void* planes,
+                        int64_t plane_stride, snuffy_stream_t stream);
+
 /* ---- a9: sparse attention  O = concat_j softmax_keys(Q_j Kp_j^T / sqrt(dk))^T V_j                      */
 /* Replaces matmul / div / softmax / dropout / matmul / transpose+contiguous (snuffy.py:160-168, 187-201).
  * Q,V [B*N,d] with row strides ldq/ldv; Kp [B*Ksel,d]; O [B*Ksel,d]; P_out [B,h,N,Ksel] optional

@@ -39,6 +39,10 @@ _SIGNATURES = {
     "snuffy_plane_elems": (c_int64, [I, I, c_int]),
     "snuffy_gemm_tc": (c_int, [P, I, P, I, I, I, I, c_int, P, c_int, P, I, P, P, P, I, P, P, I, c_float, c_uint64, c_uint64,
                               P]),
+    "snuffy_gemm_tc_auto_ksplit": (c_int64, [I, I, I]),
+    "snuffy_gemm_tc_splitk_workspace": (c_int64, [I, I, I]),
+    "snuffy_gemm_tc_splitk": (c_int, [P, I, P, I, I, I, I, c_int, I, P, P, I, P]),
+    "snuffy_planes_t_fwd": (c_int, [P, I, I, I, c_int, c_int, P, P, P, P, P, c_int, c_float, c_uint64, c_uint64, P, I, P]),
     "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),
     "snuffy_sparse_attn_fwd": (c_int, [P, I, P, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
     "snuffy_sparse_attn_tc_workspace": (c_int64, [I, I, I, I, I]),

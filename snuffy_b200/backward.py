@@ -105,7 +105,7 @@ class EncoderLayerFunction(torch.autograd.Function):
             enc_dropout=float(layer.sublayer[0].dropout.p) if training else 0.0,
             ff_dropout=float(layer.feed_forward.dropout.p) if training else 0.0)
         ctx.tape, ctx.w = tape, w
-        ctx.meta = (B, N, d, layer.self_attn.h, layer.feed_forward.activation_name)
+        ctx.meta = (B, N, d, layer.self_attn.h, layer.feed_forward.activation_name, layer._effective_precision())
         x_next = x_next.view(B, N, d)
         if probs is None:
             return x_next, None
@@ -115,24 +115,50 @@ class EncoderLayerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, _g_probs=None):
         t, w = ctx.tape, ctx.w
-        B, N, d, heads, act = ctx.meta
+        B, N, d, heads, act, precision = ctx.meta
         rows, ksel = B * N, t.sel.shape[1]
+        dff = w.w1.shape[0]
         need = ctx.needs_input_grad
         g = _flat(g_out, d)
+        # The six contractions over all N rows run on tcgen05 (split-bf16, like the forward) unless the layer is in the
+        # exact-fp32 mode; the [Ksel, d]-sized ones and the attention backward stay fp32 SIMT.
+        tc = precision != "fp32" and engine.tc_supported(d) and dff % 8 == 0
+        passes = 1 if precision == "bf16x1" else 3
+        if tc:
+            w.prepare(precision)
+            w.prepare_backward()
+            rc_d, rc_ff = ops.lib.snuffy_gemm_tc_block_n(d), ops.lib.snuffy_gemm_tc_block_n(dff)
+
+        def dx_gemm(dy, w_f32, wt_planes, n_in):                # dX = dY . W        (W = nn.Linear.weight [out, in])
+            if not tc:
+                return ops.matmul_nn(dy, w_f32)
+            _, ap, _ = ops.ln_rows(dy, None, None, apply_ln=False, want_planes=True)
+            out, _, _ = ops.gemm_tc(ap, wt_planes, M=dy.shape[0], N=n_in, K=dy.shape[1], passes=passes)
+            return out
 
         # ---- feed-forward sub-layer
         gf = ops.act_bwd(None, g, drop=t.drop_enc2)[0] if t.drop_enc2[0] > 0 else g
         d_b2 = ops.colsum(gf).view(-1)
-        da = ops.matmul_nn(gf, w.w2)                                              # [rows, dff]
-        dh, a = ops.act_bwd(t.h_pre, da, act, t.drop_ff, want_dh=True, want_a=True)
-        del da
-        d_w2 = ops.matmul_tn(gf, a)                                               # [d, dff]
-        del a
+        da = dx_gemm(gf, w.w2, w.w2t_planes, dff)                                  # [rows, dff]
+        if tc:
+            dh, _ = ops.act_bwd(t.h_pre, da, act, t.drop_ff, want_dh=True, want_a=False)
+            del da
+            d_w2 = ops.gemm_tc_splitk(ops.planes_t(gf, 128), ops.planes_t(t.h_pre, rc_ff, mode=2, act=act, drop=t.drop_ff),
+                                      M=d, N=dff, K=rows, passes=passes)           # gf^T . dropout(act(h_pre))
+            d_w1 = ops.gemm_tc_splitk(ops.planes_t(dh, 128),
+                                      ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln2_stats, gamma=w.g2, beta=w.be2,
+                                                   row_map=t.row_map, alt=t.xs_new),
+                                      M=dff, N=d, K=rows, passes=passes)           # dh^T . LN2(y)
+        else:
+            dh, a = ops.act_bwd(t.h_pre, da, act, t.drop_ff, want_dh=True, want_a=True)
+            del da
+            d_w2 = ops.matmul_tn(gf, a)                                            # [d, dff]
+            del a
+            u2, _, _ = ops.ln_rows(t.x_in, w.g2, w.be2, row_map=t.row_map, alt=t.xs_new, want_f32=True)
+            d_w1 = ops.matmul_tn(dh, u2)                                           # [dff, d]
+            del u2
         d_b1 = ops.colsum(dh).view(-1)
-        u2, _, _ = ops.ln_rows(t.x_in, w.g2, w.be2, row_map=t.row_map, alt=t.xs_new, want_f32=True)
-        d_w1 = ops.matmul_tn(dh, u2)                                              # [dff, d]
-        del u2
-        du2 = ops.matmul_nn(dh, w.w1)                                             # [rows, d]
+        du2 = dx_gemm(dh, w.w1, w.w1t_planes, d)                                   # [rows, d]
         del dh
         dy, d_g2, d_be2 = ops.ln_rows_bwd(t.x_in, t.ln2_stats, w.g2, dy=du2, row_map=t.row_map, alt=t.xs_new, add=g)
         del du2
@@ -142,16 +168,24 @@ class EncoderLayerFunction(torch.autograd.Function):
         dz = ops.act_bwd(None, dxs_new, drop=t.drop_enc1)[0] if t.drop_enc1[0] > 0 else dxs_new
         d_bo = ops.colsum(dz).view(-1)
         d_wo = ops.matmul_tn(dz, t.o)
-        d_o = ops.matmul_nn(dz, w.wo)                                             # [B*Ksel, d]
+        d_o = ops.matmul_nn(dz, w.wo)                                              # [B*Ksel, d]
         q, v = t.qv[:, :d], t.qv[:, d:]
-        dq, dv, dkp = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)
-        d_bk = ops.colsum(dkp).view(-1)                                           # == 0 up to rounding (App. B-16)
+        dq, dv, dkp, dqv = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)
+        d_bk = ops.colsum(dkp).view(-1)                                            # == 0 up to rounding (App. B-16)
         d_wk = ops.matmul_tn(dkp, t.xs)
-        u1, _, _ = ops.ln_rows(t.x_in, w.g1, w.be1, want_f32=True)
-        d_wq, d_wv = ops.matmul_tn(dq, u1), ops.matmul_tn(dv, u1)
-        del u1
-        d_bq, d_bv = ops.colsum(dq).view(-1), ops.colsum(dv).view(-1)
-        du1 = ops.matmul_nn(dv, w.wv, resid=ops.matmul_nn(dq, w.wq))              # [rows, d]
+        d_bqv = ops.colsum(dqv).view(-1)
+        d_bq, d_bv = d_bqv[:d], d_bqv[d:]
+        if tc:
+            d_wqv = ops.gemm_tc_splitk(ops.planes_t(dqv, 128),
+                                       ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln1_stats, gamma=w.g1, beta=w.be1),
+                                       M=2 * d, N=d, K=rows, passes=passes)        # [dQ | dV]^T . LN1(x)
+            d_wq, d_wv = d_wqv[:d], d_wqv[d:]
+            du1 = dx_gemm(dqv, None, w.wqvt_planes, d)                             # dQ Wq + dV Wv
+        else:
+            u1, _, _ = ops.ln_rows(t.x_in, w.g1, w.be1, want_f32=True)
+            d_wq, d_wv = ops.matmul_tn(dq, u1), ops.matmul_tn(dv, u1)
+            del u1
+            du1 = ops.matmul_nn(dv, w.wv, resid=ops.matmul_nn(dq, w.wq))           # [rows, d]
         dx, d_g1, d_be1 = ops.ln_rows_bwd(t.x_in, t.ln1_stats, w.g1, dy=du1, add=dy, want_dx=need[1])
         if dx is not None:
             # raw selected rows also feed the key projection: dx[S] += dKp Wk  (the xs residual is already in `add`)

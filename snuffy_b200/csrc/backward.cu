@@ -99,27 +99,25 @@ act_bwd_kernel(const float* __restrict__ hpre, const float* __restrict__ da, int
 
 // ------------------------------------------------------------------ weighted column sums
 // partial[chunk][c][e] = sum_{rows in chunk} w[row*C + c] * X[row*ldx + e]   (w == null -> weight 1, C = 1)
+// thread = column (coalesced row reads), 4 independent row accumulators per thread
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, int64_t rows, int d, int C,
               int64_t rows_per_chunk, float* __restrict__ partials) {
-    __shared__ float red[8][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
     for (int c = 0; c < C; ++c) {
-        for (int e0 = 0; e0 < d; e0 += 32) {
-            const int e = e0 + lane;
-            float acc = 0.f;
-            if (e < d)
-                for (int64_t r = r0 + warp; r < r1; r += 8) acc = fmaf(w ? __ldg(w + r * C + c) : 1.f, __ldg(X + r * ldx + e), acc);
-            red[warp][lane] = acc;
-            __syncthreads();
-            if (warp == 0 && e < d) {
-                float s = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) s += red[k][lane];
-                partials[((int64_t)blockIdx.x * C + c) * d + e] = s;
+        for (int e = threadIdx.x; e < d; e += blockDim.x) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int64_t r = r0;
+            for (; r + 3 < r1; r += 4) {
+                const float w0 = w ? __ldg(w + r * C + c) : 1.f, w1 = w ? __ldg(w + (r + 1) * C + c) : 1.f;
+                const float w2 = w ? __ldg(w + (r + 2) * C + c) : 1.f, w3 = w ? __ldg(w + (r + 3) * C + c) : 1.f;
+                a0 = fmaf(w0, __ldg(X + r * ldx + e), a0);
+                a1 = fmaf(w1, __ldg(X + (r + 1) * ldx + e), a1);
+                a2 = fmaf(w2, __ldg(X + (r + 2) * ldx + e), a2);
+                a3 = fmaf(w3, __ldg(X + (r + 3) * ldx + e), a3);
             }
-            __syncthreads();
+            for (; r < r1; ++r) a0 = fmaf(w ? __ldg(w + r * C + c) : 1.f, __ldg(X + r * ldx + e), a0);
+            partials[((int64_t)blockIdx.x * C + c) * d + e] = (a0 + a1) + (a2 + a3);
         }
     }
 }
@@ -195,7 +193,7 @@ extern "C" {
 // CTAs (= partial rows) snuffy_ln_rows_bwd uses; partials needs blocks * 2 * d floats
 int64_t snuffy_ln_rows_bwd_blocks(int64_t rows) {
     int64_t b = (rows + 7) / 8;
-    const int64_t cap = 4 * (int64_t)sm_count();
+    const int64_t cap = (int64_t)sm_count();               // one partial [2, d] per CTA: keep the fold short
     if (b > cap) b = cap;
     return b < 1 ? 1 : b;
 }

@@ -19,6 +19,8 @@
 
 namespace snuffy {
 
+void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream);
+
 constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 320;          // producer warp + MMA warp + 8 epilogue warps
 constexpr uint32_t TC_A_PLANE_BYTES = TC_BM * PLANE_KB * 2;          // 8 KB per plane per stage
@@ -44,6 +46,9 @@ struct TcGemmParams {
     float* preact;                   // optional fp32 [M, ldc] value before the activation
     __nv_bfloat16* out_planes; int64_t out_plane_stride;   // optional: result as A-operand planes, K_next = N
     float drop_p; uint64_t seed, offset;                   // dropout on the activated value (before the residual)
+    // split-K (dW = dY^T X contracts over all N patches but has few output tiles): tile = (mt, nt, ks), split ks covers
+    // k-blocks [ks*kb_per, ...) and writes its raw fp32 partial to out + ks*split_stride (folded by the caller)
+    int ksplit, kb_per; int64_t split_stride;
 };
 
 template <int BN>
@@ -75,7 +80,7 @@ gemm_tc_kernel(const TcGemmParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
     const bool use_lo = p.npairs > 1;
     const uint32_t stage_tx = use_lo ? Cfg::STAGE_BYTES : (TC_A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
 
@@ -84,10 +89,12 @@ gemm_tc_kernel(const TcGemmParams p) {
         int stage = 0; uint32_t phase = 0;
         const int64_t a_chunk = (int64_t)TC_BM * PLANE_KB, b_chunk = (int64_t)BN * PLANE_KB;   // elements
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
+            const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
+            const int kb0 = ksp * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
             const __nv_bfloat16* a_src = p.A + (int64_t)mt * p.num_kb * a_chunk;
             const __nv_bfloat16* b_src = p.B + (int64_t)nt * p.num_kb * b_chunk;
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                 if (lane == 0) {
                     const uint32_t bar = full0 + 8 * stage;
@@ -113,10 +120,12 @@ gemm_tc_kernel(const TcGemmParams p) {
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int ksp = tile % p.ksplit;
+            const int kb0 = ksp * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 if (lane == 0) {
@@ -130,15 +139,15 @@ gemm_tc_kernel(const TcGemmParams p) {
                             const uint64_t a_lo = make_smem_desc(sa + TC_A_PLANE_BYTES + ks * 2 * LBO_A, LBO_A, SBO);
                             const uint64_t b_lo = make_smem_desc(sb + Cfg::B_PLANE_BYTES + ks * 2 * LBO_B, LBO_B, SBO);
                             // small cross terms first, the dominant hi.hi term last
-                            tc_mma_bf16(d_tmem, a_lo, b_hi, IDESC, (kb | ks) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, a_lo, b_hi, IDESC, (kb > kb0 || ks) ? 1u : 0u);
                             tc_mma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
                             tc_mma_bf16(d_tmem, a_hi, b_hi, IDESC, 1u);
                         } else {
-                            tc_mma_bf16(d_tmem, a_hi, b_hi, IDESC, (kb | ks) ? 1u : 0u);
+                            tc_mma_bf16(d_tmem, a_hi, b_hi, IDESC, (kb > kb0 || ks) ? 1u : 0u);
                         }
                     }
                     tc_commit(empty0 + 8 * stage);                 // frees the smem slot when these MMAs retire
-                    if (kb == p.num_kb - 1) tc_commit(tfull0 + 8 * acc);
+                    if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -156,7 +165,9 @@ gemm_tc_kernel(const TcGemmParams p) {
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;           // coalesced phase: 4 rows x 8 float4 per pass
         constexpr int CH = BN / 64;                                // 32-column chunks per half
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+            const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
+            const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
+            float* const outp = p.out ? p.out + (int64_t)ksp * p.split_stride : nullptr;
             const int rr_own = quad * 32 + lane;                   // row of the tile this thread owns in TMEM
             const int64_t m_own = (int64_t)mt * TC_BM + rr_own;
             const int64_t m_base = (int64_t)mt * TC_BM + quad * 32;
@@ -259,7 +270,7 @@ gemm_tc_kernel(const TcGemmParams p) {
                             float4 o = make_float4(stg[row * 33 + c4], stg[row * 33 + c4 + 1], stg[row * 33 + c4 + 2],
                                                    stg[row * 33 + c4 + 3]);
                             if (p.resid) { o.x += r4[i].x; o.y += r4[i].y; o.z += r4[i].z; o.w += r4[i].w; }
-                            *reinterpret_cast<float4*>(p.out + m * p.ldc + col) = o;
+                            *reinterpret_cast<float4*>(outp + m * p.ldc + col) = o;
                         }
                     }
                     __syncwarp();
@@ -298,6 +309,22 @@ int64_t snuffy_plane_elems(int64_t rows, int64_t K, int rc) { return plane_elems
 // C = epilogue(A . B^T) with A, B given as split-bf16 planes (A tiled with 128 rows per chunk, B with
 // snuffy_gemm_tc_block_n(N)).  Outputs (each optional, at least one): fp32 `out` [M, ldc] (+ residual, optionally
 // redirected through row_map), fp32 `preact`, and `out_planes` = the activated result as A planes with K_next = N.
+static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const char* who) {
+    const int bn = snuffy_gemm_tc_block_n(N);
+    const int total = p.m_tiles * p.n_tiles * p.ksplit;
+    const int grid = total < sm_count() ? total : sm_count();
+    if (bn == 256) {
+        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TcCfg<256>::SMEM_BYTES));
+        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p);
+    } else {
+        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TcCfg<128>::SMEM_BYTES));
+        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(p);
+    }
+    return check_launch(who);
+}
+
 int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
                    int64_t M, int64_t N, int64_t K, int passes, const float* bias, int act, const float* resid,
                    int64_t ldr, const int32_t* row_map, const float* resid_alt, float* out, int64_t ldc,
@@ -327,18 +354,54 @@ int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_p
     p.out = out; p.ldc = ldc; p.preact = preact;
     p.out_planes = reinterpret_cast<__nv_bfloat16*>(out_planes); p.out_plane_stride = out_plane_stride;
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
-    const int total = p.m_tiles * p.n_tiles;
-    const int grid = total < sm_count() ? total : sm_count();
-    if (bn == 256) {
-        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)TcCfg<256>::SMEM_BYTES));
-        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p);
-    } else {
-        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)TcCfg<128>::SMEM_BYTES));
-        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(p);
+    p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
+    return launch_gemm_tc(p, N, stream, "snuffy_gemm_tc");
+}
+
+// Split-K form for the weight gradients dW[M, N] = A . B^T with a long contraction (K = all patches of the step) and few
+// output tiles: `ksplit` <= 0 picks one that fills the machine.  partials: snuffy_gemm_tc_splitk_workspace floats * 4 bytes.
+int64_t snuffy_gemm_tc_auto_ksplit(int64_t M, int64_t N, int64_t K) {
+    const int bn = snuffy_gemm_tc_block_n(N);
+    const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + bn - 1) / bn);
+    const int64_t num_kb = plane_kblocks(K);
+    int64_t ks = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+    if (ks > num_kb / 8) ks = num_kb / 8;                  // at least 8 k-blocks (256 k) per split
+    if (ks < 1) ks = 1;
+    const int64_t per = (num_kb + ks - 1) / ks;
+    return (num_kb + per - 1) / per;                       // every split owns at least one k-block
+}
+int64_t snuffy_gemm_tc_splitk_workspace(int64_t M, int64_t N, int64_t ksplit) { return ksplit > 1 ? M * N * ksplit * 4 : 0; }
+
+int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                          int64_t M, int64_t N, int64_t K, int passes, int64_t ksplit, float* out, void* workspace,
+                          int64_t workspace_bytes, cudaStream_t stream) {
+    SNUFFY_REQUIRE(A_planes && B_planes && out, "snuffy_gemm_tc_splitk: null pointer");
+    SNUFFY_REQUIRE(M >= 1 && N >= 1 && K >= 1 && N % 4 == 0 && (uintptr_t)out % 16 == 0, "snuffy_gemm_tc_splitk: bad problem");
+    SNUFFY_REQUIRE(passes == 1 || passes == 3, "snuffy_gemm_tc_splitk: passes must be 1 or 3");
+    if (ksplit <= 0) ksplit = snuffy_gemm_tc_auto_ksplit(M, N, K);
+    const int64_t num_kb = plane_kblocks(K);
+    const int64_t per = (num_kb + ksplit - 1) / ksplit;
+    ksplit = (num_kb + per - 1) / per;
+    SNUFFY_REQUIRE(ksplit == 1 || (workspace && workspace_bytes >= snuffy_gemm_tc_splitk_workspace(M, N, ksplit) &&
+                                   (uintptr_t)workspace % 16 == 0), "snuffy_gemm_tc_splitk: workspace too small");
+    TcGemmParams p{};
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A_planes); p.a_plane_stride = a_plane_stride;
+    p.B = reinterpret_cast<const __nv_bfloat16*>(B_planes); p.b_plane_stride = b_plane_stride;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    const int bn = snuffy_gemm_tc_block_n(N);
+    p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    p.n_tiles = (int)((N + bn - 1) / bn);
+    p.num_kb = (int)num_kb;
+    p.npairs = passes;
+    p.act = ACT_NONE;
+    p.out = ksplit > 1 ? reinterpret_cast<float*>(workspace) : out; p.ldc = N;
+    p.ksplit = (int)ksplit; p.kb_per = (int)per; p.split_stride = M * N;
+    if (int rc = launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_splitk")) return rc;
+    if (ksplit > 1) {
+        launch_fold_partials(reinterpret_cast<const float*>(workspace), (int)ksplit, M * N / 4, out, stream);
+        return check_launch("snuffy_gemm_tc_splitk");
     }
-    return check_launch("snuffy_gemm_tc");
+    return 0;
 }
 
 }  // extern "C"

@@ -462,3 +462,93 @@ int snuffy_ln_mean_head_fwd(const float* x, const float* gamma, const float* bet
 
 }  // extern "C"
 #pragma GCC visibility pop
+
+// ------------------------------------------------------------------ transposed operand planes (weight gradients)
+// planes of X^T for an fp32 X [R, C]: plane row = column c of X, k = row r of X (the contraction of dW = dY^T X runs over
+// the rows).  Optional element-wise prologue so the transposed operand is produced straight from what the forward saved:
+//   mode 0: x                       mode 1: LayerNorm(x-with-mapped-rows) from saved (mean, rstd) + affine
+//   mode 2: dropout(act(x))  (x = saved pre-activation)
+namespace snuffy {
+struct PlanesTParams {
+    const float* x; int64_t ldx; int64_t R; int C; int rc; int mode;
+    const float* stats; const float* gamma; const float* beta; const int32_t* row_map; const float* alt;
+    int act; float drop_p; uint64_t seed, offset;
+    __nv_bfloat16* planes; int64_t plane_stride;
+};
+
+__global__ void __launch_bounds__(256)
+planes_t_kernel(const PlanesTParams p) {
+    __shared__ float tile[32][129];
+    const int t = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * 32;
+    const int c0 = blockIdx.x * 128;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = t + i * 256, row = idx >> 5, c4 = (idx & 31) * 4;
+        const int64_t r = r0 + row;
+        const int c = c0 + c4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < p.R && c < p.C) {
+            const float* src = p.x + r * p.ldx;
+            if (p.mode == 1 && p.row_map) { const int32_t slot = p.row_map[r]; if (slot >= 0) src = p.alt + (int64_t)slot * p.ldx; }
+            if (c + 3 < p.C) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src + c));
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            } else {
+                for (int j = 0; j < 4; ++j) if (c + j < p.C) v[j] = src[c + j];
+            }
+            if (p.mode == 1) {
+                const float mean = p.stats[r * 2], rstd = p.stats[r * 2 + 1];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (c + j < p.C) v[j] = (v[j] - mean) * rstd * p.gamma[c + j] + p.beta[c + j];
+            } else if (p.mode == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = act_apply(p.act, v[j]);
+                    if (p.drop_p > 0.f) a *= drop_keep_scale(p.seed, p.offset, (uint64_t)(r * p.C + c + j), p.drop_p);
+                    v[j] = (c + j < p.C) ? a : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile[row][c4 + j] = v[j];
+    }
+    __syncthreads();
+    const int64_t nkb = plane_kblocks(p.R);
+    const int64_t kb = blockIdx.y;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int u = t + i * 256, kg = u >> 7, cl = u & 127;
+        const int64_t prow = c0 + cl;                              // plane row = column of X (rows >= C are zero padding)
+        bf16x8 h, l;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_bf16(tile[kg * 8 + j][cl], h.v[j], l.v[j]);
+        const int64_t rt = prow / p.rc, rr = prow % p.rc;
+        const int64_t off = ((rt * nkb + kb) * 4 + kg) * (int64_t)p.rc * 8 + rr * 8;
+        *reinterpret_cast<bf16x8*>(p.planes + off) = h;
+        *reinterpret_cast<bf16x8*>(p.planes + p.plane_stride + off) = l;
+    }
+}
+}  // namespace snuffy
+
+#pragma GCC visibility push(default)
+extern "C" int snuffy_planes_t_fwd(const float* x, int64_t ldx, int64_t R, int64_t C, int plane_rc, int mode,
+                                   const float* stats, const float* gamma, const float* beta, const int32_t* row_map,
+                                   const float* alt, int act, float dropout_p, uint64_t seed, uint64_t offset, void* planes,
+                                   int64_t plane_stride, cudaStream_t stream) {
+    using namespace snuffy;
+    SNUFFY_REQUIRE(x && planes && R >= 1 && C >= 1, "snuffy_planes_t_fwd: bad arguments");
+    SNUFFY_REQUIRE(plane_rc == 128 || plane_rc == 256, "snuffy_planes_t_fwd: plane_rc must be 128 or 256");
+    SNUFFY_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || (stats && gamma && beta)) && (!row_map || alt),
+                   "snuffy_planes_t_fwd: inconsistent prologue arguments");
+    SNUFFY_REQUIRE(ldx % 4 == 0 && (uintptr_t)x % 16 == 0 && (!alt || (uintptr_t)alt % 16 == 0) && (uintptr_t)planes % 16 == 0 &&
+                       plane_stride % 8 == 0, "snuffy_planes_t_fwd: rows must be 16-byte aligned");
+    PlanesTParams p{x, ldx, R, (int)C, plane_rc, mode, stats, gamma, beta, row_map, alt, act, dropout_p, seed, offset,
+                    reinterpret_cast<__nv_bfloat16*>(planes), plane_stride};
+    const int64_t cpad = plane_rtiles(C, plane_rc) * plane_rc;
+    dim3 grid((unsigned)(cpad / 128), (unsigned)plane_kblocks(R));
+    SNUFFY_REQUIRE(grid.y <= 65535, "snuffy_planes_t_fwd: too many rows for one launch");
+    planes_t_kernel<<<grid, 256, 0, stream>>>(p);
+    return check_launch("snuffy_planes_t_fwd");
+}
+#pragma GCC visibility pop

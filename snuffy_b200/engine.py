@@ -160,6 +160,10 @@ class LayerWeights:
     bqv_fold: Optional[torch.Tensor] = None
     w1_fold_planes: Optional[Planes] = None
     b1_fold: Optional[torch.Tensor] = None
+    # transposed weights as B operands of the backward dX = dY . W products
+    w2t_planes: Optional[Planes] = None
+    w1t_planes: Optional[Planes] = None
+    wqvt_planes: Optional[Planes] = None
 
     def prepare(self, precision: str) -> None:
         if self.wqv is None:
@@ -172,6 +176,12 @@ class LayerWeights:
             self.w2_planes = ops.weight_planes(self.w2.detach())
             self.wk_planes = ops.weight_planes(self.wk.detach())
             self.wo_planes = ops.weight_planes(self.wo.detach())
+
+    def prepare_backward(self) -> None:
+        if self.w2t_planes is None:
+            self.w2t_planes = ops.weight_planes_t(self.w2.detach())
+            self.w1t_planes = ops.weight_planes_t(self.w1.detach())
+            self.wqvt_planes = ops.weight_planes_t(self.wqv)
 
     def prepare_folded(self) -> None:
         if self.wqv_fold_planes is None:

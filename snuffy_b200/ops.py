@@ -401,7 +401,7 @@ def sparse_attn_bwd(q: torch.Tensor, v: torch.Tensor, kp: torch.Tensor, d_o: tor
     """Backward of O_j = softmax_keys(Q_j Kp_j^T / sqrt(dk))^T V_j  (snuffy.py:160-168).
 
     q, v: [B*N, d] (row-strided views allowed); kp, d_o: [B*Ksel, d]; stats [B, h, N, 2] from the forward.
-    Returns (dQ [B*N, d], dV [B*N, d], dKp [B*Ksel, d]).  The [B, h, N, Ksel] score tensors are materialised here
+    Returns (dQ, dV (column halves of dQV), dKp [B*Ksel, d], dQV [B*N, 2d]).  The [B, h, N, Ksel] score tensors are materialised here
     (recompute, never saved by the forward) and every contraction is one head-batched SIMT GEMM launch."""
     q, v = _rows_view(q, "q"), _rows_view(v, "v")
     kp, d_o = _f32(kp, "kp"), _f32(d_o, "d_o")
@@ -413,8 +413,8 @@ def sparse_attn_bwd(q: torch.Tensor, v: torch.Tensor, kp: torch.Tensor, d_o: tor
     S = torch.empty(B * h * N, Ksel, dtype=torch.float32, device=dev)
     Pd = torch.empty_like(S)
     G = torch.empty_like(S)
-    dq = torch.empty(B * N, d, dtype=torch.float32, device=dev)
-    dv = torch.empty(B * N, d, dtype=torch.float32, device=dev)
+    dqv = torch.empty(B * N, 2 * d, dtype=torch.float32, device=dev)      # dQ | dV side by side: one operand for dWqv / du1
+    dq, dv = dqv[:, :d], dqv[:, d:]
     dkp = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
     hb = dict(nb_outer=B, nb_inner=h)
     s_str = (h * N * Ksel, N * Ksel)                    # [B, h, N, Ksel] matrices
@@ -423,19 +423,19 @@ def sparse_attn_bwd(q: torch.Tensor, v: torch.Tensor, kp: torch.Tensor, d_o: tor
                      sa=(N * ldq, dk), sb=(Ksel * d, dk), sc=s_str, ksplit=1, **hb)
     attn_rows_bwd(S, stats, N, 0, scale, drop, pd=Pd)
     # dV_j = P~_j dO_j          [N, dk]   (B operand dO_j stored [key, c]: k-major rows)
-    gemm_f32_batched(Pd, d_o, dv, M=N, N=dk, K=Ksel, lda=Ksel, ldb=d, ldc=d, b_kc=False,
-                     sa=s_str, sb=(Ksel * d, dk), sc=(N * d, dk), ksplit=1, **hb)
+    gemm_f32_batched(Pd, d_o, dv, M=N, N=dk, K=Ksel, lda=Ksel, ldb=d, ldc=2 * d, b_kc=False,
+                     sa=s_str, sb=(Ksel * d, dk), sc=(N * 2 * d, dk), ksplit=1, **hb)
     # G = V_j dO_j^T            [N, Ksel]
     gemm_f32_batched(v, d_o, G, M=N, N=Ksel, K=dk, lda=ldv, ldb=d, ldc=Ksel,
                      sa=(N * ldv, dk), sb=(Ksel * d, dk), sc=s_str, ksplit=1, **hb)
     attn_rows_bwd(S, stats, N, 1, scale, drop, g=G)     # G <- dS
     # dQ_j = dS_j Kp_j          [N, dk]
-    gemm_f32_batched(G, kp, dq, M=N, N=dk, K=Ksel, lda=Ksel, ldb=d, ldc=d, b_kc=False,
-                     sa=s_str, sb=(Ksel * d, dk), sc=(N * d, dk), ksplit=1, **hb)
+    gemm_f32_batched(G, kp, dq, M=N, N=dk, K=Ksel, lda=Ksel, ldb=d, ldc=2 * d, b_kc=False,
+                     sa=s_str, sb=(Ksel * d, dk), sc=(N * 2 * d, dk), ksplit=1, **hb)
     # dKp_j = dS_j^T Q_j        [Ksel, dk], contraction over the N patches -> split-K
     gemm_f32_batched(G, q, dkp, M=Ksel, N=dk, K=N, lda=Ksel, ldb=ldq, ldc=d, a_kc=False, b_kc=False,
                      sa=s_str, sb=(N * ldq, dk), sc=(Ksel * d, dk), **hb)
-    return dq, dv, dkp
+    return dq, dv, dkp, dqv
 
 
 def softmax_cols_bwd(a: torch.Tensor, da: torch.Tensor, scale: float) -> torch.Tensor:
@@ -445,3 +445,36 @@ def softmax_cols_bwd(a: torch.Tensor, da: torch.Tensor, scale: float) -> torch.T
     check(lib.snuffy_softmax_cols_bwd(a.data_ptr(), da.data_ptr(), a.shape[0], a.shape[1], float(scale), ds.data_ptr(),
                                       _stream()), "snuffy_softmax_cols_bwd")
     return ds
+
+
+# ------------------------------------------------------------------ tensor-core backward operands (csrc/norm.cu, gemm_tc.cu)
+def planes_t(x: torch.Tensor, rc: int, *, mode: int = 0, stats=None, gamma=None, beta=None, row_map=None, alt=None,
+             act: str = "none", drop: Tuple[float, int, int] = (0.0, 0, 0)) -> Planes:
+    """Operand planes of x^T for x [R, C] fp32 (row-strided views allowed): plane rows = columns of x, k = rows of x.
+    mode 1: LayerNorm(x through row_map) from saved stats; mode 2: dropout(act(x))."""
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.reshape(-1, x.shape[-1]).contiguous()
+    R, C = x.shape
+    out = Planes(C, R, rc, x.device)
+    check(lib.snuffy_planes_t_fwd(x.data_ptr(), x.stride(0), R, C, rc, mode, _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(row_map),
+                                  _ptr(alt), ACT_IDS[act], float(drop[0]), drop[1] & _U64, drop[2] & _U64, out.ptr, out.stride,
+                                  _stream()), "snuffy_planes_t_fwd")
+    return out
+
+
+def weight_planes_t(weight: torch.Tensor) -> Planes:
+    """B-operand planes of W^T for W [out, in]: rows = input features, k = output features (dX = dY . W)."""
+    weight = _f32(weight, "weight")
+    return planes_t(weight, lib.snuffy_gemm_tc_block_n(weight.shape[1]))
+
+
+def gemm_tc_splitk(a: Planes, b: Planes, *, M: int, N: int, K: int, passes: int = 3) -> torch.Tensor:
+    """out [M, N] = A . B^T over a long contraction (weight gradients), split over CTAs with a deterministic fold."""
+    dev = a.buf.device
+    out = torch.empty(M, N, dtype=torch.float32, device=dev)
+    ks = lib.snuffy_gemm_tc_auto_ksplit(M, N, K)
+    ws_bytes = lib.snuffy_gemm_tc_splitk_workspace(M, N, ks)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    check(lib.snuffy_gemm_tc_splitk(a.ptr, a.stride, b.ptr, b.stride, M, N, K, passes, ks, out.data_ptr(), ws.data_ptr(),
+                                    ws_bytes, _stream()), "snuffy_gemm_tc_splitk")
+    return out

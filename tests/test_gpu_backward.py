@@ -299,7 +299,7 @@ def test_sparse_attention_backward(ops, B, n, ks, h, d):
     d_o = torch.randn(B * ks, d, device="cuda", generator=g)
     q, v = qv[:, :d], qv[:, d:]
     _, _, stats = ops.sparse_attn(q, v, kp, B, n, ks, h, want_probs=False, want_stats=True)
-    dq, dv, dkp = ops.sparse_attn_bwd(q, v, kp, d_o, stats, B, n, ks, h)
+    dq, dv, dkp, _ = ops.sparse_attn_bwd(q, v, kp, d_o, stats, B, n, ks, h)
     dk = d // h
     q64 = q.double().clone().requires_grad_(True)
     v64 = v.double().clone().requires_grad_(True)
@@ -349,3 +349,26 @@ def test_dsmil_gradients(name):
     assert abs(float(loss) - float(loss64)) < 1e-4
     _compare_grads(model, P)
     assert _rel(xg.grad.double().cpu(), x64.grad) < 2e-3
+
+
+def test_tensor_core_backward_matches_fp32_backward_at_scale():
+    """cfg2-shaped layer (d = 512, 8 heads, K = 200) on 3000 patches, train mode with dropout: the tcgen05 backward
+    (transposed split-bf16 planes + split-K) against the exact-fp32 SIMT backward of the same forward."""
+    from snuffy_b200 import snuffy
+    c = dict(n=3000, d=512, heads=8, K=200, r=0.5, depth=1, act="relu", wseed=0, xseed=7)
+    params, x = snuffy_inputs(c)
+    grads = {}
+    for precision in ("fp32", "bf16x3"):
+        model = load_params(build_snuffy(snuffy, c, ff_dropout=0.1, enc_dropout=0.1), params)
+        model.train()
+        set_precision(model, precision)
+        rs = np.random.RandomState(1)
+        force_selections(model, [rs.permutation(c["n"])[:200][None]])
+        torch.manual_seed(5)
+        classes, bag, _ = model(torch.from_numpy(x).cuda())
+        mil_loss(classes, bag, torch.ones(1, 1).cuda()).backward()
+        grads[precision] = {k: p.grad.detach().double() for k, p in model.named_parameters()}
+    for k, ref in grads["fp32"].items():
+        if ref.abs().max() < 1e-9:
+            continue
+        assert _rel(grads["bf16x3"][k], ref) < 1e-3, (k, _rel(grads["bf16x3"][k], ref))

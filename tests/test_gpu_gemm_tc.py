@@ -84,3 +84,52 @@ def test_gemm_tc_chained_like_ffn(ops):
     out, _, _ = ops.gemm_tc(hp, ops.weight_planes(t(w2)), M=M, N=d, K=dff, resid=t(x))
     ref = x + np.maximum(x.astype(np.float64) @ w1.T.astype(np.float64), 0) @ w2.T.astype(np.float64)
     assert np.abs(out.cpu().numpy() - ref).max() < 5e-5
+
+
+# ------------------------------------------------------------------ backward operands: transposed planes + split-K
+@pytest.mark.parametrize("R,C,rc", [(1000, 96, 128), (333, 512, 256), (64, 40, 128)])
+def test_planes_t_modes(ops, R, C, rc):
+    import torch.nn.functional as F
+    from helpers import decode_planes
+    g = torch.Generator(device="cuda").manual_seed(R)
+    x = torch.randn(R, C, device="cuda", generator=g)
+    # mode 0: plain transpose
+    hi, lo = decode_planes(ops.planes_t(x, rc), C, R)
+    assert np.abs((hi + lo)[:, R:]).max() == 0                       # k padding is zero
+    hi, lo = hi[:, :R], lo[:, :R]
+    ref = x.double().cpu().numpy().T
+    assert np.abs(hi + lo - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+    # mode 1: LayerNorm from saved statistics, rows redirected through row_map
+    gamma, beta = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    alt = torch.randn(5, C, device="cuda", generator=g)
+    idx = torch.tensor([[3, 17, R - 1, 0, 9]], device="cuda")
+    row_map = ops.build_row_map(idx, R)
+    y = x.clone(); y[idx[0]] = alt
+    _, _, stats = ops.ln_rows(x, gamma, beta, row_map=row_map, alt=alt, want_f32=True, want_stats=True)
+    hi, lo = decode_planes(ops.planes_t(x, rc, mode=1, stats=stats, gamma=gamma, beta=beta, row_map=row_map, alt=alt), C, R)
+    ref = F.layer_norm(y.double(), (C,), gamma.double(), beta.double()).cpu().numpy().T
+    assert np.abs((hi + lo)[:, :R] - ref).max() < 1e-4
+    # mode 2: activation of a saved pre-activation
+    hi, lo = decode_planes(ops.planes_t(x, rc, mode=2, act="gelu"), C, R)
+    assert np.abs((hi + lo)[:, :R] - F.gelu(x.double()).cpu().numpy().T).max() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 10000), (1024, 512, 3000), (128, 256, 40), (200, 64, 777)])
+def test_gemm_tc_splitk_weight_gradient(ops, M, N, K):
+    """dW[M, N] = dY^T X with dY [K, M], X [K, N]: transposed planes + split-K tcgen05 GEMM vs fp64."""
+    g = torch.Generator(device="cuda").manual_seed(K)
+    dy = torch.randn(K, M, device="cuda", generator=g)
+    x = torch.randn(K, N, device="cuda", generator=g)
+    out = ops.gemm_tc_splitk(ops.planes_t(dy, 128), ops.planes_t(x, ops.lib.snuffy_gemm_tc_block_n(N)), M=M, N=N, K=K)
+    ref = dy.double().t() @ x.double()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+def test_weight_planes_t_dx_product(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dy = torch.randn(700, 256, device="cuda", generator=g)
+    w = torch.randn(256, 96, device="cuda", generator=g)                     # nn.Linear.weight [out, in]
+    _, ap, _ = ops.ln_rows(dy, None, None, apply_ln=False, want_planes=True)
+    out, _, _ = ops.gemm_tc(ap, ops.weight_planes_t(w), M=700, N=96, K=256, passes=3)
+    ref = dy.double() @ w.double()
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-5
