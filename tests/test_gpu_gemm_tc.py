@@ -95,7 +95,7 @@ def test_planes_t_modes(ops, R, C, rc):
     x = torch.randn(R, C, device="cuda", generator=g)
     # mode 0: plain transpose
     hi, lo = decode_planes(ops.planes_t(x, rc), C, R)
-    assert np.abs((hi + lo)[:, R:]).max() == 0                       # k padding is zero
+    assert not (hi + lo)[:, R:].any()                                # k padding is zero
     hi, lo = hi[:, :R], lo[:, :R]
     ref = x.double().cpu().numpy().T
     assert np.abs(hi + lo - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
@@ -108,10 +108,11 @@ def test_planes_t_modes(ops, R, C, rc):
     _, _, stats = ops.ln_rows(x, gamma, beta, row_map=row_map, alt=alt, want_f32=True, want_stats=True)
     hi, lo = decode_planes(ops.planes_t(x, rc, mode=1, stats=stats, gamma=gamma, beta=beta, row_map=row_map, alt=alt), C, R)
     ref = F.layer_norm(y.double(), (C,), gamma.double(), beta.double()).cpu().numpy().T
-    assert np.abs((hi + lo)[:, :R] - ref).max() < 1e-4
+    assert np.abs((hi + lo)[:, :R] - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()) + 2e-6
     # mode 2: activation of a saved pre-activation
     hi, lo = decode_planes(ops.planes_t(x, rc, mode=2, act="gelu"), C, R)
-    assert np.abs((hi + lo)[:, :R] - F.gelu(x.double()).cpu().numpy().T).max() < 2e-5
+    ref = F.gelu(x.double()).cpu().numpy().T
+    assert np.abs((hi + lo)[:, :R] - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 2048, 10000), (1024, 512, 3000), (128, 256, 40), (200, 64, 777)])
