@@ -144,6 +144,23 @@ int snuffy_dsmil_pool_fwd(const float* Q, const float* qmax, const float* V, con
                           float* Bm, float* logits, float* stats_out, void* workspace,
                           int64_t workspace_bytes, snuffy_stream_t stream);
 
+/* ---- packed variable-length bags (BASELINE configs[3]; the reference loops over bags one by one, train.py:249-258)
+ * x is the packed [T, d] concatenation, cu_seqlens [B+1] int64 on the device, max_n = longest bag.  Selection returns
+ * GLOBAL row indices, so every row-wise entry point above runs on the packed tensor as one bag of T rows; only the
+ * per-bag reductions need the offsets: selection, the attention's softmax^T V reduction, and the mean-pool head.      */
+int snuffy_select_topk_varlen(const float* scores, const int64_t* cu_seqlens, int64_t B, int64_t max_n, int64_t C,
+                              int64_t K, int64_t* idx_out, uint8_t* flags, snuffy_stream_t stream);
+int snuffy_select_random_varlen(const uint8_t* flags, const int64_t* cu_seqlens, int64_t B, int64_t max_n, int64_t K,
+                                uint64_t seed, uint64_t offset, int64_t* idx_out, snuffy_stream_t stream);
+int snuffy_sparse_attn_tc_varlen_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0,
+                                     int64_t v_col0, const float* Kp, const int64_t* cu_seqlens, int64_t B,
+                                     int64_t max_n, int64_t Ksel, int64_t h, int64_t d, float* O, void* workspace,
+                                     int64_t workspace_bytes, snuffy_stream_t stream);
+int snuffy_ln_mean_head_varlen_fwd(const float* x, const int64_t* cu_seqlens, const float* gamma, const float* beta,
+                                   const float* Wh, const float* bh, int64_t B, int64_t max_n, int64_t d, int64_t C,
+                                   float* partials, uint32_t* tickets, float* pooled, float* bag_out,
+                                   snuffy_stream_t stream);
+
 /* ---- backward (train.py:259 loss.backward() through the drop-in modules; autograd only sequences these)   */
 /* Batched / split-K form of snuffy_gemm_f32 (no epilogue but alpha and bias): batch z = (zo, zi) offsets the
  * operands by zo*s?_o + zi*s?_i elements (outer = bag, inner = head slice); ksplit > 1 splits the contraction

@@ -49,6 +49,10 @@ _SIGNATURES = {
     "snuffy_sparse_attn_tc_fwd": (c_int, [P, I, I, I, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
     "snuffy_dsmil_workspace": (c_int64, [I, I, I]),
     "snuffy_dsmil_pool_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P, P, P, P, P, I, P]),
+    "snuffy_select_topk_varlen": (c_int, [P, P, I, I, I, I, P, P, P]),
+    "snuffy_select_random_varlen": (c_int, [P, P, I, I, I, c_uint64, c_uint64, P, P]),
+    "snuffy_sparse_attn_tc_varlen_fwd": (c_int, [P, I, I, I, I, P, P, I, I, I, I, I, P, P, I, P]),
+    "snuffy_ln_mean_head_varlen_fwd": (c_int, [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P]),
     "snuffy_gemm_f32_batched_workspace": (c_int64, [I, I, I, I]),
     "snuffy_gemm_f32_auto_ksplit": (c_int64, [I, I, I, I]),
     "snuffy_gemm_f32_batched": (c_int, [P, I, c_int, P, I, c_int, P, I, I, I, I, c_float, P, I, I, I, I, I, I, I, I, I, P, I, P]),

@@ -57,6 +57,7 @@ struct AttnTcParams {
     float* P_out;                     // [B, h, N, Ksel] or null (pre-dropout)
     float* stats_out;                 // [B, h, N, 2] (row max of the scaled scores, 1 / row sum) or null
     float drop_p; uint64_t seed, offset;
+    const int64_t* cu_seqlens;        // packed variable-length bags: rows [cu[b], cu[b+1]) (null: b*N .. (b+1)*N)
 };
 
 // MODE 0: all keys of a head fit one chunk (Ksel <= 256): scores, softmax and P^T V fused in one pass.
@@ -113,7 +114,8 @@ attn_tc_kernel(const AttnTcParams p) {
         const int b = item / (p.splits * p.nkc * p.h);
         const int key0 = kc * p.KC;                                         // first key of this chunk
         const int kvalid = min(p.KC, p.Ksel - key0);                        // keys of this chunk (the rest of KP is padding)
-        const int64_t g_lo = (int64_t)b * p.N, g_hi = g_lo + p.N;           // global rows of this bag
+        const int64_t g_lo = p.cu_seqlens ? p.cu_seqlens[b] : (int64_t)b * p.N;            // global rows of this bag
+        const int64_t g_hi = p.cu_seqlens ? p.cu_seqlens[b + 1] : g_lo + p.N;
         const int64_t t_first = g_lo / AT_TILE, t_last = (g_hi + AT_TILE - 1) / AT_TILE;
         const int64_t t0 = t_first + (int64_t)split * p.tiles_per_split;
         const int64_t t1 = min(t_last, t0 + p.tiles_per_split);
@@ -463,10 +465,10 @@ int64_t snuffy_sparse_attn_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int6
 
 // Same contract as snuffy_sparse_attn_fwd, but Q and V arrive as the split-bf16 planes the Q|V projection wrote
 // (planes over [B*N, ldk] columns, Q at column q_col0, V at column v_col0; ldk, q_col0, v_col0 multiples of 32).
-int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,
-                              const float* Kp, int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d,
-                              float dropout_p, uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
-                              void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+static int launch_attn_tc(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,
+                          const float* Kp, int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d,
+                          float dropout_p, uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
+                          void* workspace, int64_t workspace_bytes, const int64_t* cu_seqlens, cudaStream_t stream) {
     SNUFFY_REQUIRE(qv_planes && Kp && O && workspace, "snuffy_sparse_attn_tc_fwd: null pointer");
     const AttnTcPlan pl = plan_attn_tc(B, N, Ksel, h, d);
     SNUFFY_REQUIRE(pl.ok, "snuffy_sparse_attn_tc_fwd: unsupported shape (h=%lld d=%lld Ksel=%lld)", (long long)h,
@@ -489,6 +491,7 @@ int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64
     p.stats_part = p.O_part + (int64_t)pl.splits * B * Ksel * d;
     p.P_out = P_out; p.stats_out = stats_out;
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
+    p.cu_seqlens = cu_seqlens;
     if (pl.nkc == 1) {
         SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         attn_tc_kernel<0><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
@@ -500,6 +503,26 @@ int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64
     }
     launch_fold_partials(p.O_part, pl.splits, B * Ksel * d / 4, O, stream);
     return check_launch("snuffy_sparse_attn_tc_fwd", pl.nkc == 1 ? 2 : 3);
+}
+
+int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,
+                              const float* Kp, int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d,
+                              float dropout_p, uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
+                              void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+    return launch_attn_tc(qv_planes, plane_stride, ldk, q_col0, v_col0, Kp, B, N, Ksel, h, d, dropout_p, seed, offset, O, P_out,
+                          stats_out, workspace, workspace_bytes, nullptr, stream);
+}
+
+// Packed variable-length bags (inference): the planes cover the packed [T, ldk] rows, bag b = rows
+// [cu_seqlens[b], cu_seqlens[b+1]), every bag has Ksel keys (Kp [B*Ksel, d]); max_n = longest bag sizes the work split and
+// the workspace (snuffy_sparse_attn_tc_workspace(B, max_n, ...)).
+int snuffy_sparse_attn_tc_varlen_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0,
+                                     int64_t v_col0, const float* Kp, const int64_t* cu_seqlens, int64_t B, int64_t max_n,
+                                     int64_t Ksel, int64_t h, int64_t d, float* O, void* workspace, int64_t workspace_bytes,
+                                     cudaStream_t stream) {
+    SNUFFY_REQUIRE(cu_seqlens, "snuffy_sparse_attn_tc_varlen_fwd: null cu_seqlens");
+    return launch_attn_tc(qv_planes, plane_stride, ldk, q_col0, v_col0, Kp, B, max_n, Ksel, h, d, 0.f, 0, 0, O, nullptr, nullptr,
+                          workspace, workspace_bytes, cu_seqlens, stream);
 }
 
 #ifdef ATTN_DEBUG_TIMING

@@ -256,13 +256,16 @@ __global__ void __launch_bounds__(256)
 ln_mean_head_reg_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                         const float* __restrict__ Wh, const float* __restrict__ bh, int64_t N, int d, int C,
                         float* __restrict__ partials, unsigned int* __restrict__ tickets, float* __restrict__ stats,
-                        float* __restrict__ pooled, float* __restrict__ bag_out) {
+                        float* __restrict__ pooled, float* __restrict__ bag_out, const int64_t* __restrict__ cu_seqlens) {
     extern __shared__ __align__(16) float hs[];            // [8 warps][d]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = gridDim.x, chunk = blockIdx.x, bag = blockIdx.y;
+    int64_t row_base = (int64_t)bag * N;                    // packed variable-length bags: rows [cu[bag], cu[bag+1])
+    if (cu_seqlens) { row_base = cu_seqlens[bag]; N = cu_seqlens[bag + 1] - row_base; }
     const int64_t per = (N + chunks - 1) / chunks;
     const int64_t r0 = chunk * per, r1 = min(N, r0 + per);
-    const float* xb = x + (int64_t)bag * N * d;
+    const float* xb = x + row_base * d;
+    if (stats) stats += row_base * 2 - (int64_t)bag * N * 2;
     const float inv_d = 1.f / (float)d;
     float4 acc[MAXIT];
 #pragma unroll
@@ -318,13 +321,16 @@ __global__ void __launch_bounds__(256)
 ln_mean_head_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ Wh, const float* __restrict__ bh, int64_t N, int d, int C,
                     float* __restrict__ partials, unsigned int* __restrict__ tickets, float* __restrict__ stats,
-                    float* __restrict__ pooled, float* __restrict__ bag_out) {
+                    float* __restrict__ pooled, float* __restrict__ bag_out, const int64_t* __restrict__ cu_seqlens) {
     extern __shared__ __align__(16) float hs[];            // [8 warps][d] then reused
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunks = gridDim.x, chunk = blockIdx.x, bag = blockIdx.y;
+    int64_t row_base = (int64_t)bag * N;
+    if (cu_seqlens) { row_base = cu_seqlens[bag]; N = cu_seqlens[bag + 1] - row_base; }
     const int64_t per = (N + chunks - 1) / chunks;
     const int64_t r0 = chunk * per, r1 = min(N, r0 + per);
-    const float* xb = x + (int64_t)bag * N * d;
+    const float* xb = x + row_base * d;
+    if (stats) stats += row_base * 2 - (int64_t)bag * N * 2;
     float* wacc = hs + (size_t)warp * d;
     for (int e = lane; e < d; e += 32) wacc[e] = 0.f;
     for (int64_t r = r0 + warp; r < r1; r += 8) {
@@ -431,9 +437,9 @@ int64_t snuffy_ln_mean_head_chunks(int64_t B, int64_t N) {
 }
 
 // bag[B, C] = head( mean_n LN_f(x[b, n, :]) )        snuffy.py:86 + 71
-int snuffy_ln_mean_head_fwd(const float* x, const float* gamma, const float* beta, const float* Wh, const float* bh,
-                            int64_t B, int64_t N, int64_t d, int64_t C, float* partials, uint32_t* tickets,
-                            float* stats, float* pooled, float* bag_out, cudaStream_t stream) {
+static int launch_ln_mean_head(const float* x, const float* gamma, const float* beta, const float* Wh, const float* bh,
+                               int64_t B, int64_t N, int64_t d, int64_t C, float* partials, uint32_t* tickets,
+                               float* stats, float* pooled, float* bag_out, const int64_t* cu_seqlens, cudaStream_t stream) {
     SNUFFY_REQUIRE(x && gamma && beta && Wh && partials && tickets && bag_out, "snuffy_ln_mean_head_fwd: null pointer");
     SNUFFY_REQUIRE(B >= 1 && N >= 1 && C >= 1 && d % 4 == 0 && (uintptr_t)x % 16 == 0,
                    "snuffy_ln_mean_head_fwd: needs d %% 4 == 0 and 16-byte aligned rows (d=%lld)", (long long)d);
@@ -447,17 +453,33 @@ int snuffy_ln_mean_head_fwd(const float* x, const float* gamma, const float* bet
         if (smem > 48 * 1024)
             SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_reg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ln_mean_head_reg_kernel<4><<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
-                                                                stats, pooled, bag_out);
+                                                                stats, pooled, bag_out, cu_seqlens);
     } else if (d <= 1024) {
         if (smem > 48 * 1024)
             SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ln_mean_head_reg_kernel<8><<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
-                                                                stats, pooled, bag_out);
+                                                                stats, pooled, bag_out, cu_seqlens);
     } else {
         ln_mean_head_kernel<<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
-                                                         stats, pooled, bag_out);
+                                                         stats, pooled, bag_out, cu_seqlens);
     }
     return check_launch("snuffy_ln_mean_head_fwd");
+}
+
+int snuffy_ln_mean_head_fwd(const float* x, const float* gamma, const float* beta, const float* Wh, const float* bh,
+                            int64_t B, int64_t N, int64_t d, int64_t C, float* partials, uint32_t* tickets,
+                            float* stats, float* pooled, float* bag_out, cudaStream_t stream) {
+    return launch_ln_mean_head(x, gamma, beta, Wh, bh, B, N, d, C, partials, tickets, stats, pooled, bag_out, nullptr, stream);
+}
+
+// packed variable-length bags: x [T, d], bag b = rows [cu_seqlens[b], cu_seqlens[b+1]); max_n sizes the grid / partials
+// (snuffy_ln_mean_head_chunks(B, max_n)).
+int snuffy_ln_mean_head_varlen_fwd(const float* x, const int64_t* cu_seqlens, const float* gamma, const float* beta,
+                                   const float* Wh, const float* bh, int64_t B, int64_t max_n, int64_t d, int64_t C,
+                                   float* partials, uint32_t* tickets, float* pooled, float* bag_out, cudaStream_t stream) {
+    SNUFFY_REQUIRE(cu_seqlens, "snuffy_ln_mean_head_varlen_fwd: null cu_seqlens");
+    return launch_ln_mean_head(x, gamma, beta, Wh, bh, B, max_n, d, C, partials, tickets, nullptr, pooled, bag_out, cu_seqlens,
+                               stream);
 }
 
 }  // extern "C"

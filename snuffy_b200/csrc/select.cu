@@ -84,7 +84,8 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t offset, 
 template <int MODE>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, int cache_keys,
-              uint8_t* __restrict__ flags, uint64_t seed, uint64_t offset, int64_t* __restrict__ out) {
+              uint8_t* __restrict__ flags, uint64_t seed, uint64_t offset, int64_t* __restrict__ out,
+              const int64_t* __restrict__ cu_seqlens) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint64_t* sortbuf = reinterpret_cast<uint64_t*>(sel_smem);
     uint32_t* keys = reinterpret_cast<uint32_t*>(sel_smem + (size_t)Kpad * 8);
@@ -94,8 +95,13 @@ select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, i
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int col = blockIdx.x, bag = blockIdx.y;
-    const float* sc = scores ? scores + ((int64_t)bag * N) * C + col : nullptr;
-    uint8_t* fl = flags ? flags + (int64_t)bag * N : nullptr;
+    // packed variable-length bags: rows [cu[bag], cu[bag+1]) of one [T, C] score matrix; the indices written are GLOBAL
+    // rows of the packed tensor, so every row-wise kernel downstream runs on it as one "bag" of T rows
+    int64_t base = (int64_t)bag * N;
+    if (cu_seqlens) { base = cu_seqlens[bag]; N = (int)(cu_seqlens[bag + 1] - base); }
+    const int64_t idx_add = cu_seqlens ? base : 0;
+    const float* sc = scores ? scores + base * C + col : nullptr;
+    uint8_t* fl = flags ? flags + base : nullptr;
 
     auto raw_key = [&](int i) -> uint32_t {
         if (MODE == 0) return float_key(sc[(int64_t)i * C]);
@@ -206,7 +212,7 @@ select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, i
     int64_t* o = out + ((int64_t)bag * gridDim.x + col) * K;
     for (int r = tid; r < K; r += SEL_THREADS) {
         const uint32_t idx = ~(uint32_t)sortbuf[r];
-        o[r] = (int64_t)idx;
+        o[r] = (int64_t)idx + idx_add;
         if (MODE == 0 && fl) fl[idx] = 1;
     }
 }
@@ -294,7 +300,8 @@ int snuffy_scores_fwd(const float* x, const float* W, const float* bias, float* 
 static int next_pow2(int v) { int p = 2; while (p < v) p <<= 1; return p; }
 
 static int launch_select(int mode, const float* scores, int64_t B, int64_t N, int64_t C, int64_t K,
-                         uint8_t* flags, uint64_t seed, uint64_t offset, int64_t* out, cudaStream_t stream) {
+                         uint8_t* flags, uint64_t seed, uint64_t offset, int64_t* out, cudaStream_t stream,
+                         const int64_t* cu_seqlens = nullptr) {
     SNUFFY_REQUIRE(B >= 1 && N >= 1 && C >= 1, "select: bad shape B=%lld N=%lld C=%lld", (long long)B,
                    (long long)N, (long long)C);
     SNUFFY_REQUIRE(K >= 0 && K <= N, "select: K=%lld must be in [0, N=%lld]", (long long)K, (long long)N);
@@ -308,11 +315,11 @@ static int launch_select(int mode, const float* scores, int64_t B, int64_t N, in
     if (mode == 0) {
         SNUFFY_CUDA(cudaFuncSetAttribute(select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         select_kernel<0><<<grid, SEL_THREADS, smem, stream>>>(scores, (int)N, (int)C, (int)K, Kpad, cache, flags,
-                                                              seed, offset, out);
+                                                              seed, offset, out, cu_seqlens);
     } else {
         SNUFFY_CUDA(cudaFuncSetAttribute(select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         select_kernel<1><<<grid, SEL_THREADS, smem, stream>>>(nullptr, (int)N, 1, (int)K, Kpad, cache, flags, seed,
-                                                              offset, out);
+                                                              offset, out, cu_seqlens);
     }
     return check_launch("snuffy_select");
 }
@@ -331,6 +338,20 @@ int snuffy_select_random(const uint8_t* flags, int64_t B, int64_t N, int64_t K, 
                          int64_t* idx_out, cudaStream_t stream) {
     SNUFFY_REQUIRE(flags && idx_out, "snuffy_select_random: null pointer");
     return launch_select(1, nullptr, B, N, 1, K, const_cast<uint8_t*>(flags), seed, offset, idx_out, stream);
+}
+
+// Packed variable-length forms (BASELINE configs[3]): bag b owns rows [cu_seqlens[b], cu_seqlens[b+1]) of the packed
+// [T, C] scores / [T] flags (cu_seqlens: B+1 int64 on the device; max_n = longest bag; every bag needs >= K rows, which the
+// caller checks on the host).  The indices written are GLOBAL rows of the packed tensor.
+int snuffy_select_topk_varlen(const float* scores, const int64_t* cu_seqlens, int64_t B, int64_t max_n, int64_t C, int64_t K,
+                              int64_t* idx_out, uint8_t* flags, cudaStream_t stream) {
+    SNUFFY_REQUIRE(scores && idx_out && cu_seqlens, "snuffy_select_topk_varlen: null pointer");
+    return launch_select(0, scores, B, max_n, C, K, flags, 0, 0, idx_out, stream, cu_seqlens);
+}
+int snuffy_select_random_varlen(const uint8_t* flags, const int64_t* cu_seqlens, int64_t B, int64_t max_n, int64_t K,
+                                uint64_t seed, uint64_t offset, int64_t* idx_out, cudaStream_t stream) {
+    SNUFFY_REQUIRE(flags && idx_out && cu_seqlens, "snuffy_select_random_varlen: null pointer");
+    return launch_select(1, nullptr, B, max_n, 1, K, const_cast<uint8_t*>(flags), seed, offset, idx_out, stream, cu_seqlens);
 }
 
 // out[B, cap] = ascending indices of flagged rows (first cap of them), counts[B] = number flagged.

@@ -220,18 +220,29 @@ def tc_supported(d: int) -> bool:
 
 def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w: LayerWeights, heads: int,
                           activation: str, precision: str, want_probs: bool, save: bool = False,
-                          attn_dropout: float = 0.0, enc_dropout: float = 0.0, ff_dropout: float = 0.0
+                          attn_dropout: float = 0.0, enc_dropout: float = 0.0, ff_dropout: float = 0.0,
+                          varlen: Optional[Tuple[torch.Tensor, int, int, int]] = None
                           ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[LayerTape]]:
     """One EncoderLayer (snuffy.py:126-157) on x [B*N, d] with the selection sel [B, Ksel].
 
     The three dropout rates are 0 in eval mode; in train mode they are the reference's (attention probabilities
     snuffy.py:166-167, both sublayer outputs 108/110, FFN hidden 225), drawn from counter-based masks that the backward
-    regenerates.  Returns (x_next [B*N, d], P [B, h, N, Ksel] or None, tape or None)."""
+    regenerates.  Returns (x_next [B*N, d], P [B, h, N, Ksel] or None, tape or None).
+
+    varlen = (cu_seqlens [bags+1] int64 on the device, bags, keys per bag, longest bag): x is the packed concatenation of
+    variable-length bags, passed as B = 1, N = T with `sel` [1, bags*Ksel] holding GLOBAL rows.  Every row-wise kernel is
+    unchanged; only the attention reduction needs the bag boundaries (inference only)."""
     d = x.shape[1]
     rows = B * N
     Ksel = sel.shape[1]
     if precision != "fp32" and not tc_supported(d):
         precision = "fp32"                                   # tcgen05 planes need d % 8 == 0; still the CUDA path
+    if varlen is not None:
+        cu, bags, ksel_bag, max_n = varlen
+        if save or want_probs or precision == "fp32" or attn_dropout > 0 or \
+                not ops.sparse_attn_tc_supported(bags, max_n, ksel_bag, heads, d):
+            raise NotImplementedError("packed variable-length bags: inference on the tensor-core path only "
+                                      "(eval mode, return_attn = False, head size a multiple of 32 and <= 128)")
     w.prepare(precision)
     passes = 1 if precision == "bf16x1" else 3
     # Inference shares ONE set of normalised planes z = (x - mean) * rstd between LN1 and LN2 (their affines are folded
@@ -254,7 +265,7 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         else:
             _, up, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_planes=True, want_stats=save)
             wqv_p, bqv = w.wqv_planes, w.bqv
-        attn_tc = ATTN_TC and ops.sparse_attn_tc_supported(B, N, Ksel, heads, d)
+        attn_tc = varlen is not None or (ATTN_TC and ops.sparse_attn_tc_supported(B, N, Ksel, heads, d))
         # the projection writes Q|V straight as the planes the tensor-core attention consumes (fp32 only if saved)
         qv, _, qvp = ops.gemm_tc(up, wqv_p, M=rows, N=2 * d, K=d, passes=passes, bias=bqv,
                                  want_out=save or not attn_tc, want_planes=attn_tc)
@@ -267,7 +278,9 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     def draw(p):
         return (float(p),) + _RANDOM.next() if p > 0.0 else (0.0, 0, 0)
     drop, drop_enc1, drop_ff, drop_enc2 = draw(attn_dropout), draw(enc_dropout), draw(ff_dropout), draw(enc_dropout)
-    if attn_tc:
+    if varlen is not None:
+        o, probs, attn_stats = ops.sparse_attn_tc_varlen(qvp, kp, cu, bags, max_n, ksel_bag, heads, d), None, None
+    elif attn_tc:
         o, probs, attn_stats = ops.sparse_attn_tc(qvp, kp, B, N, Ksel, heads, d, want_probs=want_probs, want_stats=save,
                                                   dropout_p=drop[0], seed=drop[1], offset=drop[2])
     else:

@@ -478,3 +478,51 @@ def gemm_tc_splitk(a: Planes, b: Planes, *, M: int, N: int, K: int, passes: int 
     check(lib.snuffy_gemm_tc_splitk(a.ptr, a.stride, b.ptr, b.stride, M, N, K, passes, ks, out.data_ptr(), ws.data_ptr(),
                                     ws_bytes, _stream()), "snuffy_gemm_tc_splitk")
     return out
+
+
+# ------------------------------------------------------------------ packed variable-length bags (inference)
+def select_topk_varlen(c: torch.Tensor, cu: torch.Tensor, B: int, max_n: int, k: int, flags: Optional[torch.Tensor] = None):
+    """c [T, C] packed scores -> idx [B, C, k] int64 GLOBAL rows (per bag and class, descending score)."""
+    c = _f32(c, "c")
+    C = c.shape[-1]
+    idx = torch.empty(B, C, k, dtype=torch.int64, device=c.device)
+    check(lib.snuffy_select_topk_varlen(c.data_ptr(), cu.data_ptr(), B, max_n, C, k, idx.data_ptr(), _ptr(flags), _stream()),
+          "snuffy_select_topk_varlen")
+    return idx
+
+
+def select_random_varlen(flags: torch.Tensor, cu: torch.Tensor, B: int, max_n: int, k: int, seed: int, offset: int):
+    idx = torch.empty(B, k, dtype=torch.int64, device=flags.device)
+    check(lib.snuffy_select_random_varlen(flags.data_ptr(), cu.data_ptr(), B, max_n, k, seed & _U64, offset & _U64,
+                                          idx.data_ptr(), _stream()), "snuffy_select_random_varlen")
+    return idx
+
+
+def sparse_attn_tc_varlen(qv_planes: Planes, kp: torch.Tensor, cu: torch.Tensor, B: int, max_n: int, Ksel: int, h: int, d: int):
+    kp = _f32(kp, "kp")
+    ws_bytes = lib.snuffy_sparse_attn_tc_workspace(B, max_n, Ksel, h, d)
+    if ws_bytes < 0:
+        raise ValueError("shape not served by the tensor-core attention kernel")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=kp.device)
+    o = torch.empty(B * Ksel, d, dtype=torch.float32, device=kp.device)
+    check(lib.snuffy_sparse_attn_tc_varlen_fwd(qv_planes.ptr, qv_planes.stride, qv_planes.K, 0, d, kp.data_ptr(), cu.data_ptr(), B,
+                                               max_n, Ksel, h, d, o.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+          "snuffy_sparse_attn_tc_varlen_fwd")
+    return o
+
+
+def ln_mean_head_varlen(x: torch.Tensor, cu: torch.Tensor, B: int, max_n: int, gamma, beta, w_head, b_head) -> torch.Tensor:
+    x = _f32(x, "x")
+    d = x.shape[-1]
+    C = w_head.shape[0]
+    chunks = lib.snuffy_ln_mean_head_chunks(B, max_n)
+    key = (x.device.index, B)
+    tickets = _HEAD_WS.get(key)
+    if tickets is None:
+        tickets = _HEAD_WS[key] = torch.zeros(B, dtype=torch.int32, device=x.device)
+    partials = torch.empty(B * chunks * d, dtype=torch.float32, device=x.device)
+    bag = torch.empty(B, C, dtype=torch.float32, device=x.device)
+    check(lib.snuffy_ln_mean_head_varlen_fwd(x.data_ptr(), cu.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w_head.data_ptr(),
+                                             _ptr(b_head), B, max_n, d, C, partials.data_ptr(), tickets.data_ptr(), None,
+                                             bag.data_ptr(), _stream()), "snuffy_ln_mean_head_varlen_fwd")
+    return bag

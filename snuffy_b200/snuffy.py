@@ -58,3 +58,50 @@ def forward_bags(milnet: MILNet, x: torch.Tensor):
     b = milnet.b_classifier
     bag = ln_mean_head_fn(h, enc.norm.weight, enc.norm.bias, b.linear.weight, b.linear.bias)
     return classes, bag, attn
+
+
+def forward_packed(milnet: MILNet, x: torch.Tensor, cu_seqlens):
+    """Packed variable-length extension (BASELINE configs[3]): `x` [T, d] is the concatenation of B bags of different
+    lengths, `cu_seqlens` their B + 1 row offsets (list or tensor).  One launch sequence for all bags: every row-wise kernel
+    runs on the packed rows; selection, the attention reduction and the mean-pool head are per bag.  Inference only.
+    Returns (classes [T, 1], bag [B, 1]).  Every bag needs at least big_lambda patches (shorter bags: call the model)."""
+    if x.dim() != 2:
+        raise ValueError(f"forward_packed expects the packed bags as [T, d], got {tuple(x.shape)}")
+    if torch.is_grad_enabled() and any(p.requires_grad for p in milnet.parameters()):
+        raise NotImplementedError("forward_packed is an inference path: wrap the call in torch.no_grad()")
+    cu_host = [int(v) for v in (cu_seqlens.tolist() if torch.is_tensor(cu_seqlens) else cu_seqlens)]
+    B = len(cu_host) - 1
+    lens = [cu_host[i + 1] - cu_host[i] for i in range(B)]
+    if B < 1 or cu_host[0] != 0 or cu_host[-1] != x.shape[0] or min(lens) < 1:
+        raise ValueError("cu_seqlens must start at 0, end at T and describe non-empty bags")
+    T, d = x.shape
+    max_n = max(lens)
+    cu = torch.tensor(cu_host, dtype=torch.int64, device=x.device)
+    from . import ops
+    from .autograd import scores_fn
+    lin = milnet.i_classifier.fc[0]
+    classes = scores_fn(x, lin.weight, lin.bias)                                        # [T, 1]
+    enc = milnet.b_classifier.encoder
+    h = x.detach().contiguous()
+    top = flags = None
+    for layer in enc.layers:
+        kt = engine.k_top_of(layer.big_lambda, layer.random_patch_share)
+        kr = int(layer.big_lambda * layer.random_patch_share)
+        if min(lens) < kt + kr:
+            raise ValueError(f"forward_packed: every bag needs >= {kt + kr} patches (shortest has {min(lens)})")
+        if top is None:                                                                  # c is the same for every layer
+            flags = torch.zeros(T, dtype=torch.uint8, device=x.device)
+            top = ops.select_topk_varlen(classes.view(T, 1), cu, B, max_n, kt, flags).view(B, kt)
+        sel = top
+        if kr > 0:
+            seed, offset = engine._RANDOM.next()
+            sel = torch.cat((top, ops.select_random_varlen(flags, cu, B, max_n, kr, seed, offset)), dim=1)
+        ksel = sel.shape[1]
+        h, _, _ = engine.encoder_layer_forward(h, 1, T, sel.reshape(1, B * ksel).contiguous(), layer.layer_weights(),
+                                               layer.self_attn.h, layer.feed_forward.activation_name,
+                                               layer._effective_precision(), want_probs=False,
+                                               varlen=(cu, B, ksel, max_n))
+    b = milnet.b_classifier
+    bag = ops.ln_mean_head_varlen(h, cu, B, max_n, enc.norm.weight.detach(), enc.norm.bias.detach(), b.linear.weight.detach(),
+                                  b.linear.bias.detach())
+    return classes, bag

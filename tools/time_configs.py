@@ -56,3 +56,21 @@ for name, mod, kw, B, n in cases:
         ms = timeit(fn)
     print(json.dumps({"config": name, "bags": B, "N": n, **{k: v for k, v in kw.items() if k != "multiclass"},
                       "ms_per_call": round(ms, 4), "slides_per_s": round(B / ms * 1e3, 1)}), flush=True)
+
+# cfg4 proper: 64 bags with N ~ log-uniform[1k, 50k] (seed 7), K sweep, packed into one launch sequence vs one call per bag
+import numpy as np
+rs = np.random.RandomState(7)
+lens = np.exp(rs.uniform(np.log(1000), np.log(50000), 64)).astype(int)
+cu = np.concatenate([[0], np.cumsum(lens)])
+xp = torch.randn(int(cu[-1]), 512, device="cuda")
+for K in (64, 256, 1024):
+    m = build(snuffy, d=512, h=8, K=K, r=0.5, depth=1, C=1, multiclass=False)
+    with torch.no_grad():
+        ok = lens >= K
+        cu_ok = np.concatenate([[0], np.cumsum(lens[ok])])
+        xs = torch.cat([xp[cu[i]:cu[i + 1]] for i in range(64) if ok[i]])
+        ms_packed = timeit(lambda: snuffy.forward_packed(m, xs, cu_ok), iters=3)
+        ms_loop = timeit(lambda: [m(xp[cu[i]:cu[i + 1]][None]) for i in range(64) if ok[i]], iters=2)
+    print(json.dumps({"config": "cfg4 varlen 64 bags N~logU[1k,50k]", "K": K, "bags": int(ok.sum()), "rows": int(cu_ok[-1]),
+                      "ms_packed": round(ms_packed, 3), "ms_one_call_per_bag": round(ms_loop, 3),
+                      "slides_per_s_packed": round(ok.sum() / ms_packed * 1e3, 1)}), flush=True)
