@@ -511,7 +511,7 @@ def main():
             line["roofline"]["kernel"] = kernels[0]["kernel"]
             line["roofline"]["peak_source"] = kernels[0].get("peak_source")
             line["kernels"] = kernels
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:                # the CPU arm is timed beside the GPU number at N = 1 only
             line["cpu_baseline"] = cpu_baseline(params)
         print(json.dumps(line), flush=True)
     if world > 1:
