@@ -157,3 +157,41 @@ def test_two_gpu_data_parallel_equals_gradient_averaging():
     trainer.train_step(x, torch.tensor([[labels[i]] for i in ids]))
     g1, g2 = trainer.flat.flat_grad.cpu(), out[0][1]
     assert (g1 - g2).abs().max() < 1e-5 * max(1.0, float(g2.abs().max())), float((g1 - g2).abs().max())
+
+
+def test_reference_style_training_loop_with_torch_optimizer():
+    """The literal caller pattern of train.py:249-264, 828-846, 468-473 on the drop-in module: torch's BCEWithLogitsLoss on
+    (bag, max instance), loss.backward(), torch.optim.AdamW.step() (in-place updates bump the parameter versions, so the
+    cached operand planes are rebuilt), three bags -- against the same loop over the reference op sequence in float64."""
+    from snuffy_b200 import snuffy
+    z, c = load_golden("bin_tiny_relu")
+    params, _ = snuffy_inputs(c)
+    model = load_params(build_snuffy(snuffy, c), params)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.train()
+    criterion = torch.nn.BCEWithLogitsLoss()
+    w = torch.tensor(0.5, device="cuda")                                      # single_weight_parameter (train.py:804)
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-3, betas=(0.5, 0.9), weight_decay=5e-3)
+    P64 = _params64(params)
+    ropt = torch.optim.AdamW(list(P64.values()), lr=2e-3, betas=(0.5, 0.9), weight_decay=5e-3)
+    rs = np.random.RandomState(9)
+    ksel = len(z["ref32_sel"][0])
+    for step in range(3):
+        bag_np = rs.standard_normal((1, c["n"], c["d"])).astype(np.float32)
+        label = torch.tensor([[float(step & 1)]])
+        sels = [rs.permutation(c["n"])[:ksel][None] for _ in range(c["depth"])]
+        force_selections(model, sels)
+        ins_prediction, bag_prediction, _ = model(torch.from_numpy(bag_np).cuda())
+        max_prediction, _ = torch.max(ins_prediction, 1)
+        loss = w * criterion(bag_prediction.view(1, -1), label.cuda().view(1, -1)) + \
+            (1 - w) * criterion(max_prediction.view(1, -1), label.cuda().view(1, -1))
+        loss.backward()
+        opt.step(); opt.zero_grad()
+        ropt.zero_grad()
+        c64, bag64 = ref_forward(torch.from_numpy(bag_np).double(), P64, c["heads"], c["depth"], c["act"],
+                                 [torch.from_numpy(s) for s in sels])
+        rl = ref_mil_loss(c64, bag64, label.double())
+        rl.backward(); ropt.step()
+        assert abs(float(loss) - float(rl)) < 2e-4, (step, float(loss), float(rl))
