@@ -167,12 +167,18 @@ class EncoderLayerFunction(torch.autograd.Function):
         dxs_new = ops.gather_rows(dy.view(B, N, d), t.sel).view(B * ksel, d)
         dz = ops.act_bwd(None, dxs_new, drop=t.drop_enc1)[0] if t.drop_enc1[0] > 0 else dxs_new
         d_bo = ops.colsum(dz).view(-1)
-        d_wo = ops.matmul_tn(dz, t.o)
-        d_o = ops.matmul_nn(dz, w.wo)                                              # [B*Ksel, d]
+        if tc:
+            d_wo = ops.gemm_tc_splitk(ops.planes_t(dz, 128), ops.planes_t(t.o, rc_d), M=d, N=d, K=B * ksel, passes=passes)
+        else:
+            d_wo = ops.matmul_tn(dz, t.o)
+        d_o = dx_gemm(dz, w.wo, w.wot_planes, d)                                   # [B*Ksel, d]
         q, v = t.qv[:, :d], t.qv[:, d:]
         dq, dv, dkp, dqv = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)
         d_bk = ops.colsum(dkp).view(-1)                                            # == 0 up to rounding (App. B-16)
-        d_wk = ops.matmul_tn(dkp, t.xs)
+        if tc:
+            d_wk = ops.gemm_tc_splitk(ops.planes_t(dkp, 128), ops.planes_t(t.xs, rc_d), M=d, N=d, K=B * ksel, passes=passes)
+        else:
+            d_wk = ops.matmul_tn(dkp, t.xs)
         d_bqv = ops.colsum(dqv).view(-1)
         d_bq, d_bv = d_bqv[:d], d_bqv[d:]
         if tc:
@@ -189,7 +195,7 @@ class EncoderLayerFunction(torch.autograd.Function):
         dx, d_g1, d_be1 = ops.ln_rows_bwd(t.x_in, t.ln1_stats, w.g1, dy=du1, add=dy, want_dx=need[1])
         if dx is not None:
             # raw selected rows also feed the key projection: dx[S] += dKp Wk  (the xs residual is already in `add`)
-            ops.scatter_add_rows(dx.view(B, N, d), t.sel, ops.matmul_nn(dkp, w.wk))
+            ops.scatter_add_rows(dx.view(B, N, d), t.sel, dx_gemm(dkp, w.wk, w.wkt_planes, d))
             dx = dx.view(B, N, d)
         ctx.tape = None
         return (None, dx, None, d_wq, d_bq, d_wk, d_bk, d_wv, d_bv, d_wo, d_bo, d_w1, d_b1, d_w2, d_b2,

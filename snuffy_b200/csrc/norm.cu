@@ -234,8 +234,16 @@ __device__ __forceinline__ void ln_mean_head_tail(float* hs, const float* __rest
     __threadfence();
     const float inv_n = 1.f / (float)N;
     for (int e = threadIdx.x; e < d; e += blockDim.x) {
-        float s = 0.f;
-        for (int ch = 0; ch < chunks; ++ch) s += __ldcg(partials + ((int64_t)bag * chunks + ch) * d + e);
+        // fixed summation order (deterministic); 8 independent loads in flight: this serial tail is what a single bag waits on
+        const float* col = partials + (int64_t)bag * chunks * d + e;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int ch = 0;
+        for (; ch + 8 <= chunks; ch += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += __ldcg(col + (int64_t)(ch + u) * d);
+        }
+        for (; ch < chunks; ++ch) a[0] += __ldcg(col + (int64_t)ch * d);
+        const float s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
         const float p = gamma[e] * (s * inv_n) + beta[e];
         hs[e] = p;
         if (pooled) pooled[(int64_t)bag * d + e] = p;

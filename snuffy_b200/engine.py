@@ -164,6 +164,8 @@ class LayerWeights:
     w2t_planes: Optional[Planes] = None
     w1t_planes: Optional[Planes] = None
     wqvt_planes: Optional[Planes] = None
+    wot_planes: Optional[Planes] = None
+    wkt_planes: Optional[Planes] = None
 
     def prepare(self, precision: str) -> None:
         if self.wqv is None:
@@ -182,6 +184,8 @@ class LayerWeights:
             self.w2t_planes = ops.weight_planes_t(self.w2.detach())
             self.w1t_planes = ops.weight_planes_t(self.w1.detach())
             self.wqvt_planes = ops.weight_planes_t(self.wqv)
+            self.wot_planes = ops.weight_planes_t(self.wo.detach())
+            self.wkt_planes = ops.weight_planes_t(self.wk.detach())
 
     def prepare_folded(self) -> None:
         if self.wqv_fold_planes is None:
@@ -269,7 +273,9 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         # the projection writes Q|V straight as the planes the tensor-core attention consumes (fp32 only if saved)
         qv, _, qvp = ops.gemm_tc(up, wqv_p, M=rows, N=2 * d, K=d, passes=passes, bias=bqv,
                                  want_out=save or not attn_tc, want_planes=attn_tc)
-    small_tc = precision != "fp32" and B * Ksel >= 256          # [B*Ksel, d] projections: tensor cores once they fill tiles
+    # [B*Ksel, d] key / output projections: a handful of tcgen05 tiles beat the SIMT kernel even for one bag (200 rows:
+    # 8 SIMT CTAs looping over K take ~90 us, four tcgen05 CTAs ~10 us)
+    small_tc = precision != "fp32"
     if small_tc:
         _, xsp, _ = ops.ln_rows(xs, None, None, apply_ln=False, want_planes=True)
         kp, _, _ = ops.gemm_tc(xsp, w.wk_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bk)
