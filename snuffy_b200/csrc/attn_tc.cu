@@ -25,7 +25,11 @@ namespace snuffy {
 
 void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream);
 
-constexpr int AT_THREADS = 320;          // producer + MMA issuer + 8 softmax warps
+#ifndef AT_PARTS_N
+#define AT_PARTS_N 2
+#endif
+constexpr int AT_PARTS = AT_PARTS_N;     // softmax warps per TMEM lane quadrant (each owns a contiguous range of key chunks)
+constexpr int AT_THREADS = 64 + 128 * AT_PARTS;   // producer + MMA issuer + 4 * AT_PARTS softmax warps
 constexpr int AT_TILE = 128;            // queries per tile (UMMA M)
 constexpr uint32_t AT_O_COL = 256;      // TMEM column of the O accumulators
 
@@ -78,7 +82,7 @@ attn_tc_kernel(const AttnTcParams p) {
     unsigned char* sV = sQ + 2 * QV_PLANE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * QV_PLANE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    float* sRed = reinterpret_cast<float*>(bars + 10);       // [2 tile parities][max | sum][2 halves][128 rows]
+    float* sRed = reinterpret_cast<float*>(bars + 10);       // [max | sum][AT_PARTS][128 rows] (single-buffered: s_full(t+1) orders all reads of tile t first)
     const uint32_t b0 = smem_u32(bars);
     const uint32_t q_full = b0, q_empty = b0 + 8, v_full = b0 + 16, v_empty = b0 + 24, s_full = b0 + 32,
                    s_empty = b0 + 40, p_full = b0 + 48, p_empty = b0 + 56, o_full = b0 + 64;
@@ -86,7 +90,7 @@ attn_tc_kernel(const AttnTcParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+        mbar_init(s_full, 1); mbar_init(s_empty, 4 * AT_PARTS); mbar_init(p_full, 4 * AT_PARTS); mbar_init(p_empty, 1); mbar_init(o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -234,11 +238,13 @@ attn_tc_kernel(const AttnTcParams p) {
         } else {
             // ------------------------------------------------ softmax warps.  Thread = one query row of the tile;
             // the two warps of a TMEM lane quadrant split the key chunks and exchange (max, sum) through smem.
-            const int quad = warp & 3, half = (warp - 2) >> 2;
+            const int quad = warp & 3, half = (warp - 2) >> 2;      // `half` = this warp's part (0 .. AT_PARTS-1) of the key chunks
             const int rr = quad * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
             const int nchunks = (KP + 31) / 32;
-            const int c_lo = half ? (nchunks + 1) / 2 : 0, c_hi = half ? nchunks : (nchunks + 1) / 2;
+            const int cper = (nchunks + AT_PARTS - 1) / AT_PARTS;
+            const int c_lo = min(nchunks, half * cper), c_hi = min(nchunks, c_lo + cper);
+            constexpr int RED = AT_PARTS * 128;
             const uint32_t bar_id = 1 + quad;                       // named barrier of this quadrant's warp pair
             for (int t = 0; t < ntiles; ++t, ++it) {
                 const int64_t g = (t0 + t) * AT_TILE + rr;
@@ -264,9 +270,10 @@ attn_tc_kernel(const AttnTcParams p) {
                             for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) mx = fmaxf(mx, v[e]);
                         }
                     }
-                    sRed[(it & 1) * 512 + half * 128 + rr] = mx;
-                    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                    mx = fmaxf(mx, sRed[(it & 1) * 512 + (half ^ 1) * 128 + rr]);
+                    sRed[half * 128 + rr] = mx;
+                    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AT_PARTS * 32) : "memory");
+#pragma unroll
+                    for (int q = 0; q < AT_PARTS; ++q) mx = fmaxf(mx, sRed[q * 128 + rr]);
                     if (stamp) DBG_STAMP(0, it, 2);
                     if (!valid) mx = 0.f;
                     // rows of a neighbouring bag / padding: exp2(s*c - inf) = 0 -> P = 0 exactly (never inf * 0 = NaN)
@@ -286,9 +293,11 @@ attn_tc_kernel(const AttnTcParams p) {
                         if (MODE == 0) tc_st32(lane_addr + (uint32_t)(c * 32), v);
                     }
                     if (MODE == 0) tc_wait_st();
-                    sRed[(it & 1) * 512 + 256 + half * 128 + rr] = sum;
-                    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                    sum += sRed[(it & 1) * 512 + 256 + (half ^ 1) * 128 + rr];
+                    sRed[RED + half * 128 + rr] = sum;
+                    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AT_PARTS * 32) : "memory");
+                    sum = 0.f;
+#pragma unroll
+                    for (int q = 0; q < AT_PARTS; ++q) sum += sRed[RED + q * 128 + rr];
                     if (stamp) DBG_STAMP(0, it, 3);
                     if (MODE == 1) {
                         // per-chunk partial statistics for pass 2 (raw-score max, sum of exp2 relative to it)
@@ -380,7 +389,7 @@ attn_tc_kernel(const AttnTcParams p) {
                 // ---- item epilogue: O (TMEM lane = key) -> this split's partial; each half takes one 128-key block
                 mbar_wait(o_full, item_no & 1);
                 tc_fence_after();
-                for (int mb = half; mb < mblocks; mb += 2) {
+                for (int mb = half; mb < mblocks; mb += AT_PARTS) {
                     const int key = mb * 128 + rr;
                     for (int c = 0; c < dk / 32; ++c) {
                         float v[32];
