@@ -180,6 +180,10 @@ attn_tc_kernel(const AttnTcParams p) {
             const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                     ((uint32_t)(dk >> 3) << 17) | (8u << 24);
+            // N = 2 dk: the hi and lo planes of V are contiguous in the MN-major layout (QV_PLANE = dk/8 groups x SBO), so
+            // P_hi^T [V_hi | V_lo] is ONE MMA whose A operand is read once (P^T V is bound by its shared-memory reads)
+            const uint32_t idesc2w = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                     ((uint32_t)(dk >> 2) << 17) | (8u << 24);
             const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP), aV = smem_u32(sV);
             auto mma2 = [&](uint32_t itp, bool first) {
                 // O[mblk] (+)= P(t)^T V(t): A = P planes (MN-major, M = key), B = V planes (MN-major, N = dv)
@@ -191,14 +195,15 @@ attn_tc_kernel(const AttnTcParams p) {
                 tc_fence_after();
                 if (lane == 0) {
                     for (int mb = 0; mb < mblocks; ++mb) {
-                        const uint32_t d_tmem = tmem_base + AT_O_COL + (uint32_t)(mb * dk);
+                        // accumulators of key block mb: columns [0, dk) = P_hi^T V_hi + P_lo^T V_hi, [dk, 2 dk) = P_hi^T V_lo
+                        const uint32_t d_tmem = tmem_base + AT_O_COL + (uint32_t)(mb * 2 * dk);
                         for (int ks = 0; ks < AT_TILE / 16; ++ks) {
                             const uint32_t pa = aP + mb * (16 * 2048) + ks * 256, va = aV + ks * 256;
                             const uint64_t p_hi = make_smem_desc(pa, 128, 2048), p_lo = make_smem_desc(pa + P_PLANE, 128, 2048);
                             const uint64_t v_hi = make_smem_desc(va, 128, 2048), v_lo = make_smem_desc(va + QV_PLANE, 128, 2048);
-                            tc_mma_bf16(d_tmem, p_lo, v_hi, idesc2, (first && ks == 0) ? 0u : 1u);
-                            tc_mma_bf16(d_tmem, p_hi, v_lo, idesc2, 1u);
-                            tc_mma_bf16(d_tmem, p_hi, v_hi, idesc2, 1u);
+                            (void)v_lo;
+                            tc_mma_bf16(d_tmem, p_hi, v_hi, idesc2w, (first && ks == 0) ? 0u : 1u);
+                            tc_mma_bf16(d_tmem, p_lo, v_hi, idesc2, 1u);
                         }
                     }
                     tc_commit(p_empty);
@@ -393,7 +398,11 @@ attn_tc_kernel(const AttnTcParams p) {
                     const int key = mb * 128 + rr;
                     for (int c = 0; c < dk / 32; ++c) {
                         float v[32];
-                        tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * dk + c * 32), v);
+                        float v2[32];
+                        tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * 2 * dk + c * 32), v);
+                        tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * 2 * dk + dk + c * 32), v2);
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] += v2[e];
                         if (key < kvalid) {
                             float* o = p.O_part + (((int64_t)split * p.B + b) * p.Ksel + key0 + key) * p.d + j * dk + c * 32;
 #pragma unroll
@@ -432,6 +441,7 @@ static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, in
     for (int nkc = 1; nkc <= 512; ++nkc) {
         const int KC = (int)(((Ksel + nkc - 1) / nkc + 15) / 16 * 16);
         if (KC > 256) continue;
+        if (((KC + 127) / 128) * 2 * dk > 256) continue;      // O accumulators: 2 dk TMEM columns per 128-key block from column 256
         const size_t smem = attn_tc_smem(KC, dk);
         if (smem > 227 * 1024) continue;
         // the second 128-key MMA block addresses 16 key groups from its base: must stay inside the CTA's window
