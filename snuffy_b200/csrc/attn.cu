@@ -237,16 +237,29 @@ __global__ void __launch_bounds__(256)
 fold_partials_kernel(const float* __restrict__ part, int splits, int64_t n4, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(part) + (int64_t)s * n4 + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    // fixed order (deterministic), four independent accumulators so that the loads of different splits overlap
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(part) + (int64_t)(s + u) * n4 + i);
+            a[u].x += v.x; a[u].y += v.y; a[u].z += v.z; a[u].w += v.w;
+        }
     }
-    reinterpret_cast<float4*>(out)[i] = acc;
+    for (; s < splits; ++s) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(part) + (int64_t)s * n4 + i);
+        a[0].x += v.x; a[0].y += v.y; a[0].z += v.z; a[0].w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4((a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y),
+                                                    (a[0].z + a[1].z) + (a[2].z + a[3].z), (a[0].w + a[1].w) + (a[2].w + a[3].w));
 }
 
 void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream) {
-    fold_partials_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(part, splits, n4, out);
+    const int threads = n4 >= 64 * 1024 ? 256 : 64;          // small folds: more CTAs, the loop over splits is the latency
+    fold_partials_kernel<<<(unsigned)((n4 + threads - 1) / threads), threads, 0, stream>>>(part, splits, n4, out);
 }
 
 struct AttnPlan { int KC, nkc, nvs, splits, rows_per_split; size_t smem; };

@@ -99,26 +99,26 @@ act_bwd_kernel(const float* __restrict__ hpre, const float* __restrict__ da, int
 
 // ------------------------------------------------------------------ weighted column sums
 // partial[chunk][c][e] = sum_{rows in chunk} w[row*C + c] * X[row*ldx + e]   (w == null -> weight 1, C = 1)
-// thread = column (coalesced row reads), 4 independent row accumulators per thread
+// grid (row chunks, column slabs of 256): thread = one column (coalesced row reads), 4 independent row accumulators
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, int64_t rows, int d, int C,
               int64_t rows_per_chunk, float* __restrict__ partials) {
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+    const int e = blockIdx.y * 256 + threadIdx.x;
+    if (e >= d) return;
     for (int c = 0; c < C; ++c) {
-        for (int e = threadIdx.x; e < d; e += blockDim.x) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int64_t r = r0;
-            for (; r + 3 < r1; r += 4) {
-                const float w0 = w ? __ldg(w + r * C + c) : 1.f, w1 = w ? __ldg(w + (r + 1) * C + c) : 1.f;
-                const float w2 = w ? __ldg(w + (r + 2) * C + c) : 1.f, w3 = w ? __ldg(w + (r + 3) * C + c) : 1.f;
-                a0 = fmaf(w0, __ldg(X + r * ldx + e), a0);
-                a1 = fmaf(w1, __ldg(X + (r + 1) * ldx + e), a1);
-                a2 = fmaf(w2, __ldg(X + (r + 2) * ldx + e), a2);
-                a3 = fmaf(w3, __ldg(X + (r + 3) * ldx + e), a3);
-            }
-            for (; r < r1; ++r) a0 = fmaf(w ? __ldg(w + r * C + c) : 1.f, __ldg(X + r * ldx + e), a0);
-            partials[((int64_t)blockIdx.x * C + c) * d + e] = (a0 + a1) + (a2 + a3);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int64_t r = r0;
+        for (; r + 3 < r1; r += 4) {
+            const float w0 = w ? __ldg(w + r * C + c) : 1.f, w1 = w ? __ldg(w + (r + 1) * C + c) : 1.f;
+            const float w2 = w ? __ldg(w + (r + 2) * C + c) : 1.f, w3 = w ? __ldg(w + (r + 3) * C + c) : 1.f;
+            a0 = fmaf(w0, __ldg(X + r * ldx + e), a0);
+            a1 = fmaf(w1, __ldg(X + (r + 1) * ldx + e), a1);
+            a2 = fmaf(w2, __ldg(X + (r + 2) * ldx + e), a2);
+            a3 = fmaf(w3, __ldg(X + (r + 3) * ldx + e), a3);
         }
+        for (; r < r1; ++r) a0 = fmaf(w ? __ldg(w + r * C + c) : 1.f, __ldg(X + r * ldx + e), a0);
+        partials[((int64_t)blockIdx.x * C + c) * d + e] = (a0 + a1) + (a2 + a3);
     }
 }
 
@@ -126,9 +126,14 @@ __global__ void __launch_bounds__(256)
 fold_scalar_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += __ldcg(part + (int64_t)s * n + i);
-    out[i] = acc;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] += __ldcg(part + (int64_t)(s + u) * n + i);
+    }
+    for (; s < splits; ++s) a[0] += __ldcg(part + (int64_t)s * n + i);
+    out[i] = (a[0] + a[1]) + (a[2] + a[3]);
 }
 
 // ------------------------------------------------------------------ attention backward, row-local pieces
@@ -256,9 +261,10 @@ int snuffy_colsum(const float* X, int64_t ldx, const float* w, int64_t rows, int
     SNUFFY_REQUIRE(X && out && partials && rows >= 1 && d >= 1 && C >= 1 && (w || C == 1), "snuffy_colsum: bad arguments");
     const int64_t chunks = snuffy_colsum_chunks(rows);
     const int64_t rpc = (rows + chunks - 1) / chunks;
-    colsum_kernel<<<(unsigned)chunks, 256, 0, stream>>>(X, ldx, w, rows, (int)d, (int)C, rpc, partials);
+    dim3 grid((unsigned)chunks, (unsigned)((d + 255) / 256));
+    colsum_kernel<<<grid, 256, 0, stream>>>(X, ldx, w, rows, (int)d, (int)C, rpc, partials);
     const int64_t n = C * d;
-    fold_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(partials, (int)chunks, n, out);
+    fold_scalar_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(partials, (int)chunks, n, out);
     return check_launch("snuffy_colsum", 2);
 }
 
