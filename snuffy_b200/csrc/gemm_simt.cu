@@ -95,7 +95,7 @@ __device__ __forceinline__ void store_tile(float (*S)[SG_BM + SG_PAD], const flo
 }
 
 template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)     // <= 128 registers: two CTAs per SM hide the short-K latency of the backward GEMMs
 gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const float* __restrict__ B, int64_t sbn,
                  int64_t sbk, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, bool vecA,
                  bool vecB, SimtEpilogue ep, SimtBatch bt) {
