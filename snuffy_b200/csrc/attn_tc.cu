@@ -14,11 +14,15 @@
 //   Kp    : fp32 [B*Ksel, d]; each CTA splits its head's keys into shared memory once per work item.
 //   P     : never leaves the SM: the softmax warps write it as MN-major split-bf16 planes (M = key, K = query).
 //
-// Work item = (bag, head, row-tile range).  Per 128-query tile:
-//   warp 0   bulk-copy producer: Q tile, V tile (single buffers, re-armed by tcgen05.commit)
-//   warp 1   MMA issuer:  S(t) = Q Kp^T  -> TMEM[0, KP);  O += P(t-1)^T V(t-1) -> TMEM[256, 256 + 2*dk)
-//   warps 2-9  one query row per thread (two warps per TMEM lane quadrant split the keys): three passes over the TMEM row (max, sum, normalise), P -> smem,
-//            at the end of the item O -> registers -> per-split partial (folded by fold_partials_kernel).
+// Work item = (bag, head, key chunk, row-tile range).  Per 128-query tile:
+//   warp 0     bulk-copy producer: Q tile, V tile (single buffers, re-armed by tcgen05.commit)
+//   warp 1     MMA issuer:  S(t) = Q Kp^T -> TMEM[0, KP);  O += P(t-1)^T V(t-1) -> TMEM[256, ...): per 128-key block 2 dk
+//              columns, [0, dk) = P_hi^T V_hi + P_lo^T V_hi, [dk, 2 dk) = P_hi^T V_lo (the two V planes are one N = 2 dk operand)
+//   warps 2-9  one query row per thread (AT_PARTS warps per TMEM lane quadrant split the key chunks): row max, then exp ONCE
+//              per score parked back into TMEM (tcgen05.st), then normalise + integer-pipe bf16 split -> P planes in smem;
+//              at the end of the item O -> registers -> per-split partial (folded by fold_partials_kernel).
+// Ksel > 256 (or a wide head): two launches over key chunks, MODE 1 = per-chunk row statistics, MODE 2 = merged statistics,
+// P and P^T V per chunk.  Measured timeline and what bounds each phase: profiles/r01_summary.md (rounds 1c, 1d).
 #include "tc_ptx.cuh"
 
 namespace snuffy {
