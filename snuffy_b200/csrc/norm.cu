@@ -23,8 +23,10 @@ ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map,
     const int64_t row0 = (int64_t)blockIdx.x * 8;
     const int64_t row = row0 + warp;
     const int nunits = (int)plane_kblocks(d) * 4;          // 16-byte units per row incl. K padding
-    bf16x8* s_hi = reinterpret_cast<bf16x8*>(ln_smem);      // [nunits][8 rows]
-    bf16x8* s_lo = s_hi + (size_t)nunits * 8;
+    // staging [nunits][8 rows (+1 pad)] of 16-byte units: the pad rotates the 16-byte slot by the unit index, so a warp's
+    // 32 stores (same row, consecutive units) spread over all banks instead of serialising on four
+    bf16x8* s_hi = reinterpret_cast<bf16x8*>(ln_smem);
+    bf16x8* s_lo = s_hi + (size_t)nunits * 9;
 
     float v[MAXIT][8];
     const bool live = row < rows;
@@ -111,8 +113,8 @@ ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map,
                 bf16x8 h, l;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) split_bf16(u[j], h.v[j], l.v[j]);
-                s_hi[unit * 8 + warp] = h;
-                s_lo[unit * 8 + warp] = l;
+                s_hi[unit * 9 + warp] = h;
+                s_lo[unit * 9 + warp] = l;
             }
         }
     }
@@ -122,8 +124,8 @@ ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map,
         for (int s = threadIdx.x; s < nunits * 8; s += blockDim.x) {
             const int unit = s >> 3, rr = s & 7;
             const int64_t off = plane_unit_offset(row0, (int64_t)unit * 8, d, rc) + rr * 8;
-            *reinterpret_cast<bf16x8*>(planes + off) = s_hi[s];
-            *reinterpret_cast<bf16x8*>(planes + plane_stride + off) = s_lo[s];
+            *reinterpret_cast<bf16x8*>(planes + off) = s_hi[unit * 9 + rr];
+            *reinterpret_cast<bf16x8*>(planes + plane_stride + off) = s_lo[unit * 9 + rr];
         }
     }
 }
@@ -400,7 +402,7 @@ int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt,
         return check_launch("snuffy_ln_rows_fwd");
     }
     SNUFFY_REQUIRE(d <= 4096, "snuffy_ln_rows_fwd: d=%lld > 4096 unsupported", (long long)d);
-    const size_t smem = planes ? (size_t)plane_kblocks(d) * 4 * 8 * 16 * 2 : 0;
+    const size_t smem = planes ? (size_t)plane_kblocks(d) * 4 * 9 * 16 * 2 : 0;
     __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(planes);
 #define LN_LAUNCH(MAXIT)                                                                                        \
     do {                                                                                                        \
