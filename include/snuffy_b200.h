@@ -67,6 +67,11 @@ int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt,
                        const float* beta, int64_t rows, int64_t d, int apply_ln, float* out_f32,
                        void* planes, int64_t plane_stride, int plane_rc, float* stats,
                        snuffy_stream_t stream);
+/* Layer-0 fusion (inference): one pass over the bag gives the instance scores (snuffy.py:39-41) AND the
+ * normalised operand planes shared by LN1 / LN2 (snuffy.py:107,110); scores are bit-identical to snuffy_scores_fwd. */
+int snuffy_scores_ln_planes_fwd(const float* x, const float* W, const float* bias, int64_t rows, int64_t d,
+                                int64_t C, float* c, void* planes, int64_t plane_stride, float* stats,
+                                snuffy_stream_t stream);
 /* Overwrite plane rows b*N + idx[b,k] with split(LN(src[b*K+k])): LN1 and LN2 (snuffy.py:107,110) share one set
  * of normalised planes, only the Ksel rows changed by the attention sub-layer (snuffy.py:152-155) are redone.
  * apply_ln everywhere: 0 = convert (optional per-column gain gamma), 1 = LN with affine, 2 = normalise only.     */

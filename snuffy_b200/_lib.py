@@ -30,6 +30,7 @@ _SIGNATURES = {
     "snuffy_gather_rows": (c_int, [P, P, I, I, I, I, P, P]),
     "snuffy_build_row_map": (c_int, [P, I, I, I, P, P]),
     "snuffy_ln_rows_fwd": (c_int, [P, P, P, P, P, I, I, c_int, P, P, I, c_int, P, P]),
+    "snuffy_scores_ln_planes_fwd": (c_int, [P, P, P, I, I, I, P, P, I, P, P]),
     "snuffy_ln_rows_scatter_planes": (c_int, [P, P, I, I, I, I, P, P, c_int, P, I, P]),
     "snuffy_ln_mean_head_chunks": (c_int64, [I, I]),
     "snuffy_ln_mean_head_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P, P, P, P, P, P]),

@@ -168,8 +168,13 @@ class Encoder(nn.Module):
         """All layers WITHOUT the final LayerNorm (BClassifier fuses it with the mean-pool + head)."""
         attn = None
         state = {}
+        hint = getattr(self, "_zplanes_hint", None)           # (data_ptr of x, planes) left by MILNet.forward's fused scorer
+        self._zplanes_hint = None
+        if hint is not None and hint[0] == x.data_ptr():
+            state["zplanes"] = hint[1]
         for i, layer in enumerate(self.layers):
             x, attn = layer(x, c, i, _state=state)
+            state.pop("zplanes", None)
         return x, attn
 
     def forward(self, x, c):
@@ -205,7 +210,14 @@ class MILNet(nn.Module):
         self.b_classifier = b_classifier
 
     def forward(self, x):
-        feats, classes = self.i_classifier(x)
+        if x.dim() == 3 and engine.fused_scores_available(self, x):
+            # inference: ONE pass over the bag yields the instance scores and layer 0's normalised operand planes
+            lin = self.i_classifier.fc[0]
+            feats = x.contiguous()
+            classes, planes = ops.scores_ln_planes(feats, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
+            self.b_classifier.encoder._zplanes_hint = (feats.data_ptr(), planes)
+        else:
+            feats, classes = self.i_classifier(x)
         prediction_bag, A = self.b_classifier(feats, classes)
         return classes, prediction_bag, A
 
@@ -276,4 +288,4 @@ class EncoderLayerBase(nn.Module):
             sel = sel.unsqueeze(0)
         sel = sel.to(device=x.device, dtype=torch.int64).contiguous()
         from .autograd import encoder_layer_fn
-        return encoder_layer_fn(self, x, sel)
+        return encoder_layer_fn(self, x, sel, zplanes=state.get("zplanes"))

@@ -44,7 +44,7 @@ def ln_mean_head_fn(x, gamma, beta, w_head, b_head) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ one encoder layer (snuffy.py:126-157)
-def encoder_layer_fn(layer, x: torch.Tensor, sel: torch.Tensor):
+def encoder_layer_fn(layer, x: torch.Tensor, sel: torch.Tensor, zplanes=None):
     """x [B, N, d], sel [B, Ksel] -> (x_next [B, N, d], A [B, h, N, Ksel] or None)."""
     B, N, d = x.shape
     precision = layer._effective_precision()
@@ -61,5 +61,5 @@ def encoder_layer_fn(layer, x: torch.Tensor, sel: torch.Tensor):
     xc = x.detach().contiguous().view(B * N, d)
     x_next, probs, _ = engine.encoder_layer_forward(xc, B, N, sel, w, heads, act, precision,
                                                     want_probs=layer.return_attn, attn_dropout=p_attn,
-                                                    enc_dropout=p_enc, ff_dropout=p_ff)
+                                                    enc_dropout=p_enc, ff_dropout=p_ff, zplanes=zplanes)
     return x_next.view(B, N, d), probs

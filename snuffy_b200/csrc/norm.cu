@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map, const float* __restrict__ alt,
                const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int d,
                float* __restrict__ out_f32, __nv_bfloat16* __restrict__ planes, int64_t plane_stride,
-               float* __restrict__ stats, int apply_ln, int rc) {
+               float* __restrict__ stats, int apply_ln, int rc, const float* __restrict__ score_w = nullptr,
+               const float* __restrict__ score_b = nullptr, float* __restrict__ score_out = nullptr, int score_c = 0) {
     extern __shared__ __align__(16) unsigned char ln_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = (int64_t)blockIdx.x * 8;
@@ -52,6 +53,28 @@ ln_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_map,
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[it][j] = 0.f;
+        }
+    }
+    if (score_out) {
+        // fused instance scorer c = y W^T + b (snuffy.py:39-41) on the RAW row while it is in registers: layer 0 then reads
+        // the bag once for both the scores and the normalised planes.  Same per-lane partition and accumulation order as
+        // scores_kernel (select.cu) -> bit-identical scores.
+        for (int c = 0; c < score_c; ++c) {
+            float acc = 0.f;
+#pragma unroll
+            for (int it = 0; it < MAXIT; ++it) {
+                const int e = (it * 32 + lane) * 8;
+                if (live && e < d) {
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(score_w + (int64_t)c * d + e));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(score_w + (int64_t)c * d + e + 4));
+                    acc = fmaf(v[it][0], w0.x, acc); acc = fmaf(v[it][1], w0.y, acc);
+                    acc = fmaf(v[it][2], w0.z, acc); acc = fmaf(v[it][3], w0.w, acc);
+                    acc = fmaf(v[it][4], w1.x, acc); acc = fmaf(v[it][5], w1.y, acc);
+                    acc = fmaf(v[it][6], w1.z, acc); acc = fmaf(v[it][7], w1.w, acc);
+                }
+            }
+            acc = warp_sum(acc);
+            if (live && lane == 0) score_out[row * score_c + c] = acc + (score_b ? score_b[c] : 0.f);
         }
     }
     // apply_ln: 0 = plain convert (optionally scaled per column by gamma: folds a LayerNorm gain into a weight),
@@ -419,6 +442,32 @@ int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt,
     else LN_LAUNCH(16);
 #undef LN_LAUNCH
     return check_launch("snuffy_ln_rows_fwd");
+}
+
+// Layer-0 fusion (inference): ONE pass over the bag produces the instance scores c = x W^T + b (snuffy.py:39-41) and the
+// normalised operand planes z = (x - mean) * rstd that LN1 / LN2 share (snuffy.py:107,110).  c [rows, C]; needs d % 8 == 0.
+int snuffy_scores_ln_planes_fwd(const float* x, const float* W, const float* bias, int64_t rows, int64_t d, int64_t C,
+                                float* c, void* planes, int64_t plane_stride, float* stats, cudaStream_t stream) {
+    SNUFFY_REQUIRE(x && W && c && planes && rows >= 1 && C >= 1, "snuffy_scores_ln_planes_fwd: bad arguments");
+    SNUFFY_REQUIRE(d % 8 == 0 && d <= 4096 && (uintptr_t)x % 16 == 0 && (uintptr_t)W % 16 == 0,
+                   "snuffy_scores_ln_planes_fwd: needs d %% 8 == 0, d <= 4096 and 16-byte aligned rows (d=%lld)", (long long)d);
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    const size_t smem = (size_t)plane_kblocks(d) * 4 * 9 * 16 * 2;
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(planes);
+#define LNS_LAUNCH(MAXIT)                                                                                              \
+    do {                                                                                                               \
+        if (smem > 48 * 1024)                                                                                          \
+            SNUFFY_CUDA(cudaFuncSetAttribute(ln_rows_kernel<MAXIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ln_rows_kernel<MAXIT><<<grid, 256, smem, stream>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)d, nullptr, pl,  \
+                                                           plane_stride, stats, 2, 128, W, bias, c, (int)C);            \
+    } while (0)
+    const int iters = (int)((plane_kblocks(d) * 4 + 31) / 32);
+    if (iters <= 2) LNS_LAUNCH(2);
+    else if (iters <= 4) LNS_LAUNCH(4);
+    else if (iters <= 8) LNS_LAUNCH(8);
+    else LNS_LAUNCH(16);
+#undef LNS_LAUNCH
+    return check_launch("snuffy_scores_ln_planes_fwd");
 }
 
 // planes rows b*N + idx[b,k] <- split(LN(src[b*K + k]))   (apply_ln as in snuffy_ln_rows_fwd; A-operand planes, RC = 128)

@@ -26,7 +26,25 @@ scores_kernel(const float* __restrict__ x, const float* __restrict__ W, const fl
     float acc[CC];
 #pragma unroll
     for (int j = 0; j < CC; ++j) acc[j] = 0.f;
-    if (vec_ok) {
+    if (vec_ok == 2) {
+        // d % 8 == 0: each lane owns 8 consecutive elements per 256-element slab, accumulated in index order -- the SAME
+        // partition and order as ln_rows_kernel's fused scorer (norm.cu), so both produce bit-identical scores
+        for (int e = lane * 8; e < d; e += 256) {
+            const float4 x0 = ld_stream(reinterpret_cast<const float4*>(xr + e));
+            const float4 x1 = ld_stream(reinterpret_cast<const float4*>(xr + e + 4));
+#pragma unroll
+            for (int j = 0; j < CC; ++j) {
+                if (c0 + j < C) {
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(c0 + j) * d + e));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(c0 + j) * d + e + 4));
+                    acc[j] = fmaf(x0.x, w0.x, acc[j]); acc[j] = fmaf(x0.y, w0.y, acc[j]);
+                    acc[j] = fmaf(x0.z, w0.z, acc[j]); acc[j] = fmaf(x0.w, w0.w, acc[j]);
+                    acc[j] = fmaf(x1.x, w1.x, acc[j]); acc[j] = fmaf(x1.y, w1.y, acc[j]);
+                    acc[j] = fmaf(x1.z, w1.z, acc[j]); acc[j] = fmaf(x1.w, w1.w, acc[j]);
+                }
+            }
+        }
+    } else if (vec_ok) {
         for (int e = lane * 4; e < d; e += 128) {
             const float4 xv = ld_stream(reinterpret_cast<const float4*>(xr + e));
 #pragma unroll
@@ -283,7 +301,7 @@ int snuffy_scores_fwd(const float* x, const float* W, const float* bias, float* 
     SNUFFY_REQUIRE(rows >= 0 && d > 0 && C > 0, "snuffy_scores_fwd: bad shape rows=%lld d=%lld C=%lld",
                    (long long)rows, (long long)d, (long long)C);
     if (rows == 0) return 0;
-    const int vec = vec_ok4(x, d) && vec_ok4(W, d);
+    const int vec = (vec_ok4(x, d) && vec_ok4(W, d)) ? (d % 8 == 0 ? 2 : 1) : 0;
     const int warps = 8;
     const unsigned grid = (unsigned)((rows + warps - 1) / warps);
     for (int c0 = 0; c0 < C; c0 += 4) {

@@ -222,10 +222,24 @@ def tc_supported(d: int) -> bool:
     return d % 8 == 0
 
 
+def fused_scores_available(milnet, x: torch.Tensor) -> bool:
+    """True when layer 0 can take its normalised planes from the scoring pass: inference, tensor-core precision, shared
+    z planes, a plain FCLayer scorer.  (The planes are only valid for the encoder's first layer: x is its input.)"""
+    from ._modules import FCLayer
+    layers = milnet.b_classifier.encoder.layers
+    if not SHARE_Z or len(layers) == 0 or not isinstance(milnet.i_classifier, FCLayer):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in milnet.parameters())):
+        return False
+    if not x.is_cuda or x.dtype != torch.float32 or x.shape[-1] % 8 != 0 or x.shape[-1] > 4096:
+        return False
+    return layers[0]._effective_precision() != "fp32"
+
+
 def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w: LayerWeights, heads: int,
                           activation: str, precision: str, want_probs: bool, save: bool = False,
                           attn_dropout: float = 0.0, enc_dropout: float = 0.0, ff_dropout: float = 0.0,
-                          varlen: Optional[Tuple[torch.Tensor, int, int, int]] = None
+                          varlen: Optional[Tuple[torch.Tensor, int, int, int]] = None, zplanes: Optional[Planes] = None
                           ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[LayerTape]]:
     """One EncoderLayer (snuffy.py:126-157) on x [B*N, d] with the selection sel [B, Ksel].
 
@@ -264,7 +278,10 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     else:
         if share_z:
             w.prepare_folded()
-            _, up, ln1_stats = ops.ln_rows(x, None, None, want_planes=True, affine=False)
+            if zplanes is not None and zplanes.rows == rows and zplanes.K == d:
+                up, ln1_stats = zplanes, None            # layer 0: produced together with the instance scores
+            else:
+                _, up, ln1_stats = ops.ln_rows(x, None, None, want_planes=True, affine=False)
             wqv_p, bqv = w.wqv_fold_planes, w.bqv_fold
         else:
             _, up, ln1_stats = ops.ln_rows(x, w.g1, w.be1, want_planes=True, want_stats=save)

@@ -132,6 +132,20 @@ def ln_rows(x: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch
     return out, planes, stats
 
 
+def scores_ln_planes(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+    """One pass over x [..., d]: (c [..., C] instance scores, Planes of the normalised rows).  Layer-0 fusion."""
+    x = _f32(x, "x")
+    weight = _f32(weight, "weight")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    C = weight.shape[0]
+    c = torch.empty(*x.shape[:-1], C, dtype=torch.float32, device=x.device)
+    planes = Planes(rows, d, 128, x.device)
+    check(lib.snuffy_scores_ln_planes_fwd(x.data_ptr(), weight.data_ptr(), _ptr(bias), rows, d, C, c.data_ptr(), planes.ptr,
+                                          planes.stride, None, _stream()), "snuffy_scores_ln_planes_fwd")
+    return c, planes
+
+
 def ln_rows_scatter_planes(src: torch.Tensor, idx: torch.Tensor, N: int, planes: Planes, gamma=None, beta=None,
                            apply_ln: bool = True, affine: bool = False) -> None:
     """planes rows b*N + idx[b, k] <- split(LN(src[b*K + k]))  (in place; src [B*K, d], idx [B, K])."""

@@ -45,7 +45,14 @@ class EncoderLayer(EncoderLayerBase):
 def forward_bags(milnet: MILNet, x: torch.Tensor):
     """Batched extension: run `milnet` on B same-sized bags x [B, N, d] in one pass (one launch sequence fills
     148 SMs far better than B separate forwards).  Returns (classes [B, N, 1], bag [B, 1], A [B, h, N, Ksel])."""
-    feats, classes = milnet.i_classifier(x)
+    zplanes = None
+    if x.dim() == 3 and engine.fused_scores_available(milnet, x):
+        from . import ops
+        lin = milnet.i_classifier.fc[0]
+        feats = x.contiguous()
+        classes, zplanes = ops.scores_ln_planes(feats, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
+    else:
+        feats, classes = milnet.i_classifier(x)
     enc = milnet.b_classifier.encoder
     state = {}
     attn = None
@@ -53,7 +60,8 @@ def forward_bags(milnet: MILNet, x: torch.Tensor):
     for layer in enc.layers:
         sel = layer.forced_selection if layer.forced_selection is not None else layer.select(classes, state)
         from .autograd import encoder_layer_fn
-        h, attn = encoder_layer_fn(layer, h, sel.to(device=h.device, dtype=torch.int64).contiguous())
+        h, attn = encoder_layer_fn(layer, h, sel.to(device=h.device, dtype=torch.int64).contiguous(), zplanes=zplanes)
+        zplanes = None
     from .autograd import ln_mean_head_fn
     b = milnet.b_classifier
     bag = ln_mean_head_fn(h, enc.norm.weight, enc.norm.bias, b.linear.weight, b.linear.bias)
@@ -80,9 +88,13 @@ def forward_packed(milnet: MILNet, x: torch.Tensor, cu_seqlens):
     from . import ops
     from .autograd import scores_fn
     lin = milnet.i_classifier.fc[0]
-    classes = scores_fn(x, lin.weight, lin.bias)                                        # [T, 1]
-    enc = milnet.b_classifier.encoder
     h = x.detach().contiguous()
+    zplanes = None
+    if engine.fused_scores_available(milnet, h):
+        classes, zplanes = ops.scores_ln_planes(h, lin.weight.detach(), lin.bias.detach() if lin.bias is not None else None)
+    else:
+        classes = scores_fn(x, lin.weight, lin.bias)                                    # [T, 1]
+    enc = milnet.b_classifier.encoder
     top = flags = None
     for layer in enc.layers:
         kt = engine.k_top_of(layer.big_lambda, layer.random_patch_share)
@@ -100,7 +112,8 @@ def forward_packed(milnet: MILNet, x: torch.Tensor, cu_seqlens):
         h, _, _ = engine.encoder_layer_forward(h, 1, T, sel.reshape(1, B * ksel).contiguous(), layer.layer_weights(),
                                                layer.self_attn.h, layer.feed_forward.activation_name,
                                                layer._effective_precision(), want_probs=False,
-                                               varlen=(cu, B, ksel, max_n))
+                                               varlen=(cu, B, ksel, max_n), zplanes=zplanes)
+        zplanes = None
     b = milnet.b_classifier
     bag = ops.ln_mean_head_varlen(h, cu, B, max_n, enc.norm.weight.detach(), enc.norm.bias.detach(), b.linear.weight.detach(),
                                   b.linear.bias.detach())

@@ -343,3 +343,19 @@ def test_sparse_attention_tensor_core_unsupported_shapes(ops):
     assert not ops.sparse_attn_tc_supported(1, 256, 32, 8, 320)      # dk = 40 is not a multiple of 32
     assert ops.sparse_attn_tc_supported(1, 600, 392, 8, 768)         # served in key chunks since round 1c
     assert ops.sparse_attn_tc_supported(1, 50000, 1024, 8, 512)
+
+
+@pytest.mark.parametrize("rows,d,C", [(1000, 512, 1), (333, 768, 3), (64, 384, 2), (9, 32, 1)])
+def test_fused_scores_and_normalised_planes_are_bit_identical(ops, rows, d, C):
+    """Layer-0 fusion: one pass gives the instance scores and the shared z planes -- identical bits to the two kernels."""
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    x = torch.randn(rows, d, device="cuda", generator=g) * 2 + 0.3
+    w = torch.randn(C, d, device="cuda", generator=g)
+    b = torch.randn(C, device="cuda", generator=g)
+    c, planes = ops.scores_ln_planes(x, w, b)
+    assert torch.equal(c, ops.scores(x, w, b))
+    _, ref, _ = ops.ln_rows(x, None, None, want_planes=True, affine=False)
+    from helpers import decode_planes
+    for got, want in zip(decode_planes(planes, rows, d), decode_planes(ref, rows, d)):     # rows beyond `rows` are padding
+        assert np.array_equal(got, want)
+    assert (c.double() - (x.double() @ w.double().t() + b.double())).abs().max() < 1e-4
