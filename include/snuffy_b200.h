@@ -122,6 +122,11 @@ int snuffy_planes_t_fwd(const float* x, int64_t ldx, int64_t R, int64_t C, int p
                         const float* alt, int act, float dropout_p, uint64_t seed, uint64_t offset, void* planes,
                         int64_t plane_stride, snuffy_stream_t stream);
 
+/* A . B^T where A is a 32-aligned K window of a wider A-plane set (e.g. the Q or the V half of the Q|V planes).         */
+int snuffy_gemm_tc_awindow(const void* A_planes, int64_t a_plane_stride, int64_t a_cols_total, int64_t a_col0,
+                           const void* B_planes, int64_t b_plane_stride, int64_t M, int64_t N, int64_t K,
+                           int passes, float* out, int64_t ldc, snuffy_stream_t stream);
+
 /* ---- a9: sparse attention  O = concat_j softmax_keys(Q_j Kp_j^T / sqrt(dk))^T V_j                      */
 /* Replaces matmul / div / softmax / dropout / matmul / transpose+contiguous (snuffy.py:160-168, 187-201).
  * Q,V [B*N,d] with row strides ldq/ldv; Kp [B*Ksel,d]; O [B*Ksel,d]; P_out [B,h,N,Ksel] optional
@@ -201,6 +206,15 @@ int snuffy_attn_rows_bwd(const float* S, const float* stats, int64_t nrows, int6
 int snuffy_scatter_add_rows(float* dx, const int64_t* idx, const float* src, int64_t B, int64_t N, int64_t K,
                             int64_t d, snuffy_stream_t stream);
 
+/* Attention backward on tensor cores (autograd of snuffy.py:160-168): all heads of a bag are contracted by one dense
+ * tcgen05 GEMM against head-block operands Kbd[(j,k), c] = Kp[k, c] on head j's columns, 0 elsewhere.
+ * snuffy_attn_seg_bwd: the row-local pieces on S_all [N, h*Ksel] (mode 0: P~, mode 1: G <- dS).                     */
+int snuffy_block_diag_rows(const float* src, int64_t Ksel, int64_t h, int64_t d, float* out, snuffy_stream_t stream);
+int snuffy_block_diag_extract(const float* bd, int64_t Ksel, int64_t h, int64_t d, float* out,
+                              snuffy_stream_t stream);
+int snuffy_attn_seg_bwd(const float* S, const float* stats, int64_t N, int64_t h, int64_t Ksel, int64_t bag, int mode,
+                        float scale, float dropout_p, uint64_t seed, uint64_t offset, float* Pd, float* G,
+                        snuffy_stream_t stream);
 /* DSMIL: backward of A = softmax over the N instances (dsmil.py:86): dS = A (dA - sum_n A dA) / scale          */
 int snuffy_softmax_cols_bwd(const float* A, const float* dA, int64_t N, int64_t C, float scale, float* dS,
                             snuffy_stream_t stream);

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "snuffy_gemm_tc_auto_ksplit": (c_int64, [I, I, I]),
     "snuffy_gemm_tc_splitk_workspace": (c_int64, [I, I, I]),
     "snuffy_gemm_tc_splitk": (c_int, [P, I, P, I, I, I, I, c_int, I, P, P, I, P]),
+    "snuffy_gemm_tc_awindow": (c_int, [P, I, I, I, P, I, I, I, I, c_int, P, I, P]),
     "snuffy_planes_t_fwd": (c_int, [P, I, I, I, c_int, c_int, P, P, P, P, P, c_int, c_float, c_uint64, c_uint64, P, I, P]),
     "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),
     "snuffy_sparse_attn_fwd": (c_int, [P, I, P, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
@@ -64,6 +65,9 @@ _SIGNATURES = {
     "snuffy_colsum": (c_int, [P, I, P, I, I, I, P, P, P]),
     "snuffy_attn_rows_bwd": (c_int, [P, P, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P]),
     "snuffy_scatter_add_rows": (c_int, [P, P, P, I, I, I, I, P]),
+    "snuffy_block_diag_rows": (c_int, [P, I, I, I, P, P]),
+    "snuffy_block_diag_extract": (c_int, [P, I, I, I, P, P]),
+    "snuffy_attn_seg_bwd": (c_int, [P, P, I, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P]),
     "snuffy_softmax_cols_bwd": (c_int, [P, P, I, I, c_float, P, P]),
     "snuffy_mil_loss": (c_int, [P, P, P, P, I, I, I, c_float, c_float, P, P, P, P, P, P, P]),
     "snuffy_sumsq_blocks": (c_int64, [I]),

@@ -19,6 +19,10 @@ import torch
 from . import engine, ops
 
 
+#: attention backward as dense tcgen05 GEMMs over head-block operands (SNUFFY_B200_ATTN_BWD=simt keeps the SIMT products)
+ATTN_BWD_TC = __import__("os").environ.get("SNUFFY_B200_ATTN_BWD", "tc") != "simt"
+
+
 def _flat(t: torch.Tensor, d: int) -> torch.Tensor:
     return t.contiguous().view(-1, d)
 
@@ -127,7 +131,7 @@ class EncoderLayerFunction(torch.autograd.Function):
         if tc:
             w.prepare(precision)
             w.prepare_backward()
-            rc_d, rc_ff = ops.lib.snuffy_gemm_tc_block_n(d), ops.lib.snuffy_gemm_tc_block_n(dff)
+            rc_d, rc_ff = ops._block_n(d), ops._block_n(dff)
 
         def dx_gemm(dy, w_f32, wt_planes, n_in):                # dX = dY . W        (W = nn.Linear.weight [out, in])
             if not tc:
@@ -173,7 +177,10 @@ class EncoderLayerFunction(torch.autograd.Function):
             d_wo = ops.matmul_tn(dz, t.o)
         d_o = dx_gemm(dz, w.wo, w.wot_planes, d)                                   # [B*Ksel, d]
         q, v = t.qv[:, :d], t.qv[:, d:]
-        dq, dv, dkp, dqv = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)
+        if tc and t.qvp is not None and ATTN_BWD_TC and ops.sparse_attn_bwd_tc_supported(B, N, ksel, heads, d):
+            dq, dv, dkp, dqv = ops.sparse_attn_bwd_tc(t.qvp, t.qv, t.kp, d_o, t.attn_stats, B, N, ksel, heads, d, t.drop, passes)
+        else:
+            dq, dv, dkp, dqv = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)
         d_bk = ops.colsum(dkp).view(-1)                                            # == 0 up to rounding (App. B-16)
         if tc:
             d_wk = ops.gemm_tc_splitk(ops.planes_t(dkp, 128), ops.planes_t(t.xs, rc_d), M=d, N=d, K=B * ksel, passes=passes)

@@ -324,3 +324,102 @@ extern "C" int snuffy_softmax_cols_bwd(const float* A, const float* dA, int64_t 
     return snuffy::check_launch("snuffy_softmax_cols_bwd");
 }
 #pragma GCC visibility pop
+
+
+// ------------------------------------------------------------------ attention backward on tensor cores: head-block operands
+// All heads of one bag are contracted by ONE dense tcgen05 GEMM against a block-structured operand
+//   Kbd[(j, k), c] = Kp[k, c] if column c belongs to head j else 0           [h*Ksel, d]
+// so that S_all[n, (j, k)] = Q[n, :] . Kbd[(j, k), :] = Q_j[n] . Kp_j[k].  The zero blocks cost 8x the useful FLOPs, which
+// the tensor cores absorb (35 us per product at cfg2) where the head-batched SIMT kernels took 200 us each.
+namespace snuffy {
+__global__ void __launch_bounds__(256)
+block_diag_rows_kernel(const float* __restrict__ src, int Ksel, int h, int d, float* __restrict__ out) {
+    const int64_t total4 = (int64_t)h * Ksel * d / 4;
+    const int dk = d / h;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)((i * 4) % d);
+        const int64_t r = (i * 4) / d;                     // row (j, k)
+        const int j = (int)(r / Ksel), k = (int)(r % Ksel);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c / dk == j) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)k * d + c));
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256)
+block_diag_extract_kernel(const float* __restrict__ bd, int Ksel, int h, int d, float* __restrict__ out) {
+    const int64_t total = (int64_t)Ksel * d;
+    const int dk = d / h;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % d), k = (int)(i / d), j = c / dk;
+    out[i] = bd[((int64_t)j * Ksel + k) * d + c];
+}
+
+// Row-local pieces on the all-heads layout S_all [N, h*Ksel] (segment j of row n = head j), RAW scores (unscaled):
+//   mode 0:  Pd = exp(S/scale - max) / sum * dropout_mask          mode 1:  G <- (Pd G - P sum_k(Pd G)) / scale
+// stats [h, N, 2] of this bag; the dropout index of (bag, j, n, key) matches the forward: ((bag*h + j)*N + n)*Ksel + key.
+__global__ void __launch_bounds__(256)
+attn_seg_bwd_kernel(const float* __restrict__ S, const float* __restrict__ stats, int64_t N, int h, int Ksel, int bag, int mode,
+                    float inv_scale, float drop_p, uint64_t seed, uint64_t offset, float* __restrict__ Pd, float* __restrict__ G) {
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (n, j)
+    if (seg >= N * h) return;
+    const int64_t n = seg / h;
+    const int j = (int)(seg % h);
+    const int64_t srow = (int64_t)j * N + n;
+    const float m = stats[srow * 2], inv = stats[srow * 2 + 1];
+    const int64_t off = n * (int64_t)h * Ksel + (int64_t)j * Ksel;
+    const uint64_t base = ((uint64_t)((int64_t)bag * h + j) * (uint64_t)N + (uint64_t)n) * (uint64_t)Ksel;
+    const float* s = S + off;
+    if (mode == 0) {
+        for (int k = lane; k < Ksel; k += 32) {
+            float p = expf(s[k] * inv_scale - m) * inv;
+            if (drop_p > 0.f) p *= drop_keep_scale(seed, offset, base + k, drop_p);
+            Pd[off + k] = p;
+        }
+        return;
+    }
+    float* g = G + off;
+    float delta = 0.f;
+    for (int k = lane; k < Ksel; k += 32) {
+        float p = expf(s[k] * inv_scale - m) * inv;
+        if (drop_p > 0.f) p *= drop_keep_scale(seed, offset, base + k, drop_p);
+        delta = fmaf(p, g[k], delta);
+    }
+    delta = warp_sum(delta);
+    for (int k = lane; k < Ksel; k += 32) {
+        const float p = expf(s[k] * inv_scale - m) * inv;
+        const float mk = drop_p > 0.f ? drop_keep_scale(seed, offset, base + k, drop_p) : 1.f;
+        g[k] = p * (mk * g[k] - delta) * inv_scale;
+    }
+}
+}  // namespace snuffy
+
+#pragma GCC visibility push(default)
+extern "C" {
+// out [h*Ksel, d]: row (j, k) = src[k, :] restricted to the columns of head j (zeros elsewhere); src [Ksel, d]
+int snuffy_block_diag_rows(const float* src, int64_t Ksel, int64_t h, int64_t d, float* out, cudaStream_t stream) {
+    SNUFFY_REQUIRE(src && out && Ksel >= 1 && h >= 1 && d % h == 0 && (d / h) % 4 == 0 && (uintptr_t)src % 16 == 0 &&
+                       (uintptr_t)out % 16 == 0, "snuffy_block_diag_rows: bad arguments");
+    const int64_t total4 = h * Ksel * d / 4;
+    int64_t blocks = (total4 + 255) / 256;
+    if (blocks > 8 * (int64_t)snuffy::sm_count()) blocks = 8 * (int64_t)snuffy::sm_count();
+    snuffy::block_diag_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, (int)Ksel, (int)h, (int)d, out);
+    return snuffy::check_launch("snuffy_block_diag_rows");
+}
+// out [Ksel, d]: out[k, c] = bd[(head(c), k), c]   (the diagonal blocks of a [h*Ksel, d] matrix)
+int snuffy_block_diag_extract(const float* bd, int64_t Ksel, int64_t h, int64_t d, float* out, cudaStream_t stream) {
+    SNUFFY_REQUIRE(bd && out && Ksel >= 1 && h >= 1 && d % h == 0, "snuffy_block_diag_extract: bad arguments");
+    snuffy::block_diag_extract_kernel<<<(unsigned)((Ksel * d + 255) / 256), 256, 0, stream>>>(bd, (int)Ksel, (int)h, (int)d, out);
+    return snuffy::check_launch("snuffy_block_diag_extract");
+}
+int snuffy_attn_seg_bwd(const float* S, const float* stats, int64_t N, int64_t h, int64_t Ksel, int64_t bag, int mode,
+                        float scale, float dropout_p, uint64_t seed, uint64_t offset, float* Pd, float* G, cudaStream_t stream) {
+    SNUFFY_REQUIRE(S && stats && N >= 1 && h >= 1 && Ksel >= 1 && (mode == 0 ? Pd != nullptr : G != nullptr),
+                   "snuffy_attn_seg_bwd: bad arguments");
+    snuffy::attn_seg_bwd_kernel<<<(unsigned)((N * h + 7) / 8), 256, 0, stream>>>(S, stats, N, (int)h, (int)Ksel, (int)bag, mode,
+                                                                               1.f / scale, dropout_p, seed, offset, Pd, G);
+    return snuffy::check_launch("snuffy_attn_seg_bwd");
+}
+}  // extern "C"
+#pragma GCC visibility pop

@@ -49,6 +49,9 @@ struct TcGemmParams {
     // split-K (dW = dY^T X contracts over all N patches but has few output tiles): tile = (mt, nt, ks), split ks covers
     // k-blocks [ks*kb_per, ...) and writes its raw fp32 partial to out + ks*split_stride (folded by the caller)
     int ksplit, kb_per; int64_t split_stride;
+    // K window of the A planes: the operand is columns [a_kb_off*32, ...) of a wider plane set with a_nkb k-blocks per row
+    // tile (e.g. Q or V inside the [rows, 2d] planes the Q|V projection wrote)
+    int a_nkb, a_kb_off;
 };
 
 template <int BN>
@@ -92,7 +95,7 @@ gemm_tc_kernel(const TcGemmParams p) {
             const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
             const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
             const int kb0 = ksp * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
-            const __nv_bfloat16* a_src = p.A + (int64_t)mt * p.num_kb * a_chunk;
+            const __nv_bfloat16* a_src = p.A + ((int64_t)mt * p.a_nkb + p.a_kb_off) * a_chunk;
             const __nv_bfloat16* b_src = p.B + (int64_t)nt * p.num_kb * b_chunk;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -355,7 +358,36 @@ int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_p
     p.out_planes = reinterpret_cast<__nv_bfloat16*>(out_planes); p.out_plane_stride = out_plane_stride;
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
     p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
+    p.a_nkb = p.num_kb; p.a_kb_off = 0;
     return launch_gemm_tc(p, N, stream, "snuffy_gemm_tc");
+}
+
+// out[M, N] (fp32, ldc) = A_window . B^T where A is the K window [a_col0, a_col0 + K) of a wider A-plane set over
+// [rows, a_cols_total] columns (a_col0, K multiples of 32).  Used by the attention backward to contract the Q / V halves of the
+// Q|V planes the forward already wrote, without re-splitting them.
+int snuffy_gemm_tc_awindow(const void* A_planes, int64_t a_plane_stride, int64_t a_cols_total, int64_t a_col0,
+                           const void* B_planes, int64_t b_plane_stride, int64_t M, int64_t N, int64_t K, int passes,
+                           float* out, int64_t ldc, cudaStream_t stream) {
+    SNUFFY_REQUIRE(A_planes && B_planes && out, "snuffy_gemm_tc_awindow: null pointer");
+    SNUFFY_REQUIRE(M >= 1 && N >= 1 && K >= 1 && N % 4 == 0 && ldc % 4 == 0 && (uintptr_t)out % 16 == 0,
+                   "snuffy_gemm_tc_awindow: bad problem");
+    SNUFFY_REQUIRE(passes == 1 || passes == 3, "snuffy_gemm_tc_awindow: passes must be 1 or 3");
+    SNUFFY_REQUIRE(a_col0 % 32 == 0 && K % 32 == 0 && a_col0 + K <= plane_kblocks(a_cols_total) * 32,
+                   "snuffy_gemm_tc_awindow: the K window must be 32-aligned inside the planes");
+    TcGemmParams p{};
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A_planes); p.a_plane_stride = a_plane_stride;
+    p.B = reinterpret_cast<const __nv_bfloat16*>(B_planes); p.b_plane_stride = b_plane_stride;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    const int bn = snuffy_gemm_tc_block_n(N);
+    p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    p.n_tiles = (int)((N + bn - 1) / bn);
+    p.num_kb = (int)plane_kblocks(K);
+    p.npairs = passes;
+    p.act = ACT_NONE;
+    p.out = out; p.ldc = ldc;
+    p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
+    p.a_nkb = (int)plane_kblocks(a_cols_total); p.a_kb_off = (int)(a_col0 / 32);
+    return launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_awindow");
 }
 
 // Split-K form for the weight gradients dW[M, N] = A . B^T with a long contraction (K = all patches of the step) and few
@@ -396,6 +428,7 @@ int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const vo
     p.act = ACT_NONE;
     p.out = ksplit > 1 ? reinterpret_cast<float*>(workspace) : out; p.ldc = N;
     p.ksplit = (int)ksplit; p.kb_per = (int)per; p.split_stride = M * N;
+    p.a_nkb = p.num_kb; p.a_kb_off = 0;
     if (int rc = launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_splitk")) return rc;
     if (ksplit > 1) {
         launch_fold_partials(reinterpret_cast<const float*>(workspace), (int)ksplit, M * N / 4, out, stream);

@@ -216,6 +216,7 @@ class LayerTape:
     drop_enc1: Tuple[float, int, int] = (0.0, 0, 0)   # sublayer[0] dropout on the attention output   snuffy.py:108
     drop_ff: Tuple[float, int, int] = (0.0, 0, 0)     # feed-forward hidden dropout                     snuffy.py:225
     drop_enc2: Tuple[float, int, int] = (0.0, 0, 0)   # sublayer[1] dropout on the FFN output           snuffy.py:110
+    qvp: Optional[Planes] = None                      # Q|V as operand planes (tensor-core attention backward)
 
 
 def tc_supported(d: int) -> bool:
@@ -341,5 +342,5 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     if save:
         tape = LayerTape(sel=sel, row_map=row_map, xs=xs, xs_new=xs_new, kp=kp, qv=qv, o=o, ln1_stats=ln1_stats,
                          ln2_stats=ln2_stats, attn_stats=attn_stats, h_pre=h_pre, x_in=x, drop=drop, drop_enc1=drop_enc1,
-                         drop_ff=drop_ff, drop_enc2=drop_enc2)
+                         drop_ff=drop_ff, drop_enc2=drop_enc2, qvp=qvp if precision != "fp32" else None)
     return x_next, probs, tape

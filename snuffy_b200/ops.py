@@ -6,6 +6,7 @@ synchronise, so a whole forward can be captured into a CUDA graph.
 """
 from __future__ import annotations
 
+import functools
 import math
 from typing import Optional, Tuple
 
@@ -19,8 +20,24 @@ _U64 = 2**64 - 1
 
 
 # ------------------------------------------------------------------ helpers
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    # current CUDA stream of the current device as a raw cudaStream_t (the fast path skips the Stream object)
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+# size queries into the library are pure functions of their integer arguments: cache them (the training step makes ~140
+# launches per bag and is otherwise bound by host-side call overhead)
+_plane_elems = functools.lru_cache(maxsize=None)(lambda rows, K, rc: lib.snuffy_plane_elems(rows, K, rc))
+_block_n = functools.lru_cache(maxsize=None)(lambda n: lib.snuffy_gemm_tc_block_n(n))
+_colsum_chunks = functools.lru_cache(maxsize=None)(lambda rows: lib.snuffy_colsum_chunks(rows))
+_ln_bwd_blocks = functools.lru_cache(maxsize=None)(lambda rows: lib.snuffy_ln_rows_bwd_blocks(rows))
+_tc_auto_ksplit = functools.lru_cache(maxsize=None)(lambda M, N, K: lib.snuffy_gemm_tc_auto_ksplit(M, N, K))
+_f32_auto_ksplit = functools.lru_cache(maxsize=None)(lambda nb, M, N, K: lib.snuffy_gemm_f32_auto_ksplit(nb, M, N, K))
 
 
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -42,7 +59,7 @@ class Planes:
 
     def __init__(self, rows: int, K: int, rc: int, device, zero: bool = False):
         self.rows, self.K, self.rc = rows, K, rc
-        self.stride = lib.snuffy_plane_elems(rows, K, rc)
+        self.stride = _plane_elems(rows, K, rc)
         alloc = torch.zeros if zero else torch.empty
         self.buf = alloc(2 * self.stride, dtype=torch.bfloat16, device=device)
 
@@ -210,7 +227,7 @@ def weight_planes(weight: torch.Tensor, col_gain: Optional[torch.Tensor] = None)
     scales the columns first (W * gamma: a LayerNorm gain folded into the weight that consumes the normalised rows)."""
     weight = _f32(weight, "weight")
     n = weight.shape[0]
-    rc = lib.snuffy_gemm_tc_block_n(n)
+    rc = _block_n(n)
     _, planes, _ = ln_rows(weight, col_gain, None, apply_ln=False, want_planes=True, plane_rc=rc, zero_planes=True)
     return planes
 
@@ -313,7 +330,7 @@ def gemm_f32_batched(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, M: in
     tensors' data pointers with element strides (outer, inner).  ksplit None = pick one that fills the machine."""
     nbatch = nb_outer * nb_inner
     if ksplit is None:
-        ksplit = lib.snuffy_gemm_f32_auto_ksplit(nbatch, M, N, K)
+        ksplit = _f32_auto_ksplit(nbatch, M, N, K)
     ws_bytes = lib.snuffy_gemm_f32_batched_workspace(nbatch, M, N, ksplit)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device) if ws_bytes else None
     check(lib.snuffy_gemm_f32_batched(a.data_ptr(), lda, 1 if a_kc else 0, b.data_ptr(), ldb, 1 if b_kc else 0, c.data_ptr(),
@@ -353,7 +370,7 @@ def ln_rows_bwd(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, *, dy
     dev = x.device
     dx = torch.empty(rows, d, dtype=torch.float32, device=dev) if want_dx else None
     gb = torch.empty(2, d, dtype=torch.float32, device=dev)
-    blocks = lib.snuffy_ln_rows_bwd_blocks(rows)
+    blocks = _ln_bwd_blocks(rows)
     partials = torch.empty(blocks * 2 * d, dtype=torch.float32, device=dev)
     if dy is not None:
         dy = _f32(dy, "dy")
@@ -388,7 +405,7 @@ def colsum(x: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
     if w is not None:
         w = _f32(w.reshape(rows, C), "w")
     out = torch.empty(C, d, dtype=torch.float32, device=x.device)
-    partials = torch.empty(lib.snuffy_colsum_chunks(rows) * C * d, dtype=torch.float32, device=x.device)
+    partials = torch.empty(_colsum_chunks(rows) * C * d, dtype=torch.float32, device=x.device)
     check(lib.snuffy_colsum(x.data_ptr(), x.stride(0), _ptr(w), rows, d, C, out.data_ptr(), partials.data_ptr(), _stream()),
           "snuffy_colsum")
     return out
@@ -479,14 +496,14 @@ def planes_t(x: torch.Tensor, rc: int, *, mode: int = 0, stats=None, gamma=None,
 def weight_planes_t(weight: torch.Tensor) -> Planes:
     """B-operand planes of W^T for W [out, in]: rows = input features, k = output features (dX = dY . W)."""
     weight = _f32(weight, "weight")
-    return planes_t(weight, lib.snuffy_gemm_tc_block_n(weight.shape[1]))
+    return planes_t(weight, _block_n(weight.shape[1]))
 
 
 def gemm_tc_splitk(a: Planes, b: Planes, *, M: int, N: int, K: int, passes: int = 3) -> torch.Tensor:
     """out [M, N] = A . B^T over a long contraction (weight gradients), split over CTAs with a deterministic fold."""
     dev = a.buf.device
     out = torch.empty(M, N, dtype=torch.float32, device=dev)
-    ks = lib.snuffy_gemm_tc_auto_ksplit(M, N, K)
+    ks = _tc_auto_ksplit(M, N, K)
     ws_bytes = lib.snuffy_gemm_tc_splitk_workspace(M, N, ks)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     check(lib.snuffy_gemm_tc_splitk(a.ptr, a.stride, b.ptr, b.stride, M, N, K, passes, ks, out.data_ptr(), ws.data_ptr(),
@@ -540,3 +557,80 @@ def ln_mean_head_varlen(x: torch.Tensor, cu: torch.Tensor, B: int, max_n: int, g
                                              _ptr(b_head), B, max_n, d, C, partials.data_ptr(), tickets.data_ptr(), None,
                                              bag.data_ptr(), _stream()), "snuffy_ln_mean_head_varlen_fwd")
     return bag
+
+
+# ------------------------------------------------------------------ attention backward on tensor cores (head-block operands)
+def gemm_tc_awindow(a: Planes, a_col0: int, b: Planes, *, M: int, N: int, K: int, passes: int = 3,
+                    out: Optional[torch.Tensor] = None, ldc: Optional[int] = None) -> torch.Tensor:
+    """out [M, N] = A[:, a_col0 : a_col0 + K] . B^T with A a column window of a wider plane set."""
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.buf.device)
+        ldc = N
+    check(lib.snuffy_gemm_tc_awindow(a.ptr, a.stride, a.K, a_col0, b.ptr, b.stride, M, N, K, passes, out.data_ptr(), ldc,
+                                     _stream()), "snuffy_gemm_tc_awindow")
+    return out
+
+
+def block_diag_rows(src: torch.Tensor, h: int) -> torch.Tensor:
+    """src [Ksel, d] -> [h*Ksel, d]: row (j, k) = src[k] on head j's columns, zeros elsewhere."""
+    src = _f32(src, "src")
+    ksel, d = src.shape
+    out = torch.empty(h * ksel, d, dtype=torch.float32, device=src.device)
+    check(lib.snuffy_block_diag_rows(src.data_ptr(), ksel, h, d, out.data_ptr(), _stream()), "snuffy_block_diag_rows")
+    return out
+
+
+def sparse_attn_bwd_tc_supported(B: int, N: int, Ksel: int, h: int, d: int) -> bool:
+    # bag row ranges must start on a 128-row plane tile (one bag per call, the reference's training pattern, or N % 128 == 0)
+    return d % 32 == 0 and (d // h) % 4 == 0 and (h * Ksel) % 8 == 0 and h * Ksel <= 4096 and (B == 1 or N % 128 == 0)
+
+
+def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: torch.Tensor, stats: torch.Tensor, B: int, N: int,
+                       Ksel: int, h: int, d: int, drop: Tuple[float, int, int] = (0.0, 0, 0), passes: int = 3):
+    """Tensor-core backward of O_j = softmax_keys(Q_j Kp_j^T / sqrt(dk))^T V_j for all heads of a bag at once.
+
+    qvp: the Q|V planes of the forward ([B*N, 2d]); qv: the same in fp32 (for the transposed operand of dKp);
+    Returns (dQ, dV (column halves of dQV), dKp [B*Ksel, d], dQV [B*N, 2d]) like sparse_attn_bwd."""
+    kp, d_o = _f32(kp, "kp"), _f32(d_o, "d_o")
+    dev = kp.device
+    dk = d // h
+    hk = h * Ksel
+    scale = math.sqrt(dk)
+    dqv = torch.empty(B * N, 2 * d, dtype=torch.float32, device=dev)
+    dkp = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
+    rc_d = _block_n(d)
+    for b in range(B):
+        rows = slice(b * N, (b + 1) * N)
+        kbd = block_diag_rows(kp[b * Ksel:(b + 1) * Ksel], h)                     # [h*Ksel, d]
+        obd = block_diag_rows(d_o[b * Ksel:(b + 1) * Ksel], h)
+        st = stats[b]                                                             # [h, N, 2]
+        # plane window of this bag's rows: whole 128-row tiles starting at b*N
+        a = Planes.__new__(Planes)
+        tile_elems = (qvp.stride // ((qvp.rows + 127) // 128))                    # elements per row tile in one plane
+        a.buf, a.rows, a.K, a.rc, a.stride = qvp.buf[(b * N // 128) * tile_elems:], N, qvp.K, 128, qvp.stride
+        S = gemm_tc_awindow(a, 0, weight_planes(kbd), M=N, N=hk, K=d, passes=passes)            # raw Q_j . Kp_j^T, all heads
+        Pd = torch.empty_like(S)
+        check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 0, scale, float(drop[0]), drop[1] & _U64,
+                                      drop[2] & _U64, Pd.data_ptr(), None, _stream()), "snuffy_attn_seg_bwd")
+        # dV = P~ . dObd            [N, d]
+        _, pdp, _ = ln_rows(Pd, None, None, apply_ln=False, want_planes=True)
+        obd_t = weight_planes_t(obd)
+        check(lib.snuffy_gemm_tc(pdp.ptr, pdp.stride, obd_t.ptr, obd_t.stride, N, d, hk, passes, None, 0, None, 0, None, None,
+                                 dqv[rows, d:].data_ptr(), 2 * d, None, None, 0, 0.0, 0, 0, _stream()), "snuffy_gemm_tc")
+        del pdp, Pd
+        # G = V . dObd^T            [N, h*Ksel]
+        G = gemm_tc_awindow(a, d, weight_planes(obd), M=N, N=hk, K=d, passes=passes)
+        check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 1, scale, float(drop[0]), drop[1] & _U64,
+                                      drop[2] & _U64, None, G.data_ptr(), _stream()), "snuffy_attn_seg_bwd")   # G <- dS
+        del S
+        # dQ = dS . Kbd             [N, d]
+        _, dsp, _ = ln_rows(G, None, None, apply_ln=False, want_planes=True)
+        kbd_t = weight_planes_t(kbd)
+        check(lib.snuffy_gemm_tc(dsp.ptr, dsp.stride, kbd_t.ptr, kbd_t.stride, N, d, hk, passes, None, 0, None, 0, None, None,
+                                 dqv[rows, :d].data_ptr(), 2 * d, None, None, 0, 0.0, 0, 0, _stream()), "snuffy_gemm_tc")
+        del dsp
+        # dKbd = dS^T . Q           [h*Ksel, d], contraction over the N patches -> split-K; its diagonal blocks are dKp
+        dkbd = gemm_tc_splitk(planes_t(G, 128), planes_t(qv[rows, :d], rc_d), M=hk, N=d, K=N, passes=passes)
+        check(lib.snuffy_block_diag_extract(dkbd.data_ptr(), Ksel, h, d, dkp[b * Ksel:(b + 1) * Ksel].data_ptr(), _stream()),
+              "snuffy_block_diag_extract")
+    return dqv[:, :d], dqv[:, d:], dkp, dqv

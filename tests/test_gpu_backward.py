@@ -375,3 +375,24 @@ def test_tensor_core_backward_matches_fp32_backward_at_scale():
         # the two runs also differ in the FORWARD precision (split-bf16 vs fp32), which the softmax Jacobian amplifies
         # for the tiny query/key-projection gradients (measured 2.3e-3 on linears.0.weight, <= 4e-4 elsewhere)
         assert _rel(grads["bf16x3"][k], ref) < 5e-3, (k, _rel(grads["bf16x3"][k], ref))
+
+
+@pytest.mark.parametrize("B,n,ks,h,d,p", [(1, 300, 40, 2, 64, 0.0), (1, 1000, 200, 8, 512, 0.0), (2, 256, 24, 4, 128, 0.0),
+                                          (1, 777, 100, 8, 768, 0.2)])
+def test_sparse_attention_backward_tensor_core(ops, B, n, ks, h, d, p):
+    """All heads of a bag through dense tcgen05 GEMMs against head-block operands == the head-batched SIMT backward
+    (and fp64 autograd when there is no dropout)."""
+    assert ops.sparse_attn_bwd_tc_supported(B, n, ks, h, d)
+    g = torch.Generator(device="cuda").manual_seed(n)
+    qv = torch.randn(B * n, 2 * d, device="cuda", generator=g)
+    kp = torch.randn(B * ks, d, device="cuda", generator=g)
+    d_o = torch.randn(B * ks, d, device="cuda", generator=g)
+    q, v = qv[:, :d], qv[:, d:]
+    drop = (p, 5, 9)
+    _, _, stats = ops.sparse_attn(q, v, kp, B, n, ks, h, want_probs=False, want_stats=True)
+    _, qvp, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    dq, dv, dkp, dqv = ops.sparse_attn_bwd_tc(qvp, qv, kp, d_o, stats, B, n, ks, h, d, drop)
+    rq, rv, rkp, _ = ops.sparse_attn_bwd(q, v, kp, d_o, stats, B, n, ks, h, drop)
+    assert _rel(dq.double(), rq.double()) < 1e-4 and _rel(dv.double(), rv.double()) < 1e-4
+    assert _rel(dkp.double(), rkp.double()) < 1e-4
+    assert torch.equal(dqv[:, :d], dq) and torch.equal(dqv[:, d:], dv)
