@@ -27,6 +27,24 @@ int check_launch(const char* what, int launches) {
     return 0;
 }
 
+cudaError_t ensure_dynamic_smem(const void* func, int bytes) {
+    struct Entry { const void* func; int dev; int bytes; };
+    static thread_local Entry cache[64];
+    static thread_local int n = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    for (int i = 0; i < n; ++i)
+        if (cache[i].func == func && cache[i].dev == dev) {
+            if (cache[i].bytes >= bytes) return cudaSuccess;
+            const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            if (e == cudaSuccess) cache[i].bytes = bytes;
+            return e;
+        }
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && n < 64) cache[n++] = Entry{func, dev, bytes};
+    return e;
+}
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;

@@ -338,7 +338,7 @@ int snuffy_sparse_attn_fwd(const float* Q, int64_t ldq, const float* V, int64_t 
     dim3 grid((unsigned)pl.splits, (unsigned)(h * pl.nvs), (unsigned)(B * pl.nkc));
 #define ATTN_LAUNCH(PASS, KC)                                                                                   \
     do {                                                                                                        \
-        SNUFFY_CUDA(cudaFuncSetAttribute(attn_simt_kernel<PASS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_simt_kernel<PASS, KC>), \
                                          (int)pl.smem));                                                        \
         attn_simt_kernel<PASS, KC><<<grid, 256, pl.smem, stream>>>(p);                                          \
     } while (0)

@@ -516,11 +516,11 @@ static int launch_attn_tc(const void* qv_planes, int64_t plane_stride, int64_t l
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
     p.cu_seqlens = cu_seqlens;
     if (pl.nkc == 1) {
-        SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_tc_kernel<0>), (int)pl.smem));
         attn_tc_kernel<0><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
     } else {
-        SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        SNUFFY_CUDA(cudaFuncSetAttribute(attn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_tc_kernel<1>), (int)pl.smem));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_tc_kernel<2>), (int)pl.smem));
         attn_tc_kernel<1><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
         attn_tc_kernel<2><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
     }

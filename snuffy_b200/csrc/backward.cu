@@ -224,7 +224,7 @@ int snuffy_ln_rows_bwd(const float* dy, const float* dy_bcast, int64_t rows_per_
     const size_t smem = (size_t)warps * 2 * d * 4;
     SNUFFY_REQUIRE(smem <= 200 * 1024, "snuffy_ln_rows_bwd: d=%lld too large", (long long)d);
     if (smem > 48 * 1024)
-        SNUFFY_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_rows_bwd_kernel), (int)smem));
     const int64_t blocks = snuffy_ln_rows_bwd_blocks(rows);
     ln_rows_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(dy, dy_bcast, rows_per_bag, bscale, x, row_map, alt,
                                                                       stats, gamma, add, rows, (int)d, dx, partials);

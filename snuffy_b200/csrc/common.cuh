@@ -14,6 +14,9 @@ namespace snuffy {
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what, int launches = 1);   // cudaGetLastError -> status; counts kernel launches
 int  sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device, size): the call costs microseconds on every launch
+// otherwise, and the training step is bound by host-side launch overhead.
+cudaError_t ensure_dynamic_smem(const void* func, int bytes);
 
 #define SNUFFY_REQUIRE(cond, ...)                         \
     do {                                                  \

@@ -317,12 +317,10 @@ static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const
     const int total = p.m_tiles * p.n_tiles * p.ksplit;
     const int grid = total < sm_count() ? total : sm_count();
     if (bn == 256) {
-        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)TcCfg<256>::SMEM_BYTES));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<256>), (int)TcCfg<256>::SMEM_BYTES));
         gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p);
     } else {
-        SNUFFY_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)TcCfg<128>::SMEM_BYTES));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<128>), (int)TcCfg<128>::SMEM_BYTES));
         gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(p);
     }
     return check_launch(who);

@@ -430,7 +430,7 @@ int snuffy_ln_rows_fwd(const float* x, const int32_t* row_map, const float* alt,
 #define LN_LAUNCH(MAXIT)                                                                                        \
     do {                                                                                                        \
         if (smem > 48 * 1024)                                                                                   \
-            SNUFFY_CUDA(cudaFuncSetAttribute(ln_rows_kernel<MAXIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_rows_kernel<MAXIT>), \
                                              (int)smem));                                                      \
         ln_rows_kernel<MAXIT><<<grid, 256, smem, stream>>>(x, row_map, alt, gamma, beta, rows, (int)d, out_f32,  \
                                                            pl, plane_stride, stats, apply_ln, plane_rc);        \
@@ -457,7 +457,7 @@ int snuffy_scores_ln_planes_fwd(const float* x, const float* W, const float* bia
 #define LNS_LAUNCH(MAXIT)                                                                                              \
     do {                                                                                                               \
         if (smem > 48 * 1024)                                                                                          \
-            SNUFFY_CUDA(cudaFuncSetAttribute(ln_rows_kernel<MAXIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_rows_kernel<MAXIT>), (int)smem)); \
         ln_rows_kernel<MAXIT><<<grid, 256, smem, stream>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)d, nullptr, pl,  \
                                                            plane_stride, stats, 2, 128, W, bias, c, (int)C);            \
     } while (0)
@@ -506,16 +506,16 @@ static int launch_ln_mean_head(const float* x, const float* gamma, const float* 
     const size_t smem = (size_t)8 * d * sizeof(float);
     SNUFFY_REQUIRE(smem <= 200 * 1024, "snuffy_ln_mean_head_fwd: d=%lld too large", (long long)d);
     if (smem > 48 * 1024)
-        SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_mean_head_kernel), (int)smem));
     dim3 grid((unsigned)chunks, (unsigned)B);
     if (d <= 512) {
         if (smem > 48 * 1024)
-            SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_reg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_mean_head_reg_kernel<4>), (int)smem));
         ln_mean_head_reg_kernel<4><<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
                                                                 stats, pooled, bag_out, cu_seqlens);
     } else if (d <= 1024) {
         if (smem > 48 * 1024)
-            SNUFFY_CUDA(cudaFuncSetAttribute(ln_mean_head_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&ln_mean_head_reg_kernel<8>), (int)smem));
         ln_mean_head_reg_kernel<8><<<grid, 256, smem, stream>>>(x, gamma, beta, Wh, bh, N, (int)d, (int)C, partials, tickets,
                                                                 stats, pooled, bag_out, cu_seqlens);
     } else {

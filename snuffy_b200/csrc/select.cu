@@ -331,11 +331,11 @@ static int launch_select(int mode, const float* scores, int64_t B, int64_t N, in
     const size_t smem = (size_t)Kpad * 8 + (cache ? (size_t)N * 4 : 0);
     dim3 grid((unsigned)C, (unsigned)B);
     if (mode == 0) {
-        SNUFFY_CUDA(cudaFuncSetAttribute(select_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&select_kernel<0>), 220 * 1024));
         select_kernel<0><<<grid, SEL_THREADS, smem, stream>>>(scores, (int)N, (int)C, (int)K, Kpad, cache, flags,
                                                               seed, offset, out, cu_seqlens);
     } else {
-        SNUFFY_CUDA(cudaFuncSetAttribute(select_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&select_kernel<1>), 220 * 1024));
         select_kernel<1><<<grid, SEL_THREADS, smem, stream>>>(nullptr, (int)N, 1, (int)K, Kpad, cache, flags, seed,
                                                               offset, out, cu_seqlens);
     }
