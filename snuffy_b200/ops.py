@@ -67,6 +67,16 @@ class Planes:
     def ptr(self) -> int:
         return self.buf.data_ptr()
 
+    def row_window(self, row0: int, rows: int) -> "Planes":
+        """View of `rows` rows starting at row0 (a multiple of rc = whole row tiles) sharing the storage: same K, same
+        distance between the hi and lo plane."""
+        if row0 % self.rc:
+            raise ValueError(f"Planes.row_window: row0={row0} must be a multiple of {self.rc}")
+        w = Planes.__new__(Planes)
+        tile_elems = self.stride // ((self.rows + self.rc - 1) // self.rc)        # elements of one row tile in one plane
+        w.buf, w.rows, w.K, w.rc, w.stride = self.buf[(row0 // self.rc) * tile_elems:], rows, self.K, self.rc, self.stride
+        return w
+
 
 # ------------------------------------------------------------------ a1: instance scores
 def scores(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
@@ -604,10 +614,7 @@ def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: tor
         kbd = block_diag_rows(kp[b * Ksel:(b + 1) * Ksel], h)                     # [h*Ksel, d]
         obd = block_diag_rows(d_o[b * Ksel:(b + 1) * Ksel], h)
         st = stats[b]                                                             # [h, N, 2]
-        # plane window of this bag's rows: whole 128-row tiles starting at b*N
-        a = Planes.__new__(Planes)
-        tile_elems = (qvp.stride // ((qvp.rows + 127) // 128))                    # elements per row tile in one plane
-        a.buf, a.rows, a.K, a.rc, a.stride = qvp.buf[(b * N // 128) * tile_elems:], N, qvp.K, 128, qvp.stride
+        a = qvp.row_window(b * N, N)                                              # this bag's rows (whole 128-row tiles)
         S = gemm_tc_awindow(a, 0, weight_planes(kbd), M=N, N=hk, K=d, passes=passes)            # raw Q_j . Kp_j^T, all heads
         Pd = torch.empty_like(S)
         check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 0, scale, float(drop[0]), drop[1] & _U64,
