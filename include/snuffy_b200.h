@@ -43,7 +43,8 @@ int snuffy_select_topk(const float* scores, int64_t B, int64_t N, int64_t C, int
                        int64_t* idx_out, uint8_t* flags, snuffy_stream_t stream);
 /* K distinct un-flagged rows per bag, uniform without replacement (Philox4x32-10 keyed by seed/offset).
  * Replaces .tolist() + python set difference + np.random.choice + .to(device)  (snuffy.py:136-143,
- * snuffy_multiclass.py:152-157) without the D2H/H2D round trip.  idx_out [B,K] int64.                  */
+ * snuffy_multiclass.py:152-157) without the D2H/H2D round trip.  idx_out [B,K] int64.  The caller guarantees
+ * that every bag has at least K un-flagged rows (the reference's Krand = min(int(K r), N - Ktop) does).          */
 int snuffy_select_random(const uint8_t* flags, int64_t B, int64_t N, int64_t K, uint64_t seed,
                          uint64_t offset, int64_t* idx_out, snuffy_stream_t stream);
 /* ascending distinct flagged rows per bag = torch.unique of the flattened per-class top-K
