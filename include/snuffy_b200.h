@@ -234,6 +234,11 @@ int snuffy_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, f
                       float beta2, float eps, float weight_decay, int64_t step, float gscale,
                       const float* gnorm_sq, float max_norm, snuffy_stream_t stream);
 
+/* dst[offsets[i] .. +sizes[i]) = srcs[i][0 .. sizes[i])  for n tensors (host arrays of device pointers / element counts):
+ * one launch per 32 tensors packs the per-parameter gradients into the flat all-reduce / optimizer buffer.         */
+int snuffy_pack_f32(const void* const* srcs, const int64_t* sizes, const int64_t* offsets, int64_t n, float* dst,
+                    snuffy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "snuffy_mil_loss": (c_int, [P, P, P, P, I, I, I, c_float, c_float, P, P, P, P, P, P, P]),
     "snuffy_sumsq_blocks": (c_int64, [I]),
     "snuffy_sumsq": (c_int, [P, I, P, P, P]),
+    "snuffy_pack_f32": (c_int, [P, P, P, I, P, P]),
     "snuffy_adamw_flat": (c_int, [P, P, P, P, I, c_float, c_float, c_float, c_float, c_float, I, c_float, P, c_float, P]),
 }
 

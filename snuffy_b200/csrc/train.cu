@@ -161,3 +161,45 @@ int snuffy_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, f
 
 }  // extern "C"
 #pragma GCC visibility pop
+
+// ------------------------------------------------------------------ gradient packing
+// Gathers up to 32 tensors per launch into one flat buffer (dst + offsets[i]): ONE launch replaces autograd's per-parameter
+// `grad += g` kernels when the gradients are needed as a single all-reduce / optimizer buffer (dp.FlatBuffers.pack).
+namespace snuffy {
+struct PackArgs { const float* src[32]; long long size[32]; long long off[32]; int n; };
+__global__ void __launch_bounds__(256)
+pack_f32_kernel(const PackArgs a, float* __restrict__ dst) {
+    const int t = blockIdx.y;
+    if (t >= a.n) return;
+    const float* s = a.src[t];
+    float* d = dst + a.off[t];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.size[t]; i += (long long)gridDim.x * blockDim.x)
+        d[i] = s[i];
+}
+}  // namespace snuffy
+
+#pragma GCC visibility push(default)
+extern "C" int snuffy_pack_f32(const void* const* srcs, const int64_t* sizes, const int64_t* offsets, int64_t n, float* dst,
+                               cudaStream_t stream) {
+    using namespace snuffy;
+    SNUFFY_REQUIRE(srcs && sizes && offsets && dst && n >= 0, "snuffy_pack_f32: bad arguments");
+    int launches = 0;
+    for (int64_t base = 0; base < n; base += 32) {
+        PackArgs a{};
+        a.n = (int)((n - base) < 32 ? (n - base) : 32);
+        long long biggest = 1;
+        for (int i = 0; i < a.n; ++i) {
+            a.src[i] = reinterpret_cast<const float*>(srcs[base + i]);
+            a.size[i] = sizes[base + i]; a.off[i] = offsets[base + i];
+            SNUFFY_REQUIRE(a.src[i] || a.size[i] == 0, "snuffy_pack_f32: null source");
+            if (a.size[i] > biggest) biggest = a.size[i];
+        }
+        long long bx = (biggest + 255) / 256;
+        if (bx > 64) bx = 64;
+        dim3 grid((unsigned)bx, (unsigned)a.n);
+        pack_f32_kernel<<<grid, 256, 0, stream>>>(a, dst);
+        ++launches;
+    }
+    return launches ? check_launch("snuffy_pack_f32", launches) : 0;
+}
+#pragma GCC visibility pop

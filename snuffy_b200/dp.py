@@ -75,6 +75,37 @@ class FlatBuffers:
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
                 p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
 
+    def detach_grads(self) -> None:
+        """Before backward: let autograd hand over each gradient tensor as is (no per-parameter `grad += g` kernel); `pack`
+        then gathers them into the flat buffer with one launch."""
+        for p in self.params:
+            p.grad = None
+
+    def pack(self) -> None:
+        """After backward: flat_grad <- the parameters' .grad tensors (zeros where a parameter received none), then the
+        .grad attributes become views of the flat buffer again."""
+        import ctypes
+        from . import _lib
+        n = len(self.params)
+        srcs, sizes, offs, keep = (ctypes.c_void_p * n)(), (ctypes.c_int64 * n)(), (ctypes.c_int64 * n)(), []
+        missing = False
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            g = p.grad
+            if g is None:
+                missing = True
+                srcs[i], sizes[i], offs[i] = None, 0, off
+                continue
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                g = g.float().contiguous()
+            keep.append(g)
+            srcs[i], sizes[i], offs[i] = g.data_ptr(), g.numel(), off
+        if missing:
+            self.flat_grad.zero_()
+        _lib.check(_lib.lib.snuffy_pack_f32(srcs, sizes, offs, n, self.flat_grad.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "snuffy_pack_f32")
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat_grad[off:off + p.numel()].view(p.shape)
+
     def allreduce_sum(self, group=None) -> None:
         """THE collective of the path: one all-reduce of the flat gradient buffer."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -184,17 +215,21 @@ class DataParallelTrainer:
             binary = any(isinstance(m, snuffy.EncoderLayer) for m in model.modules())
             forward_fn = (lambda x: snuffy.forward_bags(model, x)) if binary else model
         self.forward_fn = forward_fn
+        self._cached_layers = [m for m in model.modules() if hasattr(m, "_wcache")]
         invalidate_weight_caches(model)
 
     def train_step(self, bags: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        self.model.train()
-        self.flat.zero_grad()
+        if not self.model.training:
+            self.model.train()
+        self.flat.detach_grads()
         classes, bag, _ = self.forward_fn(bags)
         loss, _, _ = mil_loss(classes, bag, labels, self.mix_weight, self.class_weight)
         loss.backward()
+        self.flat.pack()                                              # one launch instead of one `grad += g` per parameter
         self.flat.allreduce_sum(self.group)
         self.opt.step(grad_scale=1.0 / self.world)
-        invalidate_weight_caches(self.model)
+        for m in self._cached_layers:                                 # the optimizer kernel bypasses autograd's version counters
+            m._wcache = None
         return loss.detach()
 
     @torch.no_grad()
