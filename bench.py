@@ -242,7 +242,7 @@ def kernel_rooflines(model, batch, peaks, device):
 
 
 # ------------------------------------------------------------------ training step (configs[4]: DP training loop)
-def train_throughput(device, world, steps=6, warm=2):
+def train_throughput(device, world, steps=10, warm=3):
     """Train-mode step of the reference loop (train.py:249-264: one bag per optimizer step per process) at cfg2:
     forward (bf16x3) + fused loss + backward (fp32 SIMT) + one all-reduce of the flat gradient + AdamW.  slides/s over
     all ranks; CUDA events, max over ranks done by the caller."""
