@@ -484,7 +484,7 @@ def main():
         train = {"value": world * t_steps / (t_ms * 1e-3), "unit": "slides/s", "ms_per_step": t_ms / t_steps,
                  "bags_per_step_per_gpu": 1, "steps": t_steps, "final_loss": t_loss,
                  "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
-                 "launches_per_step": int((lib.snuffy_launch_count() - lc0) / (t_steps + 2)),
+                 "launches_per_step": int((lib.snuffy_launch_count() - lc0) / (t_steps + 3)),   # 3 warm-up steps
                  "what": "train.py-style step at cfg2 (train mode, attention dropout 0.1): forward bf16x3 + fused MIL loss "
                          "+ backward (fp32 SIMT) + one flat-gradient all-reduce + flat AdamW"}
     kernels = [] if (args.skip_kernels or rank != 0) else kernel_rooflines(model, B, peaks, device)
