@@ -164,8 +164,8 @@ def kernel_rooflines(model, batch, peaks, device):
                     want_planes=True)
     t = cuda_time(ffn_up, 10)
     flops = 2.0 * rows * dff * d
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch in profiles/r01c_gemm_tc_ncu_full.csv
-    # (ncu --set full, batch 8: 168.2 MB read + 597.0 MB written), scaled to the batch in use
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch (ncu --set full): 168.2 MB read + 597.0 MB written at
+    # batch 8 (profiles/r01c_gemm_tc_ncu_full.csv), 332 MB + 1252 MB at batch 16 (profiles/r01g_...); scaled to the batch in use
     res.append(dict(kernel="gemm_tc<256> FFN-up (LN2(y) W1^T, relu, planes out)", bound="tensor",
                     achieved=flops / t / 1e12, peak=peaks["tf_burst"], unit="TFLOP/s", frac=flops / t / 1e12 / peaks["tf_burst"],
                     traffic=765.2e6 * batch / 8, launch_ms=t * 1e3, passes=3, issued_tflops=3 * flops / t / 1e12,
