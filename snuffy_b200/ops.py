@@ -591,8 +591,7 @@ def block_diag_rows(src: torch.Tensor, h: int) -> torch.Tensor:
 
 
 def sparse_attn_bwd_tc_supported(B: int, N: int, Ksel: int, h: int, d: int) -> bool:
-    # bag row ranges must start on a 128-row plane tile (one bag per call, the reference's training pattern, or N % 128 == 0)
-    return d % 32 == 0 and (d // h) % 4 == 0 and (h * Ksel) % 8 == 0 and h * Ksel <= 4096 and (B == 1 or N % 128 == 0)
+    return d % 32 == 0 and (d // h) % 4 == 0 and (h * Ksel) % 8 == 0 and h * Ksel <= 4096
 
 
 def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: torch.Tensor, stats: torch.Tensor, B: int, N: int,
@@ -614,7 +613,10 @@ def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: tor
         kbd = block_diag_rows(kp[b * Ksel:(b + 1) * Ksel], h)                     # [h*Ksel, d]
         obd = block_diag_rows(d_o[b * Ksel:(b + 1) * Ksel], h)
         st = stats[b]                                                             # [h, N, 2]
-        a = qvp.row_window(b * N, N)                                              # this bag's rows (whole 128-row tiles)
+        if (b * N) % 128 == 0:
+            a = qvp.row_window(b * N, N)                                          # this bag's rows (whole 128-row tiles)
+        else:                                                                     # bag starts inside a plane tile: re-split its rows
+            _, a, _ = ln_rows(qv[rows], None, None, apply_ln=False, want_planes=True)
         S = gemm_tc_awindow(a, 0, weight_planes(kbd), M=N, N=hk, K=d, passes=passes)            # raw Q_j . Kp_j^T, all heads
         Pd = torch.empty_like(S)
         check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 0, scale, float(drop[0]), drop[1] & _U64,
