@@ -272,8 +272,8 @@ class DsmilBClassifierFunction(torch.autograd.Function):
         mlp = _QMlp(qp)
         q, q_saved = mlp.forward(feats_d)
         crit = ops.select_topk(c.detach().contiguous().view(1, n, ncls), 1).view(1, ncls)   # dsmil.py:78-81
-        m_feats = ops.gather_rows(feats_d.view(1, n, d), crit).view(ncls, d)
-        q_max, qm_saved = mlp.forward(m_feats)
+        q_max = ops.gather_rows(q.view(1, n, q.shape[1]), crit).view(ncls, q.shape[1])    # = q(feats[crit]): row crit of Q
+        qm_saved = None
         a, bm, logits = ops.dsmil_pool(q, q_max, v, fp[0].detach(), fp[1].detach())
         ctx.mlp, ctx.saved = mlp, (feats_d, v, v_saved, q, q_saved, q_max, qm_saved, crit, a, bm, drop)
         ctx.nq, ctx.nv = len(qp), len(vp)
@@ -303,9 +303,8 @@ class DsmilBClassifierFunction(torch.autograd.Function):
         d_s = ops.softmax_cols_bwd(a, d_a, float(torch.sqrt(torch.tensor(dq_dim, dtype=torch.float32))))
         d_q = ops.matmul_nn(d_s, q_max)                                              # [N, 128]
         d_qmax = ops.matmul_tn(d_s, q)                                               # [C, 128]
-        gq, d_feats = ctx.mlp.backward(q_saved, d_q, want_dfeats)
-        gqm, d_mfeats = ctx.mlp.backward(qm_saved, d_qmax, want_dfeats)
-        q_grads = [g1 + g2 for g1, g2 in zip(gq, gqm)]
+        ops.scatter_add_rows(d_q.view(1, n, dq_dim), crit, d_qmax)                   # q_max is row crit of Q
+        q_grads, d_feats = ctx.mlp.backward(q_saved, d_q, want_dfeats)
         v_grads = []
         if ctx.nv:
             a0, hv = v_saved
@@ -316,9 +315,6 @@ class DsmilBClassifierFunction(torch.autograd.Function):
                 d_feats = d_feats + (ops.act_bwd(None, dfv, drop=drop)[0] if drop[0] > 0 else dfv)
         elif want_dfeats:
             d_feats = d_feats + d_v
-        if want_dfeats:
-            d_feats = d_feats.contiguous()
-            ops.scatter_add_rows(d_feats.view(1, n, d), crit, d_mfeats)
         ctx.saved = None
         return (None, d_feats if want_dfeats else None, None, *q_grads, *v_grads, d_fw, d_fb)
 

@@ -90,12 +90,12 @@ dsmil_pool_kernel(const float* __restrict__ V, int64_t N, int d, int C, int stat
         for (int64_t n = r0; n < r1; ++n) {
             float a[DS_MAXC];
 #pragma unroll
-            for (int c = 0; c < DS_MAXC; ++c) a[c] = (c < C) ? expf(A[n * C + c] - s_m[c]) * s_inv[c] : 0.f;
+            for (int c = 0; c < DS_MAXC; ++c) a[c] = (c < C) ? expf(__ldg(A + n * C + c) - s_m[c]) * s_inv[c] : 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int e = e0 + t + 256 * i;
                 if (e < d) {
-                    const float v = V[n * d + e];
+                    const float v = __ldg(V + n * d + e);
 #pragma unroll
                     for (int c = 0; c < DS_MAXC; ++c) acc[c][i] = fmaf(a[c], v, acc[c][i]);
                 }
@@ -124,9 +124,15 @@ dsmil_head_kernel(const float* __restrict__ B_part, int chunks, int C, int d, co
                   const float* __restrict__ bias, float* __restrict__ Bm, float* __restrict__ logits) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < C * d; i += 256) {
-        float s = 0.f;
-        for (int k = 0; k < chunks; ++k) s += B_part[(int64_t)k * C * d + i];
-        Bm[i] = s;
+        // fixed order, 8 loads in flight: a single bag waits on this serial tail
+        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int k = 0;
+        for (; k + 8 <= chunks; k += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a8[u] += __ldcg(B_part + (int64_t)(k + u) * C * d + i);
+        }
+        for (; k < chunks; ++k) a8[0] += __ldcg(B_part + (int64_t)k * C * d + i);
+        Bm[i] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
     }
     __syncthreads();
     for (int o = warp; o < C; o += 8) {

@@ -51,8 +51,8 @@ class BClassifier(nn.Module):
         q = self._q(feats)
         # critical instance per class = first row of the descending sort (dsmil.py:78-81): top-1 selection
         crit = ops.select_topk(c.view(1, n, ncls), 1).view(1, ncls)
-        m_feats = ops.gather_rows(feats.view(1, n, d), crit).view(ncls, d)
-        q_max = self._q(m_feats)
+        # q_max = q(feats[crit]) (dsmil.py:80-82) is row crit of Q: the same MLP applied to the same row -> gather it
+        q_max = ops.gather_rows(q.view(1, n, q.shape[1]), crit).view(ncls, q.shape[1])
         a, bm, logits = ops.dsmil_pool(q, q_max, v, self.fcc.weight.detach(), self.fcc.bias.detach())
         return logits.view(1, -1), a, bm.view(1, ncls, d)
 

@@ -74,3 +74,18 @@ for K in (64, 256, 1024):
     print(json.dumps({"config": "cfg4 varlen 64 bags N~logU[1k,50k]", "K": K, "bags": int(ok.sum()), "rows": int(cu_ok[-1]),
                       "ms_packed": round(ms_packed, 3), "ms_one_call_per_bag": round(ms_loop, 3),
                       "slides_per_s_packed": round(ok.sum() / ms_packed * 1e3, 1)}), flush=True)
+
+# dsmil: MILNet forward on a cfg2-shaped bag [10000, 512], C = 1, and the pooling kernel alone
+from snuffy_b200 import dsmil, ops
+for nonlinear, passing_v in ((True, False), (True, True)):
+    dm = dsmil.MILNet(dsmil.FCLayer(512, 1), dsmil.BClassifier(512, 1, 0.0, nonlinear, passing_v)).cuda().eval()
+    xd = torch.randn(10000, 512, device="cuda")
+    with torch.no_grad():
+        ms = timeit(lambda: dm(xd))
+    print(json.dumps({"config": "dsmil MILNet", "N": 10000, "d": 512, "C": 1, "nonlinear": nonlinear, "passing_v": passing_v,
+                      "ms_per_call": round(ms, 4), "slides_per_s": round(1e3 / ms, 1)}), flush=True)
+q = torch.randn(10000, 128, device="cuda"); qm = torch.randn(1, 128, device="cuda"); v = torch.randn(10000, 512, device="cuda")
+wf = torch.randn(1, 1, 512, device="cuda"); bf = torch.zeros(1, device="cuda")
+ms = timeit(lambda: ops.dsmil_pool(q, qm, v, wf, bf), iters=50)
+byts = 10000 * (128 + 512) * 4 + 10000 * 4
+print(json.dumps({"config": "dsmil_pool kernel alone", "ms": round(ms, 4), "algorithmic_GBps": round(byts / ms / 1e6, 1)}), flush=True)
