@@ -559,7 +559,7 @@ struct PlanesTParams {
 
 __global__ void __launch_bounds__(256)
 planes_t_kernel(const PlanesTParams p) {
-    __shared__ float tile[32][129];
+    __shared__ __align__(16) float tile[32][132];        // 16-byte aligned rows: float4 stores, conflict-free column reads
     const int t = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.y * 32;
     const int c0 = blockIdx.x * 128;
@@ -591,8 +591,7 @@ planes_t_kernel(const PlanesTParams p) {
                 }
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tile[row][c4 + j] = v[j];
+        *reinterpret_cast<float4*>(&tile[row][c4]) = make_float4(v[0], v[1], v[2], v[3]);
     }
     __syncthreads();
     const int64_t nkb = plane_kblocks(p.R);
