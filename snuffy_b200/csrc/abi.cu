@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 
 namespace snuffy {
 
@@ -28,11 +29,15 @@ int check_launch(const char* what, int launches) {
 }
 
 cudaError_t ensure_dynamic_smem(const void* func, int bytes) {
+    // The attribute is a property of the kernel on the device, shared by all host threads (PyTorch runs backward passes on its
+    // own autograd thread): one process-wide table, and the value only ever grows.
     struct Entry { const void* func; int dev; int bytes; };
-    static thread_local Entry cache[64];
-    static thread_local int n = 0;
+    static Entry cache[128];
+    static int n = 0;
+    static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    std::lock_guard<std::mutex> lock(mu);
     for (int i = 0; i < n; ++i)
         if (cache[i].func == func && cache[i].dev == dev) {
             if (cache[i].bytes >= bytes) return cudaSuccess;
@@ -41,7 +46,7 @@ cudaError_t ensure_dynamic_smem(const void* func, int bytes) {
             return e;
         }
     const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess && n < 64) cache[n++] = Entry{func, dev, bytes};
+    if (e == cudaSuccess && n < 128) cache[n++] = Entry{func, dev, bytes};
     return e;
 }
 
