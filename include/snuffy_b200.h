@@ -239,6 +239,19 @@ int snuffy_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, f
 int snuffy_pack_f32(const void* const* srcs, const int64_t* sizes, const int64_t* offsets, int64_t n, float* dst,
                     snuffy_stream_t stream);
 
+/* ---- patch-level outputs on the device (step after the path in valid/test)                                    */
+/* probs[i] = sigmoid(scores[i]), i < n  (train.py:913-916): the per-bag `attentions` the reference copies to the host
+ * one bag at a time (train.py:271, 345, 354); the caller points probs at a row offset of one epoch-wide buffer.   */
+int snuffy_patch_probs(const float* scores, int64_t n, float* probs, snuffy_stream_t stream);
+/* FROC detection tuples (train.py:342-345 + mp_thresholding train.py:138-141).  Slide b owns rows
+ * [cu_seqlens[b], cu_seqlens[b+1]) (cu_seqlens NULL: one slide of `total` rows); probs[r * prob_stride] is row r's
+ * probability, positions int32 [total, 2] its patch grid coordinates.  Rows with probability > threshold (strict) are
+ * kept in patch order: det_prob[start + j], det_xy[start + j] = (x * tile + half, y * tile + half), count[b] = kept.  */
+int snuffy_froc_detections(const float* probs, int64_t prob_stride, const int32_t* positions,
+                           const int32_t* cu_seqlens, int64_t slides, int64_t total, float threshold,
+                           int32_t tile, int32_t half, float* det_prob, int32_t* det_xy, int32_t* count,
+                           snuffy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,16 +195,71 @@ def gen_loss(ref_dir):
     print("loss_glue: ", [round(c["loss"], 6) for c in cases])
 
 
+def _import_reference_train(ref_dir):
+    """The caller module itself, with stand-ins for the logging / plotting / WSI packages it imports but this path never
+    touches: nothing of the reference is edited."""
+    import types
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return type(k, (), {})
+    for name in ["lightly", "lightly.utils", "lightly.utils.scheduler", "multiresolutionimageinterface", "skimage",
+                 "skimage.measure", "matplotlib", "matplotlib.pyplot", "wandb"]:
+        sys.modules.setdefault(name, _Any(name))
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import train
+    return train
+
+
+def gen_patch_outputs(ref_dir):
+    """Patch probabilities from the reference's Snuffy._run_model (train.py:913-916 over 828-846), detection tuples by the
+    expression of train.py:342-345 and the filter `mp_thresholding` (train.py:138-141) itself."""
+    import re
+    train = _import_reference_train(ref_dir)
+    rs = np.random.RandomState(21)
+    n = 300
+    logits = (rs.standard_normal((1, n, 1)) * 3).astype(np.float32)
+    logits[0, :6, 0] = [0.0, -0.0, 40.0, -40.0, 100.0, -100.0]
+    bag = rs.standard_normal((1, 1)).astype(np.float32)
+    names = [f"patch_{rs.randint(0, 400)}_{rs.randint(0, 400)}.jpeg" for _ in range(n)]
+    trainer = object.__new__(train.Snuffy)
+    trainer.milnet = lambda x: (torch.from_numpy(logits), torch.from_numpy(bag), None)
+    trainer.criterion = torch.nn.BCEWithLogitsLoss()
+    trainer.single_weight_parameter = torch.tensor(0.5)
+    pred, loss, att = trainer._run_model(torch.zeros(1, n, 4), torch.tensor([[1.0]]))
+    probs32 = att.numpy()
+    reg = r'[^\d]*(\d+)[^\d]*(\d+)[^\d]*'                                                   # train.py:313
+    pos = [tuple(map(int, re.search(reg, p).group(1, 2))) for p in names]                      # train.py:314-320
+    dets = [(float(prob), position[0] * 512 + 256, position[1] * 512 + 256)
+            for position, prob in zip(pos, probs32.squeeze())]                                 # train.py:342-345
+    thresholds = [0.5, float(np.sort(probs32.ravel())[n // 3]), 0.0, 1.0]
+    kept = [train.mp_thresholding((dets, t, "slide"))[1] for t in thresholds]
+    np.savez_compressed(os.path.join(OUT, "patch_outputs.npz"), logits=logits, bag=bag, names=np.array(names),
+                        probs32=probs32, pred=np.asarray(pred), positions=np.array(pos, dtype=np.int64),
+                        detections=np.array(dets, dtype=np.float64), thresholds=np.array(thresholds, dtype=np.float64),
+                        **{f"kept{i}": np.array(k, dtype=np.float64).reshape(-1, 3) for i, k in enumerate(kept)})
+    print("patch_outputs: kept", [len(k) for k in kept])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default=os.environ.get("SNUFFY_REF", "/root/reference"))
+    ap.add_argument("--only", default=None, help="generate one group: patch_outputs")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.only == "patch_outputs":
+        gen_patch_outputs(args.ref)
+        return
     gen_snuffy(args.ref, BINARY_CASES, multiclass=False)
     gen_snuffy(args.ref, MULTI_CASES, multiclass=True)
     gen_dsmil(args.ref)
     gen_loss(args.ref)
+    gen_patch_outputs(args.ref)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ there is no CPU or PyTorch fallback.  Drop-in modules: :mod:`snuffy_b200.snuffy`
 names by putting ``dropin/`` first on ``sys.path``).
 """
 from . import _lib  # noqa: F401  (fails loudly if the native library is missing)
-from . import dp, dsmil, engine, ops, snuffy, snuffy_multiclass, store  # noqa: F401
+from . import dp, dsmil, engine, ops, patch_outputs, snuffy, snuffy_multiclass, store  # noqa: F401
 
 __all__ = ["snuffy", "snuffy_multiclass", "dsmil", "ops", "engine", "dp", "store"]
 __version__ = "0.1.0"

@@ -74,6 +74,8 @@ _SIGNATURES = {
     "snuffy_sumsq": (c_int, [P, I, P, P, P]),
     "snuffy_pack_f32": (c_int, [P, P, P, I, P, P]),
     "snuffy_adamw_flat": (c_int, [P, P, P, P, I, c_float, c_float, c_float, c_float, c_float, I, c_float, P, c_float, P]),
+    "snuffy_patch_probs": (c_int, [P, I, P, P]),
+    "snuffy_froc_detections": (c_int, [P, I, P, P, I, I, c_float, c_int, c_int, P, P, P, P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

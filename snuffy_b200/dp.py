@@ -239,3 +239,23 @@ class DataParallelTrainer:
         classes, bag, _ = self.forward_fn(bags)
         _, pred, _ = mil_loss(classes, bag, torch.zeros_like(bag), self.mix_weight, self.class_weight)
         return pred
+
+    def validate(self, bags, collector=None):
+        """The reference's `valid` loop (train.py:334-355) without its per-bag host syncs: `bags` yields
+        (slide id, bag [1, N, d] on the device, label [1, C] on the device) — e.g. a store.PinnedPrefetcher.  Per bag:
+        eval forward, the fused loss kernel, and (if a patch_outputs.PatchOutputCollector is given) the patch probabilities
+        and the mixed prediction appended to its epoch buffers.  Returns (mean loss [device scalar], slide ids); nothing
+        is copied to the host here."""
+        self.model.eval()
+        total, ids = None, []
+        with torch.no_grad():
+            for sid, bag_x, label in bags:
+                classes, bag, _ = self.forward_fn(bag_x)
+                loss, pred, _ = mil_loss(classes, bag, label, self.mix_weight, self.class_weight)
+                if collector is not None:
+                    collector.add(classes, pred)
+                total = loss.clone() if total is None else total.add_(loss)
+                ids.append(sid)
+        if total is None:
+            raise ValueError("validate: no bags")
+        return total / len(ids), ids

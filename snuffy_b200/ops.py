@@ -643,3 +643,46 @@ def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: tor
         check(lib.snuffy_block_diag_extract(dkbd.data_ptr(), Ksel, h, d, dkp[b * Ksel:(b + 1) * Ksel].data_ptr(), _stream()),
               "snuffy_block_diag_extract")
     return dqv[:, :d], dqv[:, d:], dkp, dqv
+
+
+# ------------------------------------------------------------------ patch-level outputs
+def patch_probs(scores: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sigmoid of the instance scores (train.py:913-916), optionally written into a caller-owned slice `out`
+    (same number of elements, contiguous) of an epoch-wide buffer."""
+    s = _f32(scores, "scores")
+    if out is None:
+        out = torch.empty_like(s)
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == s.numel()):
+        raise ValueError("patch_probs: `out` must be a contiguous float32 CUDA tensor with scores.numel() elements")
+    check(lib.snuffy_patch_probs(s.data_ptr(), s.numel(), out.data_ptr(), _stream()), "snuffy_patch_probs")
+    return out
+
+
+def froc_detections(probs: torch.Tensor, positions: torch.Tensor, threshold: float,
+                    cu_seqlens: Optional[torch.Tensor] = None, tile: int = 512, half: int = 256
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Stable per-slide compaction of the patches with probability > threshold (train.py:342-345, 138-141).
+
+    probs [T] or [T, C] (column 0 is used, like the binary caller), positions int32 [T, 2], cu_seqlens int32 [B+1] or None
+    (one slide).  Returns (det_prob [T], det_xy [T, 2] int32, count [B] int32): slide b's detections are rows
+    cu_seqlens[b] .. cu_seqlens[b] + count[b] of det_*; rows beyond the count are unspecified."""
+    p = _f32(probs, "probs")
+    T = p.shape[0]
+    stride = 1 if p.dim() == 1 else int(p.shape[1])
+    if positions.dtype != torch.int32 or not positions.is_cuda or tuple(positions.shape) != (T, 2):
+        raise ValueError("froc_detections: `positions` must be an int32 CUDA tensor of shape [T, 2]")
+    positions = positions.contiguous()
+    if cu_seqlens is not None:
+        if cu_seqlens.dtype != torch.int32 or not cu_seqlens.is_cuda or cu_seqlens.dim() != 1 or cu_seqlens.numel() < 2:
+            raise ValueError("froc_detections: `cu_seqlens` must be an int32 CUDA tensor [B+1]")
+        cu_seqlens = cu_seqlens.contiguous()
+        slides = cu_seqlens.numel() - 1
+    else:
+        slides = 1
+    det_prob = torch.empty(T, dtype=torch.float32, device=p.device)
+    det_xy = torch.empty(T, 2, dtype=torch.int32, device=p.device)
+    count = torch.empty(slides, dtype=torch.int32, device=p.device)
+    check(lib.snuffy_froc_detections(p.data_ptr(), stride, positions.data_ptr(), _ptr(cu_seqlens), slides, T, float(threshold),
+                                     int(tile), int(half), det_prob.data_ptr(), det_xy.data_ptr(), count.data_ptr(), _stream()),
+          "snuffy_froc_detections")
+    return det_prob, det_xy, count
