@@ -70,6 +70,7 @@ _SIGNATURES = {
     "snuffy_attn_seg_bwd": (c_int, [P, P, I, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P]),
     "snuffy_softmax_cols_bwd": (c_int, [P, P, I, I, c_float, P, P]),
     "snuffy_mil_loss": (c_int, [P, P, P, P, I, I, I, c_float, c_float, P, P, P, P, P, P, P]),
+    "snuffy_rng_advance": (c_int, [P, c_uint64, P]),
     "snuffy_sumsq_blocks": (c_int64, [I]),
     "snuffy_sumsq": (c_int, [P, I, P, P, P]),
     "snuffy_pack_f32": (c_int, [P, P, P, I, P, P]),

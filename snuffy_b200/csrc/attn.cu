@@ -33,7 +33,8 @@ struct AttnParams {
 
 __device__ __forceinline__ float drop_scale(const AttnParams& p, int b, int j, int n, int key) {
     const uint64_t idx = (((uint64_t)(b * p.h + j) * p.N + n) * p.Ksel + key);
-    return drop_keep_scale(p.seed, p.offset, idx, p.drop_p);
+    const DrawKey draw = rng_resolve(p.seed, p.offset);
+    return drop_keep_scale(draw.seed, draw.offset, idx, p.drop_p);
 }
 
 template <int PASS, int KC>

@@ -363,10 +363,11 @@ attn_tc_kernel(const AttnTcParams p) {
                         for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) po[e] = v[e];
                     }
                     if (p.drop_p > 0.f && valid) {
+                        const DrawKey dkey = rng_resolve(p.seed, p.offset);
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             const uint64_t idx = ((uint64_t)srow * p.Ksel + key0 + c * 32 + e);
-                            v[e] *= drop_keep_scale(p.seed, p.offset, idx, p.drop_p);
+                            v[e] *= drop_keep_scale(dkey.seed, dkey.offset, idx, p.drop_p);
                         }
                     }
 #pragma unroll

@@ -81,6 +81,7 @@ ln_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy_bc
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ hpre, const float* __restrict__ da, int act, float drop_p, uint64_t seed,
                uint64_t offset, int64_t total4, float* __restrict__ dh, float* __restrict__ a_out) {
+    { const DrawKey key_ = rng_resolve(seed, offset); seed = key_.seed; offset = key_.offset; }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         float h[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
         if (hpre) { const float4 v = __ldg(reinterpret_cast<const float4*>(hpre) + i); h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w; }
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256)
 attn_rows_bwd_kernel(const float* __restrict__ S, const float* __restrict__ stats, int64_t nrows, int Ksel, int64_t N,
                      int mode, float inv_scale, float drop_p, uint64_t seed, uint64_t offset, float* __restrict__ Pd,
                      float* __restrict__ G) {
+    { const DrawKey key_ = rng_resolve(seed, offset); seed = key_.seed; offset = key_.offset; }
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= nrows) return;
@@ -361,6 +363,7 @@ block_diag_extract_kernel(const float* __restrict__ bd, int Ksel, int h, int d, 
 __global__ void __launch_bounds__(256)
 attn_seg_bwd_kernel(const float* __restrict__ S, const float* __restrict__ stats, int64_t N, int h, int Ksel, int bag, int mode,
                     float inv_scale, float drop_p, uint64_t seed, uint64_t offset, float* __restrict__ Pd, float* __restrict__ G) {
+    { const DrawKey key_ = rng_resolve(seed, offset); seed = key_.seed; offset = key_.offset; }
     const int lane = threadIdx.x & 31;
     const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (n, j)
     if (seg >= N * h) return;

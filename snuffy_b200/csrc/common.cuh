@@ -77,6 +77,18 @@ __device__ __forceinline__ float act_grad(int act, float t) {
 // ---------------------------------------------------------------- dropout
 // Counter-based keep mask: element `idx` of the tensor drawn with (seed, offset) is kept iff u(idx) >= p and
 // is then scaled by 1/(1-p) (nn.Dropout semantics).  Forward and backward regenerate the same mask.
+// Indirect draws, for CUDA-graph replays (the kernel arguments are frozen at capture): when bit 63 of `seed` is set, `offset` is
+// the address of a device uint64 step counter, and the draw actually used is
+//   (seed & 0xFFFFFFFF,  *counter + ((seed >> 32) & 0x7FFFFFFF)).
+// snuffy_rng_advance bumps the counter once per replay; forward and backward of one replay see the same value.
+struct DrawKey { uint64_t seed, offset; };
+__device__ __forceinline__ DrawKey rng_resolve(uint64_t seed, uint64_t offset) {
+    if (seed >> 63) {
+        offset = *reinterpret_cast<const uint64_t*>(offset) + ((seed >> 32) & 0x7FFFFFFFull);
+        seed &= 0xFFFFFFFFull;
+    }
+    return DrawKey{seed, offset};
+}
 __device__ __forceinline__ float drop_keep_scale(uint64_t seed, uint64_t offset, uint64_t idx, float p) {
     uint32_t x = (uint32_t)idx ^ (uint32_t)seed, y = (uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32) ^ (uint32_t)offset;
     x *= 0x85EBCA6Bu; x ^= x >> 13; x += y * 0x9E3779B9u + (uint32_t)(offset >> 32);

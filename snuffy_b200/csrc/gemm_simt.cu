@@ -196,8 +196,9 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const fl
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = act_apply(ep.act, v[j]);
                 if (ep.drop_p > 0.f) {
+                    const DrawKey key = rng_resolve(ep.seed, ep.offset);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] *= drop_keep_scale(ep.seed, ep.offset, (uint64_t)(m * N + n + j), ep.drop_p);
+                    for (int j = 0; j < 4; ++j) v[j] *= drop_keep_scale(key.seed, key.offset, (uint64_t)(m * N + n + j), ep.drop_p);
                 }
                 if (rrow) {
                     const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + n));
@@ -210,7 +211,10 @@ gemm_simt_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, const fl
                     if (n + j < N) {
                         if (ep.preact) ep.preact[m * ldc + n + j] = v[j];
                         float o = act_apply(ep.act, v[j]);
-                        if (ep.drop_p > 0.f) o *= drop_keep_scale(ep.seed, ep.offset, (uint64_t)(m * N + n + j), ep.drop_p);
+                        if (ep.drop_p > 0.f) {
+                            const DrawKey key = rng_resolve(ep.seed, ep.offset);
+                            o *= drop_keep_scale(key.seed, key.offset, (uint64_t)(m * N + n + j), ep.drop_p);
+                        }
                         if (rrow) o += rrow[n + j];
                         C[m * ldc + n + j] = o;
                     }

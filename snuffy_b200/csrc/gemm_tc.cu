@@ -222,9 +222,10 @@ gemm_tc_kernel(const TcGemmParams p) {
                         for (int j = 0; j < 32; ++j) v[j] = act_apply(p.act, v[j]);
                 }
                 if (p.drop_p > 0.f) {
+                    const DrawKey dk_ = rng_resolve(p.seed, p.offset);
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        v[j] *= drop_keep_scale(p.seed, p.offset, (uint64_t)(m_own * p.N + col0 + j), p.drop_p);
+                        v[j] *= drop_keep_scale(dk_.seed, dk_.offset, (uint64_t)(m_own * p.N + col0 + j), p.drop_p);
                 }
                 if (p.out_planes) {
                     // thread owns row m_own and 32 consecutive k of the next GEMM = one chunk column block:

@@ -586,7 +586,10 @@ planes_t_kernel(const PlanesTParams p) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float a = act_apply(p.act, v[j]);
-                    if (p.drop_p > 0.f) a *= drop_keep_scale(p.seed, p.offset, (uint64_t)(r * p.C + c + j), p.drop_p);
+                    if (p.drop_p > 0.f) {
+                        const DrawKey key = rng_resolve(p.seed, p.offset);
+                        a *= drop_keep_scale(key.seed, key.offset, (uint64_t)(r * p.C + c + j), p.drop_p);
+                    }
                     v[j] = (c + j < p.C) ? a : 0.f;
                 }
             }

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1)
 select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, int cache_keys,
               uint8_t* __restrict__ flags, uint64_t seed, uint64_t offset, int64_t* __restrict__ out,
               const int64_t* __restrict__ cu_seqlens) {
+    if (MODE == 1) { const DrawKey key_ = rng_resolve(seed, offset); seed = key_.seed; offset = key_.offset; }
     extern __shared__ __align__(16) unsigned char sel_smem[];
     uint64_t* sortbuf = reinterpret_cast<uint64_t*>(sel_smem);
     uint32_t* keys = reinterpret_cast<uint32_t*>(sel_smem + (size_t)Kpad * 8);

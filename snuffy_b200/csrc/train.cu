@@ -65,6 +65,10 @@ mil_loss_kernel(const float* __restrict__ classes, const float* __restrict__ bag
     *ticket = 0;
 }
 
+// counter += delta: the last node of a captured training step, so that the next replay draws fresh dropout masks / random
+// patches (common.cuh rng_resolve).  Every kernel of the replay itself reads the value from before this node.
+__global__ void rng_advance_kernel(unsigned long long* counter, unsigned long long delta) { *counter += delta; }
+
 __global__ void __launch_bounds__(256)
 sumsq_partial_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ partials) {
     __shared__ float red[8];
@@ -124,6 +128,12 @@ int snuffy_mil_loss(const float* classes, const float* bag, const float* label, 
     mil_loss_kernel<<<(unsigned)(B * C), 256, 0, stream>>>(classes, bag, label, weight, N, (int)C, (int)(B * C), w, gscale,
                                                           terms, ticket, loss, pred, dclasses, dbag);
     return check_launch("snuffy_mil_loss");
+}
+
+int snuffy_rng_advance(uint64_t* counter, uint64_t delta, cudaStream_t stream) {
+    SNUFFY_REQUIRE(counter, "snuffy_rng_advance: null counter");
+    rng_advance_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned long long*>(counter), (unsigned long long)delta);
+    return check_launch("snuffy_rng_advance");
 }
 
 int64_t snuffy_sumsq_blocks(int64_t n) {

@@ -195,12 +195,18 @@ def invalidate_weight_caches(model: torch.nn.Module) -> None:
 class DataParallelTrainer:
     """One process per GPU.  train_step(bags [B, N, d], labels [B, C]) = forward + fused loss + backward on this rank's
     bags, one all-reduce of the flat gradient, the same AdamW step on every rank.  Returns the local loss (device tensor,
-    no host sync; the reference's three `.item()` / `.cpu()` syncs per bag are the caller's choice here)."""
+    no host sync; the reference's three `.item()` / `.cpu()` syncs per bag are the caller's choice here).
+    cuda_graph=True replays forward + loss + backward + gradient packing as one captured graph per bag shape (dropout masks and
+    random patches are drawn from a device-side step counter, so replays differ); the returned loss tensor is then a static
+    buffer overwritten by the next step."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 2e-4, betas=(0.5, 0.9), weight_decay: float = 5e-3,
                  clip_grad: Optional[float] = None, mix_weight: float = 0.5, group=None,
-                 forward_fn: Optional[Callable] = None, class_weight: Optional[torch.Tensor] = None):
+                 forward_fn: Optional[Callable] = None, class_weight: Optional[torch.Tensor] = None,
+                 cuda_graph: bool = False):
         self.model = model
+        self.cuda_graph = bool(cuda_graph)
+        self._graph, self._graph_key = None, None
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -218,19 +224,66 @@ class DataParallelTrainer:
         self._cached_layers = [m for m in model.modules() if hasattr(m, "_wcache")]
         invalidate_weight_caches(model)
 
-    def train_step(self, bags: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        if not self.model.training:
-            self.model.train()
+    def _forward_backward(self, bags: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.flat.detach_grads()
         classes, bag, _ = self.forward_fn(bags)
         loss, _, _ = mil_loss(classes, bag, labels, self.mix_weight, self.class_weight)
         loss.backward()
         self.flat.pack()                                              # one launch instead of one `grad += g` per parameter
+        return loss.detach()
+
+    def train_step(self, bags: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        if not self.model.training:
+            self.model.train()
+        if self.cuda_graph:
+            loss = self._replay(bags, labels)
+        else:
+            loss = self._forward_backward(bags, labels)
         self.flat.allreduce_sum(self.group)
         self.opt.step(grad_scale=1.0 / self.world)
         for m in self._cached_layers:                                 # the optimizer kernel bypasses autograd's version counters
             m._wcache = None
-        return loss.detach()
+        return loss
+
+    # ---- cuda_graph=True: forward + loss + backward + gradient packing of one step are ONE graph launch (the eager step is
+    # bound by ~100 host-side launches per bag); the all-reduce and the optimizer kernel stay eager behind it.
+    def _capture(self, bags: torch.Tensor, labels: torch.Tensor) -> None:
+        from . import _lib, engine
+        dev = bags.device
+        self._static_bags, self._static_labels = bags.clone(), labels.to(device=dev, dtype=torch.float32).clone()
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                                 # warm-up off the capture: allocator, kernel attributes
+            for _ in range(2):
+                self._forward_backward(self._static_bags, self._static_labels)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for m in self._cached_layers:                                 # derived operands are rebuilt INSIDE the graph, from the
+            m._wcache = None                                          # parameters as they are at each replay
+        engine._RANDOM.next()                                         # settle the eager stream's (seed, offset) first
+        self._rng_counter = torch.tensor([engine._RANDOM._offset], dtype=torch.int64, device=dev)
+        graph = torch.cuda.CUDAGraph()
+        engine._RANDOM.begin_indirect(self._rng_counter)
+        try:
+            with torch.cuda.graph(graph):
+                self._static_loss = self._forward_backward(self._static_bags, self._static_labels)
+                self._draws_per_step = engine._RANDOM.end_indirect()
+                _lib.check(_lib.lib.snuffy_rng_advance(self._rng_counter.data_ptr(), self._draws_per_step,
+                                                       torch.cuda.current_stream(dev).cuda_stream), "snuffy_rng_advance")
+        finally:
+            engine._RANDOM.end_indirect()
+        for m in self._cached_layers:
+            m._wcache = None
+        self._graph, self._graph_key = graph, (tuple(bags.shape), tuple(labels.shape))
+
+    def _replay(self, bags: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        if self._graph is None or self._graph_key != (tuple(bags.shape), tuple(labels.shape)):
+            self._capture(bags, labels)                               # first step, or a new bag shape: (re)capture
+        self._static_bags.copy_(bags, non_blocking=True)
+        self._static_labels.copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss
 
     @torch.no_grad()
     def predict(self, bags: torch.Tensor) -> torch.Tensor:

@@ -45,8 +45,26 @@ class _RandomStream:
     def __init__(self):
         self._seed = None
         self._offset = 0
+        self._counter = None          # device int64[1] while a CUDA graph is being captured (dp.DataParallelTrainer)
+        self._delta = 0
+
+    def begin_indirect(self, counter: torch.Tensor) -> None:
+        """Until end_indirect(): draws are (seed | bit 63 | k << 32, address of `counter`) — resolved on the device at replay time
+        as (seed & 0xFFFFFFFF, counter + k), include/snuffy_b200.h "Random draws under CUDA-graph replay"."""
+        if counter.dtype != torch.int64 or not counter.is_cuda or counter.numel() != 1:
+            raise ValueError("begin_indirect: counter must be a CUDA int64 tensor with one element")
+        self._counter, self._delta = counter, 0
+
+    def end_indirect(self) -> int:
+        n, self._counter, self._delta = self._delta, None, 0
+        return n
 
     def next(self) -> Tuple[int, int]:
+        if self._counter is not None:
+            self._delta += 1
+            if self._delta >= 1 << 31:
+                raise RuntimeError("too many random draws in one captured step")
+            return (1 << 63) | (self._delta << 32) | (torch.initial_seed() & 0xFFFFFFFF), self._counter.data_ptr()
         seed = torch.initial_seed()
         if seed != self._seed:
             self._seed, self._offset = seed, 0
@@ -84,6 +102,8 @@ def select_binary(c: torch.Tensor, big_lambda: int, random_patch_share: float, r
         top = ops.select_topk(c, kt, flags).view(B, kt)
     if kr == 0:
         return top, top, flags
+    if random_mode == "numpy" and _RANDOM._counter is not None:
+        raise RuntimeError("random_mode='numpy' draws on the host and cannot be captured in a CUDA graph; use 'device'")
     if random_mode == "numpy":
         rnd = []
         for b in range(B):                                   # host round trip, reference stream
@@ -120,6 +140,8 @@ def select_multiclass(c: torch.Tensor, big_lambda: int, random_patch_share: floa
     if ref <= 0:
         raise ValueError(f"snuffy_multiclass: empty selection (N={N}, top share={kt})")
     top = uniq[:, :ref]
+    if random_mode == "numpy" and _RANDOM._counter is not None:
+        raise RuntimeError("random_mode='numpy' draws on the host and cannot be captured in a CUDA graph; use 'device'")
     if random_mode == "numpy":
         counts_h = None
         rnd = []

@@ -195,3 +195,74 @@ def test_reference_style_training_loop_with_torch_optimizer():
         rl = ref_mil_loss(c64, bag64, label.double())
         rl.backward(); ropt.step()
         assert abs(float(loss) - float(rl)) < 2e-4, (step, float(loss), float(rl))
+
+
+def _graph_pair(case, dropout, r=None, precision=None):
+    from snuffy_b200 import dp, snuffy
+    _, c = load_golden(case)
+    if r is not None:
+        c = dict(c, r=r)
+    params, _ = snuffy_inputs(c)
+    models = [load_params(build_snuffy(snuffy, c), params) for _ in range(2)]
+    for model in models:
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = dropout
+        for layer in model.b_classifier.encoder.layers:
+            layer.self_attn.dropout.p = dropout
+            layer.return_attn = False
+        if precision:
+            set_precision(model, precision)
+    eager = dp.DataParallelTrainer(models[0], lr=1e-3, clip_grad=1.0)
+    graph = dp.DataParallelTrainer(models[1], lr=1e-3, clip_grad=1.0, cuda_graph=True)
+    return c, eager, graph
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_graph_captured_step_equals_eager_step(precision):
+    """cuda_graph=True replays the same kernels: without randomness the two trainers stay bit-identical over several steps
+    (new bag contents each step, parameters updated in place between replays)."""
+    c, eager, graph = _graph_pair("bin_rand_gelu", dropout=0.0, r=0.0, precision=precision)
+    rs = np.random.RandomState(3)
+    for step in range(4):
+        x = torch.from_numpy(rs.standard_normal((1, c["n"], c["d"])).astype(np.float32)).cuda()
+        y = torch.tensor([[float(step & 1)]], device="cuda")
+        le, lg = eager.train_step(x, y), graph.train_step(x, y)
+        assert torch.equal(le, lg), (step, float(le), float(lg))
+        assert torch.equal(eager.flat.flat_grad, graph.flat.flat_grad), step
+        assert torch.equal(eager.flat.flat_param, graph.flat.flat_param), step
+    # a second bag shape is captured on demand, then the first one replays again
+    x2 = torch.from_numpy(rs.standard_normal((1, c["n"] + 37, c["d"])).astype(np.float32)).cuda()
+    y = torch.ones(1, 1, device="cuda")
+    assert torch.equal(eager.train_step(x2, y), graph.train_step(x2, y))
+    assert torch.equal(eager.flat.flat_param, graph.flat.flat_param)
+    # evaluation between replays sees the current parameters
+    assert torch.equal(eager.predict(x2), graph.predict(x2))
+    assert torch.equal(eager.train_step(x2, y), graph.train_step(x2, y))
+
+
+def test_graph_replays_draw_fresh_masks_and_match_the_eager_draws():
+    """Dropout 0.1 + random patches: every replay reads the device step counter, so (a) two replays on identical input and
+    parameters differ, (b) forward and backward of a replay agree with each other — checked by running the eager trainer on
+    the very (seed, offset) pairs the replay resolved and comparing loss and gradients."""
+    from snuffy_b200 import engine
+    torch.manual_seed(77)                                              # < 2^32: the indirect draws use seed & 0xFFFFFFFF
+    c, eager, graph = _graph_pair("bin_rand_gelu", dropout=0.1, r=0.5, precision="bf16x3")
+    for t in (eager, graph):
+        t.opt.lr, t.opt.weight_decay = 0.0, 0.0                        # parameters stay put
+    rs = np.random.RandomState(4)
+    x = torch.from_numpy(rs.standard_normal((1, c["n"], c["d"])).astype(np.float32)).cuda()
+    y = torch.ones(1, 1, device="cuda")
+    losses, grads, counters = [], [], []
+    for _ in range(3):
+        counters.append(int(graph._rng_counter) if graph._graph is not None else None)
+        losses.append(float(graph.train_step(x, y)))
+        grads.append(graph.flat.flat_grad.clone())
+    assert len(set(losses)) == 3, losses
+    n = graph._draws_per_step
+    assert n >= 3 and int(graph._rng_counter) == counters[1] + 2 * n
+    for k in (1, 2):                                                    # replay k used offsets counter + 1 .. counter + n
+        engine._RANDOM._seed, engine._RANDOM._offset = torch.initial_seed(), counters[1] + (k - 1) * n
+        le = float(eager.train_step(x, y))
+        assert le == losses[k], (k, le, losses[k])
+        assert torch.equal(eager.flat.flat_grad, grads[k]), k
