@@ -242,15 +242,17 @@ def kernel_rooflines(model, batch, peaks, device):
 
 
 # ------------------------------------------------------------------ training step (configs[4]: DP training loop)
-def train_throughput(device, world, steps=10, warm=3):
+def train_throughput(device, world, steps=10, warm=3, graph=True):
     """Train-mode step of the reference loop (train.py:249-264: one bag per optimizer step per process) at cfg2:
-    forward (bf16x3) + fused loss + backward (fp32 SIMT) + one all-reduce of the flat gradient + AdamW.  slides/s over
-    all ranks; CUDA events, max over ranks done by the caller."""
+    forward + fused loss + backward (tensor-core products as 3-pass split bf16) + one all-reduce of the flat gradient +
+    AdamW.  graph=True: forward .. gradient packing replayed as one CUDA graph.  slides/s over all ranks; CUDA events, max
+    over ranks done by the caller."""
     from snuffy_b200 import dp
     model, _ = build_model(device)
     for layer in model.b_classifier.encoder.layers:
         layer.return_attn = False
-    trainer = dp.DataParallelTrainer(model, lr=2e-4, betas=(0.5, 0.9), weight_decay=5e-3)     # train.py:58,61,110
+    trainer = dp.DataParallelTrainer(model, lr=2e-4, betas=(0.5, 0.9), weight_decay=5e-3,     # train.py:58,61,110
+                                     cuda_graph=graph)
     c = CFG
     g = torch.Generator(device=device).manual_seed(4321 + int(os.environ.get("RANK", 0)))
     bags = [torch.randn(1, c["n"], c["d"], device=device, generator=g) for _ in range(8)]      # 8 x 20.5 MB > L2
@@ -265,7 +267,7 @@ def train_throughput(device, world, steps=10, warm=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    return ms, steps, float(loss), trainer.flat.numel * 4
+    return ms, steps, float(loss), trainer.flat.numel * 4, getattr(trainer, "_graph_kernels", None)
 
 
 # ------------------------------------------------------------------ CPU baseline (port of the reference forward)
@@ -476,17 +478,22 @@ def main():
     train = None
     if not args.skip_train:
         lc0 = lib.snuffy_launch_count()
-        t_ms, t_steps, t_loss, grad_bytes = train_throughput(device, world)
+        e_ms, e_steps, _, _, _ = train_throughput(device, world, graph=False)
+        eager_launches = int((lib.snuffy_launch_count() - lc0) / (e_steps + 3))                # 3 warm-up steps
+        t_ms, t_steps, t_loss, grad_bytes, graph_kernels = train_throughput(device, world, graph=True)
         if world > 1:
-            t = torch.tensor([t_ms], device=device)
+            t = torch.tensor([t_ms, e_ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_ms = float(t.item())
+            t_ms, e_ms = float(t[0].item()), float(t[1].item())
         train = {"value": world * t_steps / (t_ms * 1e-3), "unit": "slides/s", "ms_per_step": t_ms / t_steps,
                  "bags_per_step_per_gpu": 1, "steps": t_steps, "final_loss": t_loss,
                  "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
-                 "launches_per_step": int((lib.snuffy_launch_count() - lc0) / (t_steps + 3)),   # 3 warm-up steps
-                 "what": "train.py-style step at cfg2 (train mode, attention dropout 0.1): forward bf16x3 + fused MIL loss "
-                         "+ backward (fp32 SIMT) + one flat-gradient all-reduce + flat AdamW"}
+                 "launches_per_step": eager_launches, "kernels_in_graph": graph_kernels,
+                 "eager_ms_per_step": e_ms / e_steps,
+                 "what": "train.py-style step at cfg2 (train mode, attention dropout 0.1, one bag per optimizer step): forward + "
+                         "fused MIL loss + backward (tensor-core products as 3-pass split bf16) + gradient packing replayed as ONE "
+                         "CUDA graph (dropout drawn from a device step counter), then one flat-gradient all-reduce + flat AdamW; "
+                         "eager_ms_per_step = the same step without the graph (host-launch bound)"}
     kernels = [] if (args.skip_kernels or rank != 0) else kernel_rooflines(model, B, peaks, device)
     if world > 1:
         dist.barrier()

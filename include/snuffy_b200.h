@@ -229,7 +229,8 @@ int snuffy_mil_loss(const float* classes, const float* bag, const float* label, 
 /* Random draws under CUDA-graph replay.  Every (seed, offset) pair of this header (dropout, random patches) may be given
  * INDIRECTLY: seed bit 63 set  =>  `offset` is the address of a device uint64 step counter and the draw used is
  * (seed & 0xFFFFFFFF, *counter + ((seed >> 32) & 0x7FFFFFFF)).  snuffy_rng_advance(counter, delta) is enqueued as the
- * last node of the captured step: replays then differ, while forward and backward of one replay agree.           */
+ * last node of the captured step: replays then differ, while forward and backward of one replay agree.  Direct
+ * (seed, offset) pairs must therefore keep seed bit 63 clear.                                                     */
 int snuffy_rng_advance(uint64_t* counter, uint64_t delta, snuffy_stream_t stream);
 int64_t snuffy_sumsq_blocks(int64_t n);
 int snuffy_sumsq(const float* x, int64_t n, float* partials, float* out, snuffy_stream_t stream);

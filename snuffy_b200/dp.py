@@ -264,6 +264,7 @@ class DataParallelTrainer:
         engine._RANDOM.next()                                         # settle the eager stream's (seed, offset) first
         self._rng_counter = torch.tensor([engine._RANDOM._offset], dtype=torch.int64, device=dev)
         graph = torch.cuda.CUDAGraph()
+        launches0 = _lib.lib.snuffy_launch_count()
         engine._RANDOM.begin_indirect(self._rng_counter)
         try:
             with torch.cuda.graph(graph):
@@ -275,6 +276,7 @@ class DataParallelTrainer:
             engine._RANDOM.end_indirect()
         for m in self._cached_layers:
             m._wcache = None
+        self._graph_kernels = int(_lib.lib.snuffy_launch_count() - launches0)       # library kernels per replay
         self._graph, self._graph_key = graph, (tuple(bags.shape), tuple(labels.shape))
 
     def _replay(self, bags: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:

@@ -65,7 +65,7 @@ class _RandomStream:
             if self._delta >= 1 << 31:
                 raise RuntimeError("too many random draws in one captured step")
             return (1 << 63) | (self._delta << 32) | (torch.initial_seed() & 0xFFFFFFFF), self._counter.data_ptr()
-        seed = torch.initial_seed()
+        seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF               # bit 63 is the library's "indirect draw" flag
         if seed != self._seed:
             self._seed, self._offset = seed, 0
         self._offset += 1

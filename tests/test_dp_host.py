@@ -95,3 +95,19 @@ def test_flat_gradient_allreduce_gloo_world2():
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out[0][0] and out[1][0] and out[0][1] and out[1][1]
     assert sorted(out[0][2] + out[1][2]) == list(range(9))
+
+
+def test_random_stream_keeps_the_indirect_flag_bit_clear():
+    """torch's default generator is seeded with a random 64-bit value: bit 63 (the library's "offset is a device counter"
+    flag, include/snuffy_b200.h) must never leak into a direct draw."""
+    import torch
+    from snuffy_b200 import engine
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed((1 << 63) | 99)
+        seed, offset = engine._RANDOM.next()
+        assert seed == 99 and offset == 1
+        assert engine._RANDOM.next() == (99, 2)
+    finally:
+        torch.set_rng_state(state)
+        engine._RANDOM._seed = None
