@@ -259,6 +259,11 @@ fold_partials_kernel(const float* __restrict__ part, int splits, int64_t n4, flo
 }
 
 void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream) {
+    if (fold_wide_pays(splits, n4)) {
+        fold_wide_kernel<float4><<<(unsigned)((n4 + 15) / 16), 256, 0, stream>>>(reinterpret_cast<const float4*>(part), splits, n4,
+                                                                                 reinterpret_cast<float4*>(out));
+        return;
+    }
     const int threads = n4 >= 64 * 1024 ? 256 : 64;          // small folds: more CTAs, the loop over splits is the latency
     fold_partials_kernel<<<(unsigned)((n4 + threads - 1) / threads), threads, 0, stream>>>(part, splits, n4, out);
 }

@@ -266,7 +266,10 @@ int snuffy_colsum(const float* X, int64_t ldx, const float* w, int64_t rows, int
     dim3 grid((unsigned)chunks, (unsigned)((d + 255) / 256));
     colsum_kernel<<<grid, 256, 0, stream>>>(X, ldx, w, rows, (int)d, (int)C, rpc, partials);
     const int64_t n = C * d;
-    fold_scalar_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(partials, (int)chunks, n, out);
+    if (fold_wide_pays((int)chunks, n))
+        fold_wide_kernel<float><<<(unsigned)((n + 15) / 16), 256, 0, stream>>>(partials, (int)chunks, n, out);
+    else
+        fold_scalar_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(partials, (int)chunks, n, out);
     return check_launch("snuffy_colsum", 2);
 }
 

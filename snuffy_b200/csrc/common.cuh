@@ -97,6 +97,39 @@ __device__ __forceinline__ float drop_keep_scale(uint64_t seed, uint64_t offset,
     return u >= p ? 1.f / (1.f - p) : 0.f;
 }
 
+// ---------------------------------------------------------------- folding many small partials
+// out[i] = sum_s part[s * n + i] for FEW outputs and MANY partials (LayerNorm parameter gradients: 148 x 2d, column sums:
+// ~300 x d).  One thread per output would walk `splits` dependent-latency loads; here 16 threads share an output (each takes
+// every 16th partial, two accumulators) and the 16 sums are added in a fixed order: deterministic, ~10 loads deep.
+__device__ __forceinline__ void fold_acc(float& a, float v) { a += v; }
+__device__ __forceinline__ void fold_acc(float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_wide_kernel(const T* __restrict__ part, int splits, int64_t n, T* __restrict__ out) {
+    __shared__ T red[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t i = (int64_t)blockIdx.x * 16 + tx;
+    T a0 = T(), a1 = T();
+    if (i < n) {
+        int s = ty;
+        for (; s + 16 < splits; s += 32) {
+            fold_acc(a0, __ldcg(part + (int64_t)s * n + i));
+            fold_acc(a1, __ldcg(part + (int64_t)(s + 16) * n + i));
+        }
+        if (s < splits) fold_acc(a0, __ldcg(part + (int64_t)s * n + i));
+    }
+    fold_acc(a0, a1);
+    red[ty][tx] = a0;
+    __syncthreads();
+    if (ty == 0 && i < n) {
+        T r = red[0][tx];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) fold_acc(r, red[k][tx]);
+        out[i] = r;
+    }
+}
+inline bool fold_wide_pays(int splits, int64_t n) { return splits >= 32 && n <= 16384; }
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

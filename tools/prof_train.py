@@ -8,8 +8,10 @@ from snuffy_b200 import dp
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 steps = int(os.environ.get("STEPS", 3))
-ms, n, loss, _ = bench.train_throughput(dev, 1, steps=steps, warm=2)
+ms, n, loss, _, _ = bench.train_throughput(dev, 1, steps=steps, warm=2, graph=False)
 print("train ms/step", ms / n, "loss", loss)
+if os.environ.get("PROF_ONLY"):
+    sys.exit(0)
 model, _ = bench.build_model(dev)
 for l in model.b_classifier.encoder.layers:
     l.return_attn = False
