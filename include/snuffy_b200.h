@@ -209,13 +209,15 @@ int snuffy_scatter_add_rows(float* dx, const int64_t* idx, const float* src, int
 
 /* Attention backward on tensor cores (autograd of snuffy.py:160-168): all heads of a bag are contracted by one dense
  * tcgen05 GEMM against head-block operands Kbd[(j,k), c] = Kp[k, c] on head j's columns, 0 elsewhere.
- * snuffy_attn_seg_bwd: the row-local pieces on S_all [N, h*Ksel] (mode 0: P~, mode 1: G <- dS).                     */
+ * snuffy_attn_seg_bwd: the row-local pieces on S_all [N, h*Ksel] (mode 0: P~, mode 1: G <- dS).  planes != NULL
+ * (Ksel % 8 == 0, Ksel <= 256, (h*Ksel) % 32 == 0): the result is also written as split-bf16 A-operand planes over
+ * [ceil128(N), h*Ksel] (rc = 128) for the next product, and Pd may then be NULL in mode 0.                          */
 int snuffy_block_diag_rows(const float* src, int64_t Ksel, int64_t h, int64_t d, float* out, snuffy_stream_t stream);
 int snuffy_block_diag_extract(const float* bd, int64_t Ksel, int64_t h, int64_t d, float* out,
                               snuffy_stream_t stream);
 int snuffy_attn_seg_bwd(const float* S, const float* stats, int64_t N, int64_t h, int64_t Ksel, int64_t bag, int mode,
                         float scale, float dropout_p, uint64_t seed, uint64_t offset, float* Pd, float* G,
-                        snuffy_stream_t stream);
+                        void* planes, int64_t plane_stride, snuffy_stream_t stream);
 /* DSMIL: backward of A = softmax over the N instances (dsmil.py:86): dS = A (dA - sum_n A dA) / scale          */
 int snuffy_softmax_cols_bwd(const float* A, const float* dA, int64_t N, int64_t C, float scale, float* dS,
                             snuffy_stream_t stream);

@@ -399,6 +399,81 @@ attn_seg_bwd_kernel(const float* __restrict__ S, const float* __restrict__ stats
         g[k] = p * (mk * g[k] - delta) * inv_scale;
     }
 }
+
+// Same math, one 8-key unit per lane (Ksel % 8 == 0, Ksel <= 256): S and G are read once (the probabilities stay in registers
+// between the two passes of mode 1) and the result is ALSO written as split-bf16 A-operand planes over [rows_pad, h*Ksel] — the
+// operand of the next tensor-core product (dV = P~ dObd, dQ = dS Kbd) — instead of a separate fp32 -> planes pass.  Warps of a CTA
+// take consecutive rows of one head, so the 16-byte plane units of a CTA are contiguous.  Rows [N, rows_pad) are zero-filled.
+__global__ void __launch_bounds__(256)
+attn_seg_bwd_planes_kernel(const float* __restrict__ S, const float* __restrict__ stats, int64_t N, int64_t rows_pad, int h,
+                           int Ksel, int bag, int mode, float inv_scale, float drop_p, uint64_t seed, uint64_t offset,
+                           float* __restrict__ Pd, float* __restrict__ G, __nv_bfloat16* __restrict__ planes,
+                           int64_t plane_stride) {
+    { const DrawKey key_ = rng_resolve(seed, offset); seed = key_.seed; offset = key_.offset; }
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (j, n), n fastest
+    if (seg >= rows_pad * h) return;
+    const int j = (int)(seg / rows_pad);
+    const int64_t n = seg % rows_pad;
+    const bool active = lane * 8 < Ksel;
+    const int64_t K = (int64_t)h * Ksel;
+    float out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = 0.f;
+    if (n < N) {                                                                          // warp-uniform
+        const int64_t srow = (int64_t)j * N + n;
+        const float m = stats[srow * 2], inv = stats[srow * 2 + 1];
+        const int64_t off = n * K + (int64_t)j * Ksel + lane * 8;
+        const uint64_t base = ((uint64_t)((int64_t)bag * h + j) * (uint64_t)N + (uint64_t)n) * (uint64_t)Ksel + (uint64_t)(lane * 8);
+        float p[8], pd[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { p[e] = 0.f; pd[e] = 0.f; }
+        if (active) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(S + off)), s1 = __ldg(reinterpret_cast<const float4*>(S + off + 4));
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                p[e] = expf(sv[e] * inv_scale - m) * inv;
+                pd[e] = drop_p > 0.f ? p[e] * drop_keep_scale(seed, offset, base + e, drop_p) : p[e];
+            }
+        }
+        if (mode == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) out[e] = pd[e];
+            if (Pd && active) {
+                *reinterpret_cast<float4*>(Pd + off) = make_float4(pd[0], pd[1], pd[2], pd[3]);
+                *reinterpret_cast<float4*>(Pd + off + 4) = make_float4(pd[4], pd[5], pd[6], pd[7]);
+            }
+        } else {
+            float gv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (active) {
+                const float4 g0 = *reinterpret_cast<const float4*>(G + off), g1 = *reinterpret_cast<const float4*>(G + off + 4);
+                gv[0] = g0.x; gv[1] = g0.y; gv[2] = g0.z; gv[3] = g0.w; gv[4] = g1.x; gv[5] = g1.y; gv[6] = g1.z; gv[7] = g1.w;
+            }
+            float delta = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) delta = fmaf(pd[e], gv[e], delta);
+            delta = warp_sum(delta);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                // pd = p * mask  ->  p * (mask * g - delta) = pd * g - p * delta
+                out[e] = (pd[e] * gv[e] - p[e] * delta) * inv_scale;
+            }
+            if (active) {
+                *reinterpret_cast<float4*>(G + off) = make_float4(out[0], out[1], out[2], out[3]);
+                *reinterpret_cast<float4*>(G + off + 4) = make_float4(out[4], out[5], out[6], out[7]);
+            }
+        }
+    }
+    if (active) {
+        bf16x8 hi, lo;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(out[e], hi.v[e], lo.v[e]);
+        __nv_bfloat16* dst = planes + plane_unit_offset(n, (int64_t)j * Ksel + lane * 8, K, 128);
+        *reinterpret_cast<bf16x8*>(dst) = hi;
+        *reinterpret_cast<bf16x8*>(dst + plane_stride) = lo;
+    }
+}
 }  // namespace snuffy
 
 #pragma GCC visibility push(default)
@@ -420,9 +495,22 @@ int snuffy_block_diag_extract(const float* bd, int64_t Ksel, int64_t h, int64_t 
     return snuffy::check_launch("snuffy_block_diag_extract");
 }
 int snuffy_attn_seg_bwd(const float* S, const float* stats, int64_t N, int64_t h, int64_t Ksel, int64_t bag, int mode,
-                        float scale, float dropout_p, uint64_t seed, uint64_t offset, float* Pd, float* G, cudaStream_t stream) {
-    SNUFFY_REQUIRE(S && stats && N >= 1 && h >= 1 && Ksel >= 1 && (mode == 0 ? Pd != nullptr : G != nullptr),
-                   "snuffy_attn_seg_bwd: bad arguments");
+                        float scale, float dropout_p, uint64_t seed, uint64_t offset, float* Pd, float* G, void* planes,
+                        int64_t plane_stride, cudaStream_t stream) {
+    SNUFFY_REQUIRE(S && stats && N >= 1 && h >= 1 && Ksel >= 1 && (mode == 0 || mode == 1), "snuffy_attn_seg_bwd: bad arguments");
+    if (planes) {
+        SNUFFY_REQUIRE(Ksel % 8 == 0 && Ksel <= 256 && (h * Ksel) % 32 == 0 && (mode == 0 || G != nullptr) &&
+                           plane_stride >= snuffy::plane_elems(N, h * Ksel, 128) && (uintptr_t)S % 16 == 0 &&
+                           (uintptr_t)planes % 16 == 0 && (!G || (uintptr_t)G % 16 == 0) && (!Pd || (uintptr_t)Pd % 16 == 0),
+                       "snuffy_attn_seg_bwd: plane output needs Ksel %% 8 == 0, Ksel <= 256, (h*Ksel) %% 32 == 0 and "
+                       "16-byte aligned buffers");
+        const int64_t rows_pad = (N + 127) / 128 * 128;
+        snuffy::attn_seg_bwd_planes_kernel<<<(unsigned)((rows_pad * h + 7) / 8), 256, 0, stream>>>(
+            S, stats, N, rows_pad, (int)h, (int)Ksel, (int)bag, mode, 1.f / scale, dropout_p, seed, offset, Pd, G,
+            reinterpret_cast<__nv_bfloat16*>(planes), plane_stride);
+        return snuffy::check_launch("snuffy_attn_seg_bwd");
+    }
+    SNUFFY_REQUIRE(mode == 0 ? Pd != nullptr : G != nullptr, "snuffy_attn_seg_bwd: null output");
     snuffy::attn_seg_bwd_kernel<<<(unsigned)((N * h + 7) / 8), 256, 0, stream>>>(S, stats, N, (int)h, (int)Ksel, (int)bag, mode,
                                                                                1.f / scale, dropout_p, seed, offset, Pd, G);
     return snuffy::check_launch("snuffy_attn_seg_bwd");

@@ -618,22 +618,31 @@ def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: tor
         else:                                                                     # bag starts inside a plane tile: re-split its rows
             _, a, _ = ln_rows(qv[rows], None, None, apply_ln=False, want_planes=True)
         S = gemm_tc_awindow(a, 0, weight_planes(kbd), M=N, N=hk, K=d, passes=passes)            # raw Q_j . Kp_j^T, all heads
-        Pd = torch.empty_like(S)
-        check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 0, scale, float(drop[0]), drop[1] & _U64,
-                                      drop[2] & _U64, Pd.data_ptr(), None, _stream()), "snuffy_attn_seg_bwd")
+        fused = Ksel % 8 == 0 and Ksel <= 256 and hk % 32 == 0     # the row kernel writes the next product's operand planes itself
+        if fused:
+            Pd, pdp = None, Planes(N, hk, 128, dev)
+            check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 0, scale, float(drop[0]), drop[1] & _U64,
+                                          drop[2] & _U64, None, None, pdp.ptr, pdp.stride, _stream()), "snuffy_attn_seg_bwd")
+        else:
+            Pd = torch.empty_like(S)
+            check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 0, scale, float(drop[0]), drop[1] & _U64,
+                                          drop[2] & _U64, Pd.data_ptr(), None, None, 0, _stream()), "snuffy_attn_seg_bwd")
+            _, pdp, _ = ln_rows(Pd, None, None, apply_ln=False, want_planes=True)
         # dV = P~ . dObd            [N, d]
-        _, pdp, _ = ln_rows(Pd, None, None, apply_ln=False, want_planes=True)
         obd_t = weight_planes_t(obd)
         check(lib.snuffy_gemm_tc(pdp.ptr, pdp.stride, obd_t.ptr, obd_t.stride, N, d, hk, passes, None, 0, None, 0, None, None,
                                  dqv[rows, d:].data_ptr(), 2 * d, None, None, 0, 0.0, 0, 0, _stream()), "snuffy_gemm_tc")
         del pdp, Pd
         # G = V . dObd^T            [N, h*Ksel]
         G = gemm_tc_awindow(a, d, weight_planes(obd), M=N, N=hk, K=d, passes=passes)
+        dsp = Planes(N, hk, 128, dev) if fused else None
         check(lib.snuffy_attn_seg_bwd(S.data_ptr(), st.data_ptr(), N, h, Ksel, b, 1, scale, float(drop[0]), drop[1] & _U64,
-                                      drop[2] & _U64, None, G.data_ptr(), _stream()), "snuffy_attn_seg_bwd")   # G <- dS
+                                      drop[2] & _U64, None, G.data_ptr(), dsp.ptr if fused else None, dsp.stride if fused else 0,
+                                      _stream()), "snuffy_attn_seg_bwd")                                        # G <- dS
         del S
         # dQ = dS . Kbd             [N, d]
-        _, dsp, _ = ln_rows(G, None, None, apply_ln=False, want_planes=True)
+        if not fused:
+            _, dsp, _ = ln_rows(G, None, None, apply_ln=False, want_planes=True)
         kbd_t = weight_planes_t(kbd)
         check(lib.snuffy_gemm_tc(dsp.ptr, dsp.stride, kbd_t.ptr, kbd_t.stride, N, d, hk, passes, None, 0, None, 0, None, None,
                                  dqv[rows, :d].data_ptr(), 2 * d, None, None, 0, 0.0, 0, 0, _stream()), "snuffy_gemm_tc")

@@ -378,7 +378,8 @@ def test_tensor_core_backward_matches_fp32_backward_at_scale():
 
 
 @pytest.mark.parametrize("B,n,ks,h,d,p", [(1, 300, 40, 2, 64, 0.0), (1, 1000, 200, 8, 512, 0.0), (2, 256, 24, 4, 128, 0.0),
-                                          (1, 777, 100, 8, 768, 0.2), (3, 200, 40, 4, 128, 0.1)])
+                                          (1, 777, 100, 8, 768, 0.2), (3, 200, 40, 4, 128, 0.1), (1, 500, 256, 4, 256, 0.1),
+                                          (2, 384, 8, 4, 64, 0.3)])
 def test_sparse_attention_backward_tensor_core(ops, B, n, ks, h, d, p):
     """All heads of a bag through dense tcgen05 GEMMs against head-block operands == the head-batched SIMT backward
     (and fp64 autograd when there is no dropout)."""
