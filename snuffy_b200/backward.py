@@ -143,10 +143,12 @@ class EncoderLayerFunction(torch.autograd.Function):
         # ---- feed-forward sub-layer
         gf = ops.act_bwd(None, g, drop=t.drop_enc2)[0] if t.drop_enc2[0] > 0 else g
         d_b2 = ops.colsum(gf).view(-1)
-        da = dx_gemm(gf, w.w2, w.w2t_planes, dff)                                  # [rows, dff]
+        dh_planes = None
         if tc:
-            dh, _ = ops.act_bwd(t.h_pre, da, act, t.drop_ff, want_dh=True, want_a=False)
-            del da
+            # dh = (gf W2) * act'(h_pre) * mask in the epilogue of the product, as fp32 and as the next product's operand planes
+            _, gfp, _ = ops.ln_rows(gf, None, None, apply_ln=False, want_planes=True)
+            dh, dh_planes = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes, drop=t.drop_ff)
+            del gfp
             d_w2 = ops.gemm_tc_splitk(ops.planes_t(gf, 128), ops.planes_t(t.h_pre, rc_ff, mode=2, act=act, drop=t.drop_ff),
                                       M=d, N=dff, K=rows, passes=passes)           # gf^T . dropout(act(h_pre))
             d_w1 = ops.gemm_tc_splitk(ops.planes_t(dh, 128),
@@ -154,6 +156,7 @@ class EncoderLayerFunction(torch.autograd.Function):
                                                    row_map=t.row_map, alt=t.xs_new),
                                       M=dff, N=d, K=rows, passes=passes)           # dh^T . LN2(y)
         else:
+            da = dx_gemm(gf, w.w2, w.w2t_planes, dff)                              # [rows, dff]
             dh, a = ops.act_bwd(t.h_pre, da, act, t.drop_ff, want_dh=True, want_a=True)
             del da
             d_w2 = ops.matmul_tn(gf, a)                                            # [d, dff]
@@ -162,8 +165,11 @@ class EncoderLayerFunction(torch.autograd.Function):
             d_w1 = ops.matmul_tn(dh, u2)                                           # [dff, d]
             del u2
         d_b1 = ops.colsum(dh).view(-1)
-        du2 = dx_gemm(dh, w.w1, w.w1t_planes, d)                                   # [rows, d]
-        del dh
+        if dh_planes is not None:
+            du2, _, _ = ops.gemm_tc(dh_planes, w.w1t_planes, M=rows, N=d, K=dff, passes=passes)
+        else:
+            du2 = dx_gemm(dh, w.w1, w.w1t_planes, d)                               # [rows, d]
+        del dh, dh_planes
         dy, d_g2, d_be2 = ops.ln_rows_bwd(t.x_in, t.ln2_stats, w.g2, dy=du2, row_map=t.row_map, alt=t.xs_new, add=g)
         del du2
 

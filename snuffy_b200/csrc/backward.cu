@@ -123,6 +123,44 @@ colsum_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict_
     }
 }
 
+// Vector variant (d % 4 == 0, 16-byte aligned rows): CTA = 64 column quads x 4 row lanes, two float4 loads in flight per
+// thread (the scalar kernel keeps too few bytes in flight to reach HBM speed), row lanes folded in a fixed order.
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, int64_t rows, int d, int C,
+                  int64_t rows_per_chunk, float* __restrict__ partials) {
+    __shared__ float4 red[4][64];
+    const int q = threadIdx.x & 63, rl = threadIdx.x >> 6;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+    const int e = blockIdx.y * 256 + q * 4;
+    for (int c = 0; c < C; ++c) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (e < d) {
+            int64_t r = r0 + rl;
+            for (; r + 4 < r1; r += 8) {
+                const float w0 = w ? __ldg(w + r * C + c) : 1.f, w1 = w ? __ldg(w + (r + 4) * C + c) : 1.f;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(X + r * ldx + e));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(X + (r + 4) * ldx + e));
+                a0.x = fmaf(w0, v0.x, a0.x); a0.y = fmaf(w0, v0.y, a0.y); a0.z = fmaf(w0, v0.z, a0.z); a0.w = fmaf(w0, v0.w, a0.w);
+                a1.x = fmaf(w1, v1.x, a1.x); a1.y = fmaf(w1, v1.y, a1.y); a1.z = fmaf(w1, v1.z, a1.z); a1.w = fmaf(w1, v1.w, a1.w);
+            }
+            if (r < r1) {
+                const float w0 = w ? __ldg(w + r * C + c) : 1.f;
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(X + r * ldx + e));
+                a0.x = fmaf(w0, v0.x, a0.x); a0.y = fmaf(w0, v0.y, a0.y); a0.z = fmaf(w0, v0.z, a0.z); a0.w = fmaf(w0, v0.w, a0.w);
+            }
+        }
+        red[rl][q] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+        __syncthreads();
+        if (rl == 0 && e < d) {
+            float4 s = red[0][q];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) { s.x += red[k][q].x; s.y += red[k][q].y; s.z += red[k][q].z; s.w += red[k][q].w; }
+            *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.x * C + c) * d + e) = s;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256)
 fold_scalar_kernel(const float* __restrict__ part, int splits, int64_t n, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,7 +238,7 @@ extern "C" {
 // CTAs (= partial rows) snuffy_ln_rows_bwd uses; partials needs blocks * 2 * d floats
 int64_t snuffy_ln_rows_bwd_blocks(int64_t rows) {
     int64_t b = (rows + 7) / 8;
-    const int64_t cap = (int64_t)sm_count();               // one partial [2, d] per CTA: keep the fold short
+    const int64_t cap = 4 * (int64_t)sm_count();           // 8 warps per CTA keep too few loads in flight: several CTAs per SM
     if (b > cap) b = cap;
     return b < 1 ? 1 : b;
 }
@@ -251,7 +289,7 @@ int snuffy_act_bwd(const float* hpre, const float* da, int act, float dropout_p,
 }
 
 int64_t snuffy_colsum_chunks(int64_t rows) {
-    int64_t c = (rows + 63) / 64;
+    int64_t c = (rows + 31) / 32;
     const int64_t cap = 2 * (int64_t)sm_count();
     if (c > cap) c = cap;
     return c < 1 ? 1 : c;
@@ -264,7 +302,10 @@ int snuffy_colsum(const float* X, int64_t ldx, const float* w, int64_t rows, int
     const int64_t chunks = snuffy_colsum_chunks(rows);
     const int64_t rpc = (rows + chunks - 1) / chunks;
     dim3 grid((unsigned)chunks, (unsigned)((d + 255) / 256));
-    colsum_kernel<<<grid, 256, 0, stream>>>(X, ldx, w, rows, (int)d, (int)C, rpc, partials);
+    if (d % 4 == 0 && ldx % 4 == 0 && (uintptr_t)X % 16 == 0 && (uintptr_t)partials % 16 == 0)
+        colsum_vec_kernel<<<grid, 256, 0, stream>>>(X, ldx, w, rows, (int)d, (int)C, rpc, partials);
+    else
+        colsum_kernel<<<grid, 256, 0, stream>>>(X, ldx, w, rows, (int)d, (int)C, rpc, partials);
     const int64_t n = C * d;
     if (fold_wide_pays((int)chunks, n))
         fold_wide_kernel<float><<<(unsigned)((n + 15) / 16), 256, 0, stream>>>(partials, (int)chunks, n, out);

@@ -100,7 +100,7 @@ __device__ __forceinline__ float drop_keep_scale(uint64_t seed, uint64_t offset,
 // ---------------------------------------------------------------- folding many small partials
 // out[i] = sum_s part[s * n + i] for FEW outputs and MANY partials (LayerNorm parameter gradients: 148 x 2d, column sums:
 // ~300 x d).  One thread per output would walk `splits` dependent-latency loads; here 16 threads share an output (each takes
-// every 16th partial, two accumulators) and the 16 sums are added in a fixed order: deterministic, ~10 loads deep.
+// every 16th partial, four accumulators) and the 16 sums are added in a fixed order: deterministic, ~10 loads deep.
 __device__ __forceinline__ void fold_acc(float& a, float v) { a += v; }
 __device__ __forceinline__ void fold_acc(float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
 template <typename T>
@@ -109,16 +109,18 @@ fold_wide_kernel(const T* __restrict__ part, int splits, int64_t n, T* __restric
     __shared__ T red[16][17];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int64_t i = (int64_t)blockIdx.x * 16 + tx;
-    T a0 = T(), a1 = T();
+    T a0 = T(), a1 = T(), a2 = T(), a3 = T();
     if (i < n) {
         int s = ty;
-        for (; s + 16 < splits; s += 32) {
+        for (; s + 48 < splits; s += 64) {
             fold_acc(a0, __ldcg(part + (int64_t)s * n + i));
             fold_acc(a1, __ldcg(part + (int64_t)(s + 16) * n + i));
+            fold_acc(a2, __ldcg(part + (int64_t)(s + 32) * n + i));
+            fold_acc(a3, __ldcg(part + (int64_t)(s + 48) * n + i));
         }
-        if (s < splits) fold_acc(a0, __ldcg(part + (int64_t)s * n + i));
+        for (; s < splits; s += 16) fold_acc(a0, __ldcg(part + (int64_t)s * n + i));
     }
-    fold_acc(a0, a1);
+    fold_acc(a0, a1); fold_acc(a2, a3); fold_acc(a0, a2);
     red[ty][tx] = a0;
     __syncthreads();
     if (ty == 0 && i < n) {

@@ -46,6 +46,8 @@ struct TcGemmParams {
     float* preact;                   // optional fp32 [M, ldc] value before the activation
     __nv_bfloat16* out_planes; int64_t out_plane_stride;   // optional: result as A-operand planes, K_next = N
     float drop_p; uint64_t seed, offset;                   // dropout on the activated value (before the residual)
+    // backward of an activation fused into the dX product: v *= act'(gate[m, n]) before the dropout mask (dh = (dY W) * act'(h_pre))
+    const float* gate; int64_t ldg; int gate_act;
     // split-K (dW = dY^T X contracts over all N patches but has few output tiles): tile = (mt, nt, ks), split ks covers
     // k-blocks [ks*kb_per, ...) and writes its raw fp32 partial to out + ks*split_stride (folded by the caller)
     int ksplit, kb_per; int64_t split_stride;
@@ -53,6 +55,10 @@ struct TcGemmParams {
     // tile (e.g. Q or V inside the [rows, 2d] planes the Q|V projection wrote)
     int a_nkb, a_kb_off;
 };
+
+// out of line on purpose: 32 inlined copies of the activation switch per chunk bloat the epilogue (instruction-cache misses
+// slow the whole CTA down); ReLU, the common case, is handled inline
+__device__ __noinline__ float act_grad_call(int act, float t) { return act_grad(act, t); }
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -211,6 +217,66 @@ gemm_tc_kernel(const TcGemmParams p) {
                     }
                     __syncwarp();
                 }
+                if (p.gate) {
+                    // activation backward in the epilogue: the gate rows are read in the coalesced layout of the output stores
+                    // (4 rows x 128 B per pass), the gated values go back through the transpose buffer for the plane writer
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+                    __syncwarp();
+                    const int col = col0 + c4;
+                    const DrawKey gk = rng_resolve(p.seed, p.offset);
+                    float4 g4[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t m = m_base + i * 4 + rsub;
+                        g4[i] = (m < p.M && col < p.N) ? __ldg(reinterpret_cast<const float4*>(p.gate + m * p.ldg + col))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    // act'(gate) in place, one uniform branch per chunk (a per-element switch bloats the code: see the forward path)
+                    if (p.gate_act == ACT_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            g4[i].x = g4[i].x > 0.f ? 1.f : 0.f; g4[i].y = g4[i].y > 0.f ? 1.f : 0.f;
+                            g4[i].z = g4[i].z > 0.f ? 1.f : 0.f; g4[i].w = g4[i].w > 0.f ? 1.f : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            g4[i].x = act_grad_call(p.gate_act, g4[i].x); g4[i].y = act_grad_call(p.gate_act, g4[i].y);
+                            g4[i].z = act_grad_call(p.gate_act, g4[i].z); g4[i].w = act_grad_call(p.gate_act, g4[i].w);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + rsub;
+                        const int64_t m = m_base + row;
+                        float o[4] = {stg[row * 33 + c4], stg[row * 33 + c4 + 1], stg[row * 33 + c4 + 2], stg[row * 33 + c4 + 3]};
+                        const float gg[4] = {g4[i].x, g4[i].y, g4[i].z, g4[i].w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            o[jj] *= gg[jj];
+                            if (p.drop_p > 0.f) o[jj] *= drop_keep_scale(gk.seed, gk.offset, (uint64_t)(m * p.N + col + jj), p.drop_p);
+                        }
+                        const bool live = m < p.M && col < p.N;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) stg[row * 33 + c4 + jj] = live ? o[jj] : 0.f;
+                        if (outp && live) *reinterpret_cast<float4*>(outp + m * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                    __syncwarp();
+                    if (p.out_planes && col0 < kpad_next) {
+                        __nv_bfloat16* dst = p.out_planes + (((int64_t)mt * nkb_next + (col0 >> 5)) * 4) * (TC_BM * 8) + rr_own * 8;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            bf16x8 h, l;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) split_bf16(stg[lane * 33 + u * 8 + j], h.v[j], l.v[j]);
+                            *reinterpret_cast<bf16x8*>(dst + u * (TC_BM * 8)) = h;
+                            *reinterpret_cast<bf16x8*>(dst + p.out_plane_stride + u * (TC_BM * 8)) = l;
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 switch (p.act) {          // hoisted: one uniform branch per chunk, straight-line code per activation
                     case ACT_RELU:
 #pragma unroll
@@ -327,11 +393,13 @@ static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const
     return check_launch(who);
 }
 
-int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
-                   int64_t M, int64_t N, int64_t K, int passes, const float* bias, int act, const float* resid,
-                   int64_t ldr, const int32_t* row_map, const float* resid_alt, float* out, int64_t ldc,
-                   float* preact, void* out_planes, int64_t out_plane_stride, float dropout_p, uint64_t seed,
-                   uint64_t offset, cudaStream_t stream) {
+static int gemm_tc_full(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                        int64_t M, int64_t N, int64_t K, int passes, const float* bias, int act, const float* resid,
+                        int64_t ldr, const int32_t* row_map, const float* resid_alt, float* out, int64_t ldc,
+                        float* preact, void* out_planes, int64_t out_plane_stride, float dropout_p, uint64_t seed,
+                        uint64_t offset, const float* gate, int64_t ldg, int gate_act, cudaStream_t stream) {
+    SNUFFY_REQUIRE(!gate || (ldg % 4 == 0 && ldg >= N && (uintptr_t)gate % 16 == 0),
+                   "snuffy_gemm_tc_actgrad: the gate matrix must be 16-byte aligned with ldg %% 4 == 0, ldg >= N");
     SNUFFY_REQUIRE(A_planes && B_planes, "snuffy_gemm_tc: null operand");
     SNUFFY_REQUIRE(out || out_planes || preact, "snuffy_gemm_tc: no output requested");
     SNUFFY_REQUIRE(M >= 1 && N >= 1 && K >= 1, "snuffy_gemm_tc: empty problem");
@@ -358,7 +426,29 @@ int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_p
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
     p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
     p.a_nkb = p.num_kb; p.a_kb_off = 0;
-    return launch_gemm_tc(p, N, stream, "snuffy_gemm_tc");
+    p.gate = gate; p.ldg = ldg; p.gate_act = gate_act;
+    return launch_gemm_tc(p, N, stream, gate ? "snuffy_gemm_tc_actgrad" : "snuffy_gemm_tc");
+}
+
+int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                   int64_t M, int64_t N, int64_t K, int passes, const float* bias, int act, const float* resid,
+                   int64_t ldr, const int32_t* row_map, const float* resid_alt, float* out, int64_t ldc,
+                   float* preact, void* out_planes, int64_t out_plane_stride, float dropout_p, uint64_t seed,
+                   uint64_t offset, cudaStream_t stream) {
+    return gemm_tc_full(A_planes, a_plane_stride, B_planes, b_plane_stride, M, N, K, passes, bias, act, resid, ldr, row_map,
+                        resid_alt, out, ldc, preact, out_planes, out_plane_stride, dropout_p, seed, offset, nullptr, 0, 0, stream);
+}
+
+// dX product with the activation backward in its epilogue:  result = (A . B^T) * act'(gate[m, n]) * dropout_mask(m*N + n),
+// as fp32 (out) and / or as A-operand planes for the next product.  For dh = (dY W2) * act'(h_pre) (autograd of snuffy.py:225).
+int snuffy_gemm_tc_actgrad(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                           int64_t M, int64_t N, int64_t K, int passes, const float* gate, int64_t ldg, int gate_act,
+                           float dropout_p, uint64_t seed, uint64_t offset, float* out, int64_t ldc, void* out_planes,
+                           int64_t out_plane_stride, cudaStream_t stream) {
+    SNUFFY_REQUIRE(gate, "snuffy_gemm_tc_actgrad: null gate");
+    return gemm_tc_full(A_planes, a_plane_stride, B_planes, b_plane_stride, M, N, K, passes, nullptr, ACT_NONE, nullptr, 0, nullptr,
+                        nullptr, out, ldc, nullptr, out_planes, out_plane_stride, dropout_p, seed, offset, gate, ldg, gate_act,
+                        stream);
 }
 
 // out[M, N] (fp32, ldc) = A_window . B^T where A is the K window [a_col0, a_col0 + K) of a wider A-plane set over

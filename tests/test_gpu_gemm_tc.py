@@ -134,3 +134,23 @@ def test_weight_planes_t_dx_product(ops):
     out, _, _ = ops.gemm_tc(ap, ops.weight_planes_t(w), M=700, N=96, K=256, passes=3)
     ref = dy.double() @ w.double()
     assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("act", ["relu", "gelu", "leakyrelu", "selu"])
+@pytest.mark.parametrize("M,N,K,p", [(1000, 2048, 512, 0.0), (333, 96, 64, 0.25), (128, 256, 32, 0.1)])
+def test_gemm_tc_actgrad_epilogue(ops, act, M, N, K, p):
+    """(A B^T) * act'(gate) * dropout mask in the epilogue == product, then the stand-alone activation backward kernel; the
+    operand planes it emits decode to the same matrix."""
+    a, b, ad, bd, ap, bp = _operands(ops, M, N, K, M + N + K + 1)
+    rs = np.random.RandomState(N)
+    gate = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).cuda()
+    drop = (p, 11, 3)
+    out, planes = ops.gemm_tc_actgrad(ap, bp, gate, act, M=M, N=N, K=K, drop=drop)
+    prod, _, _ = ops.gemm_tc(ap, bp, M=M, N=N, K=K)
+    want, _ = ops.act_bwd(gate, prod, act, drop, want_dh=True, want_a=False)
+    assert torch.allclose(out, want, rtol=1e-6, atol=1e-7), (out - want).abs().max()
+    hi, lo = decode_planes(planes, M, N)
+    assert np.allclose((hi + lo)[:, :N], out.cpu().numpy().astype(np.float64), rtol=2e-5, atol=1e-6)
+    if p > 0:
+        zero = (out == 0).float().mean().item()
+        assert abs(zero - p) < 0.05 or act == "relu"
