@@ -457,11 +457,21 @@ static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, in
     if (pl.nkc == 0) return pl;
     const int64_t tiles = (N + AT_TILE - 1) / AT_TILE + 1;         // a bag may straddle one extra row tile
     const int64_t per = B * h * pl.nkc;
-    const int64_t target = (per >= 32 ? 4 : 2) * (int64_t)sm_count();
-    int64_t splits = (target + per - 1) / per;
-    if (splits > tiles) splits = tiles;
-    if (splits < 1) splits = 1;
-    pl.tiles_per_split = (int)((tiles + splits - 1) / splits);
+    // Row tiles per work item: the persistent CTAs take items round-robin, so the launch lasts ceil(items / SMs) rounds of one
+    // item each.  Pick the split that minimises rounds x (tiles per item + per-item overhead: key split, O read-out) plus the
+    // cost of folding `splits` partial outputs, all in units of one tile (~5.5 us at 208 keys x 64) — e.g. 16 slides x 8 heads x
+    // 80 tiles: 10 tiles per item = 7 rounds of 10.6 instead of 5 rounds of 16.6.
+    const double fold_per_split = (double)B * (double)Ksel * (double)d * 4.0 / 4.0e6 / 5.5;
+    double best = 1e30;
+    int best_t = (int)tiles;
+    for (int64_t t = 1; t <= tiles; ++t) {
+        const int64_t s = (tiles + t - 1) / t;
+        if (s > 64) continue;
+        const int64_t rounds = (per * s + sm_count() - 1) / sm_count();
+        const double cost = (double)rounds * ((double)t + 0.6) + fold_per_split * (double)s;
+        if (cost < best - 1e-9) { best = cost; best_t = (int)t; }
+    }
+    pl.tiles_per_split = best_t;
     pl.splits = (int)((tiles + pl.tiles_per_split - 1) / pl.tiles_per_split);
     const int64_t items = per * pl.splits;
     pl.grid = (int)(items < sm_count() ? items : sm_count());
