@@ -48,6 +48,9 @@ struct TcGemmParams {
     float drop_p; uint64_t seed, offset;                   // dropout on the activated value (before the residual)
     // backward of an activation fused into the dX product: v *= act'(gate[m, n]) before the dropout mask (dh = (dY W) * act'(h_pre))
     const float* gate; int64_t ldg; int gate_act;
+    // block-diagonal B operand (attention backward against head-block matrices): B[n, k] is non-zero only where
+    // n / group_n == k / group_k, so a column tile contracts only over the k-blocks of the groups it touches (group_n == 0: dense)
+    int group_n, group_k;
     // split-K (dW = dY^T X contracts over all N patches but has few output tiles): tile = (mt, nt, ks), split ks covers
     // k-blocks [ks*kb_per, ...) and writes its raw fp32 partial to out + ks*split_stride (folded by the caller)
     int ksplit, kb_per; int64_t split_stride;
@@ -59,6 +62,20 @@ struct TcGemmParams {
 // out of line on purpose: 32 inlined copies of the activation switch per chunk bloat the epilogue (instruction-cache misses
 // slow the whole CTA down); ReLU, the common case, is handled inline
 __device__ __noinline__ float act_grad_call(int act, float t) { return act_grad(act, t); }
+
+// k-blocks [kb0, kb1) a tile contracts over: its K split, narrowed to the non-zero window of a block-diagonal B operand (any
+// superset of the window is exact: the extra blocks only multiply zeros)
+template <int BN>
+__device__ __forceinline__ void tile_kb_range(const TcGemmParams& p, int ksp, int nt, int& kb0, int& kb1) {
+    kb0 = ksp * p.kb_per;
+    kb1 = min(p.num_kb, kb0 + p.kb_per);
+    if (p.group_n > 0) {
+        const int c_lo = nt * BN, c_hi = min(p.N, c_lo + BN) - 1;
+        const int k_lo = (c_lo / p.group_n) * p.group_k, k_hi = (c_hi / p.group_n + 1) * p.group_k;
+        kb0 = max(kb0, k_lo / PLANE_KB);
+        kb1 = min(kb1, (k_hi + PLANE_KB - 1) / PLANE_KB);
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -100,7 +117,8 @@ gemm_tc_kernel(const TcGemmParams p) {
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
             const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
-            const int kb0 = ksp * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+            int kb0, kb1;
+            tile_kb_range<BN>(p, ksp, nt, kb0, kb1);
             const __nv_bfloat16* a_src = p.A + ((int64_t)mt * p.a_nkb + p.a_kb_off) * a_chunk;
             const __nv_bfloat16* b_src = p.B + (int64_t)nt * p.num_kb * b_chunk;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -130,7 +148,8 @@ gemm_tc_kernel(const TcGemmParams p) {
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int ksp = tile % p.ksplit;
-            const int kb0 = ksp * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+            int kb0, kb1;
+            tile_kb_range<BN>(p, ksp, (tile / p.ksplit) % p.n_tiles, kb0, kb1);
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -379,8 +398,8 @@ int64_t snuffy_plane_elems(int64_t rows, int64_t K, int rc) { return plane_elems
 // C = epilogue(A . B^T) with A, B given as split-bf16 planes (A tiled with 128 rows per chunk, B with
 // snuffy_gemm_tc_block_n(N)).  Outputs (each optional, at least one): fp32 `out` [M, ldc] (+ residual, optionally
 // redirected through row_map), fp32 `preact`, and `out_planes` = the activated result as A planes with K_next = N.
-static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const char* who) {
-    const int bn = snuffy_gemm_tc_block_n(N);
+static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const char* who, int force_bn = 0) {
+    const int bn = force_bn ? force_bn : snuffy_gemm_tc_block_n(N);
     const int total = p.m_tiles * p.n_tiles * p.ksplit;
     const int grid = total < sm_count() ? total : sm_count();
     if (bn == 256) {
@@ -477,6 +496,37 @@ int snuffy_gemm_tc_awindow(const void* A_planes, int64_t a_plane_stride, int64_t
     p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
     p.a_nkb = (int)plane_kblocks(a_cols_total); p.a_kb_off = (int)(a_col0 / 32);
     return launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_awindow");
+}
+
+// out[M, N] = A_window . B^T against a BLOCK-DIAGONAL B: B[n, k] != 0 only where n / group_n == k / group_k (the head-block
+// operands Kbd / dObd of the attention backward and their transposes).  Each column tile contracts only over the k-blocks of the
+// groups it touches.  b_rc = rows per chunk of the B planes (128 or 256) = the column tile width used.
+int snuffy_gemm_tc_blockdiag(const void* A_planes, int64_t a_plane_stride, int64_t a_cols_total, int64_t a_col0,
+                             const void* B_planes, int64_t b_plane_stride, int b_rc, int64_t M, int64_t N, int64_t K,
+                             int passes, int64_t group_n, int64_t group_k, float* out, int64_t ldc, cudaStream_t stream) {
+    SNUFFY_REQUIRE(A_planes && B_planes && out, "snuffy_gemm_tc_blockdiag: null pointer");
+    SNUFFY_REQUIRE(M >= 1 && N >= 1 && K >= 1 && N % 4 == 0 && ldc % 4 == 0 && (uintptr_t)out % 16 == 0,
+                   "snuffy_gemm_tc_blockdiag: bad problem");
+    SNUFFY_REQUIRE(passes == 1 || passes == 3, "snuffy_gemm_tc_blockdiag: passes must be 1 or 3");
+    SNUFFY_REQUIRE(b_rc == 128 || b_rc == 256, "snuffy_gemm_tc_blockdiag: b_rc must be 128 or 256");
+    SNUFFY_REQUIRE(group_n >= 1 && group_k >= 1 && (N + group_n - 1) / group_n == (K + group_k - 1) / group_k,
+                   "snuffy_gemm_tc_blockdiag: N / group_n and K / group_k must give the same number of groups");
+    SNUFFY_REQUIRE(a_col0 % 32 == 0 && (a_col0 == 0 || K % 32 == 0) && a_col0 + K <= plane_kblocks(a_cols_total) * 32,
+                   "snuffy_gemm_tc_blockdiag: the K window must be 32-aligned inside the planes");
+    TcGemmParams p{};
+    p.A = reinterpret_cast<const __nv_bfloat16*>(A_planes); p.a_plane_stride = a_plane_stride;
+    p.B = reinterpret_cast<const __nv_bfloat16*>(B_planes); p.b_plane_stride = b_plane_stride;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    p.n_tiles = (int)((N + b_rc - 1) / b_rc);
+    p.num_kb = (int)plane_kblocks(K);
+    p.npairs = passes;
+    p.act = ACT_NONE;
+    p.out = out; p.ldc = ldc;
+    p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
+    p.a_nkb = (int)plane_kblocks(a_cols_total); p.a_kb_off = (int)(a_col0 / 32);
+    p.group_n = (int)group_n; p.group_k = (int)group_k;
+    return launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_blockdiag", b_rc);
 }
 
 // Split-K form for the weight gradients dW[M, N] = A . B^T with a long contraction (K = all patches of the step) and few

@@ -154,3 +154,28 @@ def test_gemm_tc_actgrad_epilogue(ops, act, M, N, K, p):
     if p > 0:
         zero = (out == 0).float().mean().item()
         assert abs(zero - p) < 0.05 or act == "relu"
+
+
+@pytest.mark.parametrize("M,h,gn,gk", [(1000, 8, 200, 64), (300, 4, 24, 32), (257, 2, 40, 32), (500, 8, 64, 200), (384, 4, 16, 8),
+                                       (130, 1, 96, 64)])
+def test_gemm_tc_blockdiag_skips_only_zero_blocks(ops, M, h, gn, gk):
+    """Against a block-diagonal B the K-windowed product equals the dense one (the skipped k-blocks only meet zeros),
+    for windows that are and are not aligned to the 32-wide k-blocks, with 128- and 256-row B chunks."""
+    N, K = h * gn, h * gk
+    if N % 4 or K % 8:
+        pytest.skip("shape not served")
+    rs = np.random.RandomState(M + N + K)
+    a = rs.standard_normal((M, K)).astype(np.float32)
+    b = np.zeros((N, K), dtype=np.float32)
+    for j in range(h):
+        b[j * gn:(j + 1) * gn, j * gk:(j + 1) * gk] = rs.standard_normal((gn, gk)).astype(np.float32) / np.sqrt(gk)
+    ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    _, ap, _ = ops.ln_rows(ad, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    tol = 3e-5 * max(1.0, np.abs(ref).max())
+    for bp in (ops.weight_planes(bd), ops.planes_t(bd.t().contiguous(), 128)):
+        out = ops.gemm_tc_blockdiag(ap, 0, bp, M=M, N=N, K=K, group_n=gn, group_k=gk)
+        assert np.abs(out.cpu().numpy() - ref).max() < tol
+    wide = torch.empty(M, N + 8, device="cuda")                      # strided output, like dQ | dV
+    ops.gemm_tc_blockdiag(ap, 0, ops.weight_planes(bd), M=M, N=N, K=K, group_n=gn, group_k=gk, out=wide, ldc=N + 8)
+    assert np.abs(wide[:, :N].cpu().numpy() - ref).max() < tol
