@@ -137,6 +137,14 @@ int snuffy_gemm_tc_blockdiag(const void* A_planes, int64_t a_plane_stride, int64
                              const void* B_planes, int64_t b_plane_stride, int b_rc, int64_t M, int64_t N,
                              int64_t K, int passes, int64_t group_n, int64_t group_k, float* out, int64_t ldc,
                              snuffy_stream_t stream);
+/* Split-K product of which only the diagonal blocks (row / diag_m == col / diag_n) are wanted (dKp = diagonal blocks of
+ * dS^T Q): tiles that meet no such block are skipped, their part of `out` is unspecified.  ksplit <= 0: automatic
+ * (snuffy_gemm_tc_diag_ksplit); workspace: snuffy_gemm_tc_splitk_workspace(M, N, ksplit) bytes.                     */
+int64_t snuffy_gemm_tc_diag_ksplit(int64_t M, int64_t N, int64_t K, int b_rc, int64_t diag_m, int64_t diag_n);
+int snuffy_gemm_tc_splitk_blockdiag(const void* A_planes, int64_t a_plane_stride, const void* B_planes,
+                                    int64_t b_plane_stride, int b_rc, int64_t M, int64_t N, int64_t K, int passes,
+                                    int64_t ksplit, int64_t diag_m, int64_t diag_n, float* out, void* workspace,
+                                    int64_t workspace_bytes, snuffy_stream_t stream);
 int snuffy_gemm_tc_awindow(const void* A_planes, int64_t a_plane_stride, int64_t a_cols_total, int64_t a_col0,
                            const void* B_planes, int64_t b_plane_stride, int64_t M, int64_t N, int64_t K,
                            int passes, float* out, int64_t ldc, snuffy_stream_t stream);

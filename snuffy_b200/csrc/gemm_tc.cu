@@ -51,6 +51,9 @@ struct TcGemmParams {
     // block-diagonal B operand (attention backward against head-block matrices): B[n, k] is non-zero only where
     // n / group_n == k / group_k, so a column tile contracts only over the k-blocks of the groups it touches (group_n == 0: dense)
     int group_n, group_k;
+    // block-diagonal OUTPUT (dKp = diagonal blocks of dS^T Q): only tiles that meet a block with row / diag_m == col / diag_n are
+    // computed, the others are skipped by all three roles (diag_m == 0: every tile)
+    int diag_m, diag_n;
     // split-K (dW = dY^T X contracts over all N patches but has few output tiles): tile = (mt, nt, ks), split ks covers
     // k-blocks [ks*kb_per, ...) and writes its raw fp32 partial to out + ks*split_stride (folded by the caller)
     int ksplit, kb_per; int64_t split_stride;
@@ -75,6 +78,12 @@ __device__ __forceinline__ void tile_kb_range(const TcGemmParams& p, int ksp, in
         kb0 = max(kb0, k_lo / PLANE_KB);
         kb1 = min(kb1, (k_hi + PLANE_KB - 1) / PLANE_KB);
     }
+}
+
+__host__ __device__ __forceinline__ bool tile_live(int M, int N, int bn, int diag_m, int diag_n, int mt, int nt) {
+    if (diag_m <= 0) return true;
+    const int r_lo = mt * TC_BM, r_hi = min(M, r_lo + TC_BM) - 1, c_lo = nt * bn, c_hi = min(N, c_lo + bn) - 1;
+    return r_lo / diag_m <= c_hi / diag_n && c_lo / diag_n <= r_hi / diag_m;
 }
 
 template <int BN>
@@ -117,6 +126,7 @@ gemm_tc_kernel(const TcGemmParams p) {
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
             const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
+            if (!tile_live(p.M, p.N, BN, p.diag_m, p.diag_n, mt, nt)) continue;
             int kb0, kb1;
             tile_kb_range<BN>(p, ksp, nt, kb0, kb1);
             const __nv_bfloat16* a_src = p.A + ((int64_t)mt * p.a_nkb + p.a_kb_off) * a_chunk;
@@ -147,9 +157,10 @@ gemm_tc_kernel(const TcGemmParams p) {
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int ksp = tile % p.ksplit;
+            const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
+            if (!tile_live(p.M, p.N, BN, p.diag_m, p.diag_n, t2 / p.n_tiles, t2 % p.n_tiles)) continue;
             int kb0, kb1;
-            tile_kb_range<BN>(p, ksp, (tile / p.ksplit) % p.n_tiles, kb0, kb1);
+            tile_kb_range<BN>(p, ksp, t2 % p.n_tiles, kb0, kb1);
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -195,6 +206,7 @@ gemm_tc_kernel(const TcGemmParams p) {
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
             const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
+            if (!tile_live(p.M, p.N, BN, p.diag_m, p.diag_n, mt, nt)) continue;
             float* const outp = p.out ? p.out + (int64_t)ksp * p.split_stride : nullptr;
             const int rr_own = quad * 32 + lane;                   // row of the tile this thread owns in TMEM
             const int64_t m_own = (int64_t)mt * TC_BM + rr_own;
@@ -543,13 +555,31 @@ int64_t snuffy_gemm_tc_auto_ksplit(int64_t M, int64_t N, int64_t K) {
 }
 int64_t snuffy_gemm_tc_splitk_workspace(int64_t M, int64_t N, int64_t ksplit) { return ksplit > 1 ? M * N * ksplit * 4 : 0; }
 
-int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
-                          int64_t M, int64_t N, int64_t K, int passes, int64_t ksplit, float* out, void* workspace,
-                          int64_t workspace_bytes, cudaStream_t stream) {
+// K split for the block-diagonal-output form: fills the machine with the LIVE tiles only.
+int64_t snuffy_gemm_tc_diag_ksplit(int64_t M, int64_t N, int64_t K, int b_rc, int64_t diag_m, int64_t diag_n) {
+    if (b_rc != 128 && b_rc != 256) return 1;
+    const int m_tiles = (int)((M + TC_BM - 1) / TC_BM), n_tiles = (int)((N + b_rc - 1) / b_rc);
+    int64_t live = 0;
+    for (int mt = 0; mt < m_tiles; ++mt)
+        for (int nt = 0; nt < n_tiles; ++nt) live += tile_live((int)M, (int)N, b_rc, (int)diag_m, (int)diag_n, mt, nt) ? 1 : 0;
+    if (live < 1) live = 1;
+    const int64_t num_kb = plane_kblocks(K);
+    int64_t ks = (2 * (int64_t)sm_count() + live - 1) / live;
+    if (ks > num_kb / 8) ks = num_kb / 8;
+    if (ks < 1) ks = 1;
+    const int64_t per = (num_kb + ks - 1) / ks;
+    return (num_kb + per - 1) / per;
+}
+
+static int gemm_tc_splitk_full(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                               int b_rc, int64_t M, int64_t N, int64_t K, int passes, int64_t ksplit, int64_t diag_m,
+                               int64_t diag_n, float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
     SNUFFY_REQUIRE(A_planes && B_planes && out, "snuffy_gemm_tc_splitk: null pointer");
     SNUFFY_REQUIRE(M >= 1 && N >= 1 && K >= 1 && N % 4 == 0 && (uintptr_t)out % 16 == 0, "snuffy_gemm_tc_splitk: bad problem");
     SNUFFY_REQUIRE(passes == 1 || passes == 3, "snuffy_gemm_tc_splitk: passes must be 1 or 3");
-    if (ksplit <= 0) ksplit = snuffy_gemm_tc_auto_ksplit(M, N, K);
+    SNUFFY_REQUIRE((diag_m == 0 && diag_n == 0) || (diag_m >= 1 && diag_n >= 1 && (b_rc == 128 || b_rc == 256)),
+                   "snuffy_gemm_tc_splitk_blockdiag: bad block sizes");
+    if (ksplit <= 0) ksplit = diag_m ? snuffy_gemm_tc_diag_ksplit(M, N, K, b_rc, diag_m, diag_n) : snuffy_gemm_tc_auto_ksplit(M, N, K);
     const int64_t num_kb = plane_kblocks(K);
     const int64_t per = (num_kb + ksplit - 1) / ksplit;
     ksplit = (num_kb + per - 1) / per;
@@ -559,7 +589,7 @@ int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const vo
     p.A = reinterpret_cast<const __nv_bfloat16*>(A_planes); p.a_plane_stride = a_plane_stride;
     p.B = reinterpret_cast<const __nv_bfloat16*>(B_planes); p.b_plane_stride = b_plane_stride;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
-    const int bn = snuffy_gemm_tc_block_n(N);
+    const int bn = diag_m ? b_rc : snuffy_gemm_tc_block_n(N);
     p.m_tiles = (int)((M + TC_BM - 1) / TC_BM);
     p.n_tiles = (int)((N + bn - 1) / bn);
     p.num_kb = (int)num_kb;
@@ -568,12 +598,31 @@ int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const vo
     p.out = ksplit > 1 ? reinterpret_cast<float*>(workspace) : out; p.ldc = N;
     p.ksplit = (int)ksplit; p.kb_per = (int)per; p.split_stride = M * N;
     p.a_nkb = p.num_kb; p.a_kb_off = 0;
-    if (int rc = launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_splitk")) return rc;
+    p.diag_m = (int)diag_m; p.diag_n = (int)diag_n;
+    if (int rc = launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_splitk", diag_m ? bn : 0)) return rc;
     if (ksplit > 1) {
         launch_fold_partials(reinterpret_cast<const float*>(workspace), (int)ksplit, M * N / 4, out, stream);
         return check_launch("snuffy_gemm_tc_splitk");
     }
     return 0;
+}
+
+int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                          int64_t M, int64_t N, int64_t K, int passes, int64_t ksplit, float* out, void* workspace,
+                          int64_t workspace_bytes, cudaStream_t stream) {
+    return gemm_tc_splitk_full(A_planes, a_plane_stride, B_planes, b_plane_stride, 0, M, N, K, passes, ksplit, 0, 0, out, workspace,
+                               workspace_bytes, stream);
+}
+
+// Split-K product of which only the diagonal blocks (row / diag_m == col / diag_n) are wanted: tiles that meet no such block are
+// skipped and their part of `out` is UNSPECIFIED.  b_rc = rows per chunk of the B planes = column tile width (128 or 256).
+// dKp of the attention backward = the diagonal blocks of dS^T Q (M = h*Ksel, N = d, diag_m = Ksel, diag_n = d / h).
+int snuffy_gemm_tc_splitk_blockdiag(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                                    int b_rc, int64_t M, int64_t N, int64_t K, int passes, int64_t ksplit, int64_t diag_m,
+                                    int64_t diag_n, float* out, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+    SNUFFY_REQUIRE(diag_m >= 1 && diag_n >= 1, "snuffy_gemm_tc_splitk_blockdiag: block sizes must be positive");
+    return gemm_tc_splitk_full(A_planes, a_plane_stride, B_planes, b_plane_stride, b_rc, M, N, K, passes, ksplit, diag_m, diag_n, out,
+                               workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

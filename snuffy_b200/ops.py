@@ -606,6 +606,22 @@ def gemm_tc_blockdiag(a: Planes, a_col0: int, b: Planes, *, M: int, N: int, K: i
     return out
 
 
+_diag_ksplit = functools.lru_cache(maxsize=None)(lambda M, N, K, rc, dm, dn: lib.snuffy_gemm_tc_diag_ksplit(M, N, K, rc, dm, dn))
+
+
+def gemm_tc_splitk_blockdiag(a: Planes, b: Planes, *, M: int, N: int, K: int, diag_m: int, diag_n: int, passes: int = 3) -> torch.Tensor:
+    """Split-K out [M, N] = A . B^T of which only the blocks with row // diag_m == col // diag_n are computed (the rest of the
+    returned tensor is unspecified)."""
+    dev = a.buf.device
+    out = torch.empty(M, N, dtype=torch.float32, device=dev)
+    ks = _diag_ksplit(M, N, K, b.rc, diag_m, diag_n)
+    ws_bytes = lib.snuffy_gemm_tc_splitk_workspace(M, N, ks)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    check(lib.snuffy_gemm_tc_splitk_blockdiag(a.ptr, a.stride, b.ptr, b.stride, b.rc, M, N, K, passes, ks, diag_m, diag_n,
+                                              out.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "snuffy_gemm_tc_splitk_blockdiag")
+    return out
+
+
 def block_diag_rows(src: torch.Tensor, h: int) -> torch.Tensor:
     """src [Ksel, d] -> [h*Ksel, d]: row (j, k) = src[k] on head j's columns, zeros elsewhere."""
     src = _f32(src, "src")
@@ -673,7 +689,8 @@ def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: tor
                           out=dqv[rows, :d], ldc=2 * d)
         del dsp
         # dKbd = dS^T . Q           [h*Ksel, d], contraction over the N patches -> split-K; its diagonal blocks are dKp
-        dkbd = gemm_tc_splitk(planes_t(G, 128), planes_t(qv[rows, :d], rc_d), M=hk, N=d, K=N, passes=passes)
+        dkbd = gemm_tc_splitk_blockdiag(planes_t(G, 128), planes_t(qv[rows, :d], 128), M=hk, N=d, K=N, diag_m=Ksel, diag_n=dk,
+                                        passes=passes)
         check(lib.snuffy_block_diag_extract(dkbd.data_ptr(), Ksel, h, d, dkp[b * Ksel:(b + 1) * Ksel].data_ptr(), _stream()),
               "snuffy_block_diag_extract")
     return dqv[:, :d], dqv[:, d:], dkp, dqv

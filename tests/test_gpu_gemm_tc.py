@@ -179,3 +179,19 @@ def test_gemm_tc_blockdiag_skips_only_zero_blocks(ops, M, h, gn, gk):
     wide = torch.empty(M, N + 8, device="cuda")                      # strided output, like dQ | dV
     ops.gemm_tc_blockdiag(ap, 0, ops.weight_planes(bd), M=M, N=N, K=K, group_n=gn, group_k=gk, out=wide, ldc=N + 8)
     assert np.abs(wide[:, :N].cpu().numpy() - ref).max() < tol
+
+
+@pytest.mark.parametrize("h,dm,dn,K", [(8, 200, 64, 10000), (4, 24, 32, 700), (2, 40, 32, 257), (8, 100, 96, 1500), (1, 64, 64, 300)])
+def test_gemm_tc_splitk_blockdiag_computes_every_diagonal_block(ops, h, dm, dn, K):
+    """Tile skipping of the block-diagonal-output split-K product: every block with row // dm == col // dn is exact."""
+    M, N = h * dm, h * dn
+    rs = np.random.RandomState(M + N + K)
+    a = rs.standard_normal((K, M)).astype(np.float32)          # contraction runs over rows, like dS^T Q
+    b = rs.standard_normal((K, N)).astype(np.float32)
+    ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = ops.gemm_tc_splitk_blockdiag(ops.planes_t(ad, 128), ops.planes_t(bd, 128), M=M, N=N, K=K, diag_m=dm, diag_n=dn)
+    ref = a.astype(np.float64).T @ b.astype(np.float64)
+    got = out.cpu().numpy()
+    for j in range(h):
+        blk = (slice(j * dm, (j + 1) * dm), slice(j * dn, (j + 1) * dn))
+        assert np.abs(got[blk] - ref[blk]).max() < 3e-5 * max(1.0, np.abs(ref[blk]).max()), j
