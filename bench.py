@@ -165,10 +165,11 @@ def kernel_rooflines(model, batch, peaks, device):
     t = cuda_time(ffn_up, 10)
     flops = 2.0 * rows * dff * d
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch (ncu --set full): 168.2 MB read + 597.0 MB written at
-    # batch 8 (profiles/r01c_gemm_tc_ncu_full.csv), 332 MB + 1252 MB at batch 16 (profiles/r01g_...); scaled to the batch in use
+    # batch 8 (profiles/r01c_gemm_tc_ncu_full.csv), 332 MB + 1255 MB at batch 16 (profiles/r01k_gemm_tc_ncu_full.csv); the figure
+    # reported is the batch-16 capture scaled to the batch in use
     res.append(dict(kernel="gemm_tc<256> FFN-up (LN2(y) W1^T, relu, planes out)", bound="tensor",
                     achieved=flops / t / 1e12, peak=peaks["tf_burst"], unit="TFLOP/s", frac=flops / t / 1e12 / peaks["tf_burst"],
-                    traffic=765.2e6 * batch / 8, launch_ms=t * 1e3, passes=3, issued_tflops=3 * flops / t / 1e12,
+                    traffic=1587.0e6 * batch / 16, launch_ms=t * 1e3, passes=3, issued_tflops=3 * flops / t / 1e12,
                     algorithmic_flops_per_launch=flops, peak_source=peaks["source"] + " bf16 burst"))
     hp = [ops.gemm_tc(p, w.w1_planes, M=rows, N=dff, K=d, passes=3, bias=w.b1, act="relu", want_out=False,
                       want_planes=True)[2] for p in planes]
@@ -199,7 +200,7 @@ def kernel_rooflines(model, batch, peaks, device):
     byts = batch * (2.0 * n * d * 4 + 2.0 * ks * d * 4)
     res.append(dict(kernel="attn_tc (QK^T -> softmax -> P^T V on tcgen05, A not materialised) + fold", bound="hbm",
                     achieved=byts / t / 1e9, peak=peaks["hbm"], unit="GB/s", frac=byts / t / 1e9 / peaks["hbm"],
-                    traffic=358.6e6 * batch / 8,           # profiles/r01c_attn_ncu_full.csv: 331.4 MB read + 27.2 MB written
+                    traffic=714.4e6 * batch / 16,          # profiles/r01k_attn_ncu_full.csv (16 slides): 663.2 MB read + 51.2 MB written
                     launch_ms=t * 1e3, algorithmic_bytes_per_launch=byts,
                     useful_tflops=batch * 4.0 * n * ks * d / t / 1e12))
     xs_sel = torch.randn(batch * ks, d, device=device, generator=g)
