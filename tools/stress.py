@@ -84,7 +84,63 @@ def t_ln():
     return bool(ok), (rows, d)
 
 
-tests = [t_gemm_tc, t_splitk, t_attn, t_select, t_ln]
+def t_blockdiag():
+    """K-windowed product against a block-diagonal B, 128- and 256-row B chunks, aligned or not to the 32-wide k-blocks."""
+    h = int(rs.randint(1, 9)); gn = 4 * int(rs.randint(1, 70)); gk = 8 * int(rs.randint(1, 30)); M = int(rs.randint(1, 600))
+    N, K = h * gn, h * gk
+    a = torch.randn(M, K, device="cuda"); b = torch.zeros(N, K, device="cuda")
+    for j in range(h):
+        b[j * gn:(j + 1) * gn, j * gk:(j + 1) * gk] = torch.randn(gn, gk, device="cuda") / math.sqrt(gk)
+    _, ap, _ = ops.ln_rows(a, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    bp = ops.weight_planes(b) if runs % 2 else ops.planes_t(b.t().contiguous(), 128)
+    out = ops.gemm_tc_blockdiag(ap, 0, bp, M=M, N=N, K=K, group_n=gn, group_k=gk)
+    return rel(out.double(), a.double() @ b.double().t()) < 3e-5, (M, h, gn, gk)
+
+
+def t_splitk_blockdiag():
+    h = int(rs.randint(1, 9)); dm = 4 * int(rs.randint(1, 70)); dn = 4 * int(rs.randint(1, 40)); K = int(rs.randint(1, 4000))
+    M, N = h * dm, h * dn
+    a = torch.randn(K, M, device="cuda"); b = torch.randn(K, N, device="cuda")
+    out = ops.gemm_tc_splitk_blockdiag(ops.planes_t(a, 128), ops.planes_t(b, 128), M=M, N=N, K=K, diag_m=dm, diag_n=dn).double()
+    ref = a.double().t() @ b.double()
+    ok = True
+    for j in range(h):
+        ok = ok and rel(out[j * dm:(j + 1) * dm, j * dn:(j + 1) * dn], ref[j * dm:(j + 1) * dm, j * dn:(j + 1) * dn]) < 3e-5
+    return bool(ok), (h, dm, dn, K)
+
+
+def t_actgrad():
+    M, N, K = int(rs.randint(1, 700)), 4 * int(rs.randint(1, 300)), 8 * int(rs.randint(1, 130))
+    act = ["relu", "gelu", "leakyrelu", "selu"][runs % 4]; p = float(rs.choice([0.0, 0.2]))
+    a = torch.randn(M, K, device="cuda"); b = torch.randn(N, K, device="cuda") / math.sqrt(K); gate = torch.randn(M, N, device="cuda")
+    _, ap, _ = ops.ln_rows(a, None, None, apply_ln=False, want_planes=True)
+    bp = ops.weight_planes(b)
+    drop = (p, 5, int(rs.randint(1, 1000)))
+    out, _ = ops.gemm_tc_actgrad(ap, bp, gate, act, M=M, N=N, K=K, drop=drop, want_planes=False)
+    prod, _, _ = ops.gemm_tc(ap, bp, M=M, N=N, K=K)
+    want, _ = ops.act_bwd(gate, prod, act, drop, want_dh=True, want_a=False) if N * M % 4 == 0 else (None, None)
+    return (True if want is None else bool(torch.allclose(out, want, rtol=1e-6, atol=1e-7))), (M, N, K, act, p)
+
+
+def t_attn_bwd():
+    dk = int(rs.choice([16, 32, 64, 96])); h = int(rs.randint(1, 9)); d = dk * h
+    B = int(rs.randint(1, 3)); n = int(rs.randint(1, 600)); ks = int(rs.randint(1, 300)); p = float(rs.choice([0.0, 0.15]))
+    if not ops.sparse_attn_bwd_tc_supported(B, n, ks, h, d):
+        return True, None
+    qv = torch.randn(B * n, 2 * d, device="cuda"); kp = torch.randn(B * ks, d, device="cuda"); d_o = torch.randn(B * ks, d, device="cuda")
+    drop = (p, 3, 17)
+    _, _, stats = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, n, ks, h, want_probs=False, want_stats=True)
+    _, qvp, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    dq, dv, dkp, _ = ops.sparse_attn_bwd_tc(qvp, qv, kp, d_o, stats, B, n, ks, h, d, drop)
+    rq, rv, rkp, _ = ops.sparse_attn_bwd(qv[:, :d], qv[:, d:], kp, d_o, stats, B, n, ks, h, drop)
+    # one key per head: P = 1 and the true dQ, dKp are exactly 0 — compare against the scale of the non-degenerate gradient
+    floor = 1e-2 * float(rv.abs().max())
+    close = lambda a, b: float((a.double() - b.double()).abs().max()) <= 1e-4 * max(float(b.abs().max()), floor)
+    ok = close(dq, rq) and close(dv, rv) and close(dkp, rkp)
+    return bool(ok), (B, n, ks, h, d, p)
+
+
+tests = [t_gemm_tc, t_splitk, t_attn, t_select, t_ln, t_blockdiag, t_splitk_blockdiag, t_actgrad, t_attn_bwd]
 t0 = time.time()
 while time.time() - t0 < budget:
     fn = tests[runs % len(tests)]
