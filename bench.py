@@ -24,7 +24,6 @@ import sys
 import threading
 import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -9,7 +9,6 @@ them with ``.apply``).  The forward passes do not call PyTorch math: they dispat
 from __future__ import annotations
 
 import copy
-import math
 from typing import Optional
 
 import torch

@@ -12,8 +12,6 @@ Per encoder layer (snuffy.py:126-157), with y = x-with-rows-S-replaced, g the up
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 
 from . import engine, ops

@@ -16,7 +16,7 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
@@ -143,7 +143,6 @@ def select_multiclass(c: torch.Tensor, big_lambda: int, random_patch_share: floa
     if random_mode == "numpy" and _RANDOM._counter is not None:
         raise RuntimeError("random_mode='numpy' draws on the host and cannot be captured in a CUDA graph; use 'device'")
     if random_mode == "numpy":
-        counts_h = None
         rnd = []
         fl = flags.cpu().numpy()
         for b in range(B):

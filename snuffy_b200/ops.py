@@ -12,7 +12,6 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import _lib
 from ._lib import ACT_IDS, check, lib
 
 
@@ -648,7 +647,6 @@ def sparse_attn_bwd_tc(qvp: Planes, qv: torch.Tensor, kp: torch.Tensor, d_o: tor
     scale = math.sqrt(dk)
     dqv = torch.empty(B * N, 2 * d, dtype=torch.float32, device=dev)
     dkp = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
-    rc_d = _block_n(d)
     for b in range(B):
         rows = slice(b * N, (b + 1) * N)
         kbd = block_diag_rows(kp[b * Ksel:(b + 1) * Ksel], h)                     # [h*Ksel, d]

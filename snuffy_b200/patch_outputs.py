@@ -18,7 +18,7 @@ ROC / AUC / FROC scoring themselves (sklearn, froc.py) stay with the caller: out
 from __future__ import annotations
 
 import re
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

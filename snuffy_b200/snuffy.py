@@ -82,7 +82,7 @@ def forward_packed(milnet: MILNet, x: torch.Tensor, cu_seqlens):
     lens = [cu_host[i + 1] - cu_host[i] for i in range(B)]
     if B < 1 or cu_host[0] != 0 or cu_host[-1] != x.shape[0] or min(lens) < 1:
         raise ValueError("cu_seqlens must start at 0, end at T and describe non-empty bags")
-    T, d = x.shape
+    T = x.shape[0]
     max_n = max(lens)
     cu = torch.tensor(cu_host, dtype=torch.int64, device=x.device)
     from . import ops

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import json
 import os
-from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+from typing import Iterable, Iterator, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
