@@ -478,9 +478,14 @@ def main():
     train = None
     if not args.skip_train:
         lc0 = lib.snuffy_launch_count()
-        e_ms, e_steps, _, _, _ = train_throughput(device, world, graph=False)
+        e_ms, e_steps, e_loss, grad_bytes, _ = train_throughput(device, world, graph=False)
         eager_launches = int((lib.snuffy_launch_count() - lc0) / (e_steps + 3))                # 3 warm-up steps
-        t_ms, t_steps, t_loss, grad_bytes, graph_kernels = train_throughput(device, world, graph=True)
+        graph_error = None
+        try:
+            t_ms, t_steps, t_loss, grad_bytes, graph_kernels = train_throughput(device, world, graph=True)
+        except Exception as exc:                            # keep the bench line: report the eager step and say why
+            graph_error = repr(exc)[:300]
+            t_ms, t_steps, t_loss, graph_kernels = e_ms, e_steps, e_loss, None
         if world > 1:
             t = torch.tensor([t_ms, e_ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -494,6 +499,8 @@ def main():
                          "fused MIL loss + backward (tensor-core products as 3-pass split bf16) + gradient packing replayed as ONE "
                          "CUDA graph (dropout drawn from a device step counter), then one flat-gradient all-reduce + flat AdamW; "
                          "eager_ms_per_step = the same step without the graph (host-launch bound)"}
+        if graph_error:
+            train["graph_error"] = graph_error
     kernels = [] if (args.skip_kernels or rank != 0) else kernel_rooflines(model, B, peaks, device)
     if world > 1:
         dist.barrier()
