@@ -131,7 +131,8 @@ int snuffy_gemm_tc_actgrad(const void* A_planes, int64_t a_plane_stride, const v
                            int64_t ldg, int gate_act, float dropout_p, uint64_t seed, uint64_t offset, float* out,
                            int64_t ldc, void* out_planes, int64_t out_plane_stride, snuffy_stream_t stream);
 /* out = A_window . B^T against a block-diagonal B (B[n, k] != 0 only where n / group_n == k / group_k: the head-block
- * operands of the attention backward): every column tile contracts only over the k-blocks of the groups it touches.
+ * operands of the attention backward, autograd of snuffy.py:160-168 with the head split of 187-201): every column tile
+ * contracts only over the k-blocks of the groups it touches.
  * b_rc = rows per chunk of the B planes (128 or 256).                                                             */
 int snuffy_gemm_tc_blockdiag(const void* A_planes, int64_t a_plane_stride, int64_t a_cols_total, int64_t a_col0,
                              const void* B_planes, int64_t b_plane_stride, int b_rc, int64_t M, int64_t N,
