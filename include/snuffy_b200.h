@@ -216,6 +216,9 @@ int snuffy_ln_rows_bwd(const float* dy, const float* dy_bcast, int64_t rows_per_
 /* dh = da * dropout_mask * act'(hpre), a_out = act(hpre) * dropout_mask   (snuffy.py:216-225 backward)      */
 int snuffy_act_bwd(const float* hpre, const float* da, int act, float dropout_p, uint64_t seed,
                    uint64_t offset, int64_t total, float* dh, float* a_out, snuffy_stream_t stream);
+/* out = x + y * dropout_mask: the residual of a stand-alone SublayerConnection.forward (snuffy.py:108,110)  */
+int snuffy_residual_dropout(const float* x, const float* y, float dropout_p, uint64_t seed, uint64_t offset,
+                            int64_t total, float* out, snuffy_stream_t stream);
 /* out[c, :] = sum_rows w[row, c] * X[row, :]  (bias grads; FCLayer weight grad snuffy.py:37)                 */
 int64_t snuffy_colsum_chunks(int64_t rows);
 int snuffy_colsum(const float* X, int64_t ldx, const float* w, int64_t rows, int64_t d, int64_t C, float* out,

@@ -63,21 +63,41 @@ def clones(module, N):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
 
 
+def _draw(p: float):
+    return (float(p),) + engine._RANDOM.next() if p > 0.0 else (0.0, 0, 0)
+
+
+def _linear(lin: nn.Linear, x2: torch.Tensor, act: str = "none", drop=(0.0, 0, 0)) -> torch.Tensor:
+    """act(x2 lin.weight^T + lin.bias) on the exact-fp32 kernel, differentiable when anything asks for a gradient."""
+    if torch.is_grad_enabled() and (x2.requires_grad or lin.weight.requires_grad):
+        from .backward import LinearFunction
+        return LinearFunction.apply(x2, lin.weight, lin.bias, act, drop)
+    return ops.linear_f32(x2.detach(), lin.weight.detach(), None if lin.bias is None else lin.bias.detach(), act=act, drop=drop)
+
+
+def _sparse_attn(q2, v2, k2, nb, n, k, h, drop):
+    if torch.is_grad_enabled() and (q2.requires_grad or v2.requires_grad or k2.requires_grad):
+        from .backward import SparseAttnFunction
+        return SparseAttnFunction.apply(q2, v2, k2, nb, n, k, h, drop)
+    o, probs, _ = ops.sparse_attn(q2.detach(), v2.detach(), k2.detach(), nb, n, k, h, want_probs=True, dropout_p=drop[0],
+                                  seed=drop[1], offset=drop[2])
+    return o, probs
+
+
 def attention(query, key, value, dropout=None):
     """'Scaled dot product attention' with the reference's transposed aggregation (snuffy.py:160-168).
 
     query/value [nb, h, N, dk], key [nb, h, K, dk] -> (P^T V [nb, h, K, dk], P [nb, h, N, K]).
-    API-compat helper (the encoder calls the fused kernel directly); layout shuffles only, math in CUDA."""
+    API-compat helper (the encoder calls the fused kernel directly); layout shuffles only, math in CUDA.  Gradients flow to
+    query / key / value through the first output; P is returned without a gradient (no caller differentiates it, App. B-9)."""
+    _require_cuda(query, "attention")
     nb, h, n, dk = query.shape
     k = key.shape[2]
-    p_drop = 0.0
-    if dropout is not None and dropout.training:
-        p_drop = float(dropout.p)
+    p_drop = float(dropout.p) if dropout is not None and dropout.training else 0.0
     q2 = query.transpose(1, 2).reshape(nb * n, h * dk)
     v2 = value.transpose(1, 2).reshape(nb * n, h * dk)
     k2 = key.transpose(1, 2).reshape(nb * k, h * dk)
-    seed, offset = engine._RANDOM.next() if p_drop > 0 else (0, 0)
-    o, probs, _ = ops.sparse_attn(q2, v2, k2, nb, n, k, h, want_probs=True, dropout_p=p_drop, seed=seed, offset=offset)
+    o, probs = _sparse_attn(q2, v2, k2, nb, n, k, h, _draw(p_drop))
     return o.view(nb, k, h, dk).transpose(1, 2), probs
 
 
@@ -94,21 +114,16 @@ class MultiHeadedAttention(nn.Module):
         self.dropout = nn.Dropout(p=dropout)
 
     def forward(self, query, key, value):
+        """Stand-alone call form (the fused encoder layer reads `linears` directly): query / value [nb, N, d], key [nb, K, d]
+        -> (W3 . concat_heads(P^T V) [nb, K, d], P [nb, h, N, K])."""
         _require_cuda(query, "MultiHeadedAttention")
         nb = query.size(0)
         d = self.h * self.d_big_lambda
-        proj = []
-        for lin, t in zip(self.linears, (query, key, value)):
-            t2 = t.reshape(-1, d)
-            proj.append(ops.linear_f32(t2, lin.weight.detach(), lin.bias.detach()))
+        proj = [_linear(lin, t.reshape(-1, d)) for lin, t in zip(self.linears, (query, key, value))]
         n, k = query.shape[1], key.shape[1]
-        p_drop = float(self.dropout.p) if self.training else 0.0
-        seed, offset = engine._RANDOM.next() if p_drop > 0 else (0, 0)
-        o, probs, _ = ops.sparse_attn(proj[0], proj[2], proj[1], nb, n, k, self.h, want_probs=True, dropout_p=p_drop,
-                                      seed=seed, offset=offset)
-        self.attn = probs
-        out = ops.linear_f32(o, self.linears[3].weight.detach(), self.linears[3].bias.detach())
-        return out.view(nb, k, d), self.attn
+        o, self.attn = _sparse_attn(proj[0], proj[2], proj[1], nb, n, k, self.h,
+                                    _draw(float(self.dropout.p) if self.training else 0.0))
+        return _linear(self.linears[3], o).view(nb, k, d), self.attn
 
 
 class PositionwiseFeedForward(nn.Module):
@@ -126,18 +141,15 @@ class PositionwiseFeedForward(nn.Module):
     def forward(self, x):
         _require_cuda(x, "PositionwiseFeedForward")
         shape = x.shape
-        x2 = x.reshape(-1, shape[-1])
-        drop = (0.0, 0, 0)
-        if self.training and self.dropout.p > 0:
-            drop = (float(self.dropout.p),) + engine._RANDOM.next()
-        hdn = ops.linear_f32(x2, self.w_1.weight.detach(), self.w_1.bias.detach(), act=self.activation_name, drop=drop)
-        out = ops.linear_f32(hdn, self.w_2.weight.detach(), self.w_2.bias.detach())
+        hdn = _linear(self.w_1, x.reshape(-1, shape[-1]), self.activation_name,
+                      _draw(float(self.dropout.p) if self.training else 0.0))
+        out = _linear(self.w_2, hdn)
         return out.view(*shape[:-1], out.shape[-1])
 
 
 class SublayerConnection(nn.Module):
-    """Pre-norm residual wrapper (snuffy.py:89-110).  Parameter holder for LN1/LN2; the fused encoder layer
-    reads ``norm`` and ``dropout`` from here.  ``forward`` keeps the reference's call form for the 'ff' mode."""
+    """Pre-norm residual wrapper (snuffy.py:89-110).  Parameter holder for LN1/LN2: the fused encoder layer reads ``norm`` and
+    ``dropout`` from here.  ``forward`` keeps the reference's stand-alone call form in both modes."""
 
     def __init__(self, size, dropout):
         super().__init__()
@@ -145,14 +157,39 @@ class SublayerConnection(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def layer_norm(self, x):
-        out, _, _ = ops.ln_rows(x.reshape(-1, x.shape[-1]), self.norm.weight.detach(), self.norm.bias.detach(),
-                                want_f32=True)
-        return out.view(x.shape)
+        from .autograd import layer_norm_fn
+        return layer_norm_fn(x, self.norm.weight, self.norm.bias)
 
-    def forward(self, x, sublayer, *args):
-        # The reference only ever calls this from EncoderLayer.forward (snuffy.py:148-157); here both modes are
-        # fused into the encoder-layer kernels, so there is deliberately no stand-alone implementation.
-        raise NotImplementedError("SublayerConnection.forward is fused into EncoderLayer.forward in snuffy_b200")
+    def _residual(self, x, y):
+        drop = _draw(float(self.dropout.p) if self.training else 0.0)
+        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+            from .backward import ResidualDropoutFunction
+            return ResidualDropoutFunction.apply(x, y, drop)
+        return ops.residual_dropout(x.detach(), y.detach(), drop)
+
+    def forward(self, x, sublayer, c=None, top_big_lambda_indices=None, random_indices=None, *rest, mode=None):
+        """Apply residual connection to any sublayer with the same size.  Both reference call forms are accepted:
+        snuffy.py:100  (x, sublayer, c, top_indices, random_indices, mode) and snuffy_multiclass.py:103
+        (x, sublayer, c, top_indices [B, ref], random_indices [B, ref], num_batch, feats_size, num_classes, k, mode)."""
+        _require_cuda(x, "SublayerConnection")
+        if rest:
+            mode = rest[-1]
+        if mode == "ff":
+            return self._residual(x, sublayer(self.layer_norm(x)))
+        if mode != "attn":
+            raise ValueError(f"SublayerConnection: mode must be 'attn' or 'ff', got {mode!r}")
+        B = x.shape[0]
+        idx = top_big_lambda_indices.reshape(B, -1)
+        if random_indices is not None:
+            idx = torch.cat((idx, random_indices.reshape(B, -1)), dim=1)
+        idx = idx.to(device=x.device, dtype=torch.int64).contiguous()
+        if torch.is_grad_enabled() and x.requires_grad:
+            from .backward import GatherRowsFunction
+            top_big_lambda = GatherRowsFunction.apply(x, idx)
+        else:
+            top_big_lambda = ops.gather_rows(x.detach().contiguous(), idx)
+        multiheadedattn = sublayer(self.layer_norm(x))
+        return self._residual(top_big_lambda, multiheadedattn[0]), multiheadedattn[1]
 
 
 class Encoder(nn.Module):

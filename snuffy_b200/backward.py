@@ -213,6 +213,88 @@ class EncoderLayerFunction(torch.autograd.Function):
                 d_g1, d_be1, d_g2, d_be2)
 
 
+# ------------------------------------------------------------------ stand-alone pieces of the class surface
+# MultiHeadedAttention.forward (snuffy.py:183-205), PositionwiseFeedForward.forward (224-225), attention (160-168) and
+# SublayerConnection.forward (100-110) called on their own (the encoder layer uses the fused path above): exact-fp32 kernels.
+class LinearFunction(torch.autograd.Function):
+    """y = dropout(act(x W^T + b)) for x [rows, K], W [N, K]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, drop):
+        x2 = x.detach().contiguous()
+        need_pre = act != "none" and any(ctx.needs_input_grad[:3])
+        res = ops.gemm_f32(x2, weight.detach(), M=x2.shape[0], N=weight.shape[0], K=x2.shape[1],
+                           bias=None if bias is None else bias.detach(), act=act, want_preact=need_pre, drop=drop)
+        out, pre = res if need_pre else (res, None)
+        ctx.save_for_backward(x2, weight.detach(), pre)
+        ctx.act, ctx.drop, ctx.has_bias = act, drop, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, weight, pre = ctx.saved_tensors
+        g = g.contiguous()
+        if pre is not None or ctx.drop[0] > 0:
+            g = ops.act_bwd(pre, g, ctx.act if pre is not None else "none", ctx.drop)[0]
+        dx = ops.matmul_nn(g, weight) if ctx.needs_input_grad[0] else None
+        dw = ops.matmul_tn(g, x2) if ctx.needs_input_grad[1] else None
+        db = ops.colsum(g).view(-1) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None
+
+
+class SparseAttnFunction(torch.autograd.Function):
+    """(O [B*Ksel, d], P [B, h, N, Ksel]) of snuffy.py:160-168 for q, v [B*N, d], kp [B*Ksel, d]; P carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, q, v, kp, B, N, Ksel, h, drop):
+        q2, v2, k2 = q.detach().contiguous(), v.detach().contiguous(), kp.detach().contiguous()
+        o, probs, stats = ops.sparse_attn(q2, v2, k2, B, N, Ksel, h, want_probs=True, want_stats=True, dropout_p=drop[0],
+                                          seed=drop[1], offset=drop[2])
+        ctx.save_for_backward(q2, v2, k2, stats)
+        ctx.meta = (B, N, Ksel, h, drop)
+        ctx.mark_non_differentiable(probs)
+        return o, probs
+
+    @staticmethod
+    def backward(ctx, d_o, _dp=None):
+        q2, v2, k2, stats = ctx.saved_tensors
+        B, N, Ksel, h, drop = ctx.meta
+        dq, dv, dkp, _ = ops.sparse_attn_bwd(q2, v2, k2, d_o.contiguous(), stats, B, N, Ksel, h, drop)
+        return dq.contiguous(), dv.contiguous(), dkp, None, None, None, None, None
+
+
+class GatherRowsFunction(torch.autograd.Function):
+    """x [B, N, d], idx [B, K] -> x[b, idx[b]] (snuffy.py:103-106); backward scatters the rows back."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = x.shape
+        return ops.gather_rows(x.detach().contiguous(), idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        dx = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        ops.scatter_add_rows(dx, idx, g.contiguous().view(-1, ctx.shape[-1]))
+        return dx, None
+
+
+class ResidualDropoutFunction(torch.autograd.Function):
+    """x + dropout(y)  (snuffy.py:108,110)."""
+
+    @staticmethod
+    def forward(ctx, x, y, drop):
+        ctx.drop = drop
+        return ops.residual_dropout(x.detach().contiguous(), y.detach().contiguous(), drop)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dy = ops.act_bwd(None, g, drop=ctx.drop)[0] if ctx.drop[0] > 0 else g
+        return g, dy, None
+
+
 # ------------------------------------------------------------------ DSMIL bag classifier (dsmil.py:72-92)
 def _dsmil_params(mod):
     import torch.nn as nn

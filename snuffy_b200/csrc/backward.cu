@@ -98,6 +98,18 @@ act_bwd_kernel(const float* __restrict__ hpre, const float* __restrict__ da, int
     }
 }
 
+// ------------------------------------------------------------------ residual + dropout (stand-alone SublayerConnection)
+// out = x + y * dropout_mask    (snuffy.py:108,110 when SublayerConnection.forward is called on its own)
+__global__ void __launch_bounds__(256)
+residual_dropout_kernel(const float* __restrict__ x, const float* __restrict__ y, float drop_p, uint64_t seed, uint64_t offset,
+                        int64_t total, float* __restrict__ out) {
+    { const DrawKey key_ = rng_resolve(seed, offset); seed = key_.seed; offset = key_.offset; }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float m = drop_p > 0.f ? drop_keep_scale(seed, offset, (uint64_t)i, drop_p) : 1.f;
+        out[i] = __ldg(x + i) + __ldg(y + i) * m;
+    }
+}
+
 // ------------------------------------------------------------------ weighted column sums
 // partial[chunk][c][e] = sum_{rows in chunk} w[row*C + c] * X[row*ldx + e]   (w == null -> weight 1, C = 1)
 // grid (row chunks, column slabs of 256): thread = one column (coalesced row reads), 4 independent row accumulators
@@ -286,6 +298,18 @@ int snuffy_act_bwd(const float* hpre, const float* da, int act, float dropout_p,
     if (blocks > cap) blocks = cap;
     act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(hpre, da, act, dropout_p, seed, offset, t4, dh, a_out);
     return check_launch("snuffy_act_bwd");
+}
+
+// out = x + y * dropout_mask over `total` contiguous elements (mask of element i as in snuffy_act_bwd with hpre == null)
+int snuffy_residual_dropout(const float* x, const float* y, float dropout_p, uint64_t seed, uint64_t offset, int64_t total,
+                            float* out, cudaStream_t stream) {
+    SNUFFY_REQUIRE(x && y && out && total >= 0, "snuffy_residual_dropout: bad arguments");
+    if (total == 0) return 0;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = 16 * (int64_t)sm_count();
+    if (blocks > cap) blocks = cap;
+    residual_dropout_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, y, dropout_p, seed, offset, total, out);
+    return check_launch("snuffy_residual_dropout");
 }
 
 int64_t snuffy_colsum_chunks(int64_t rows) {

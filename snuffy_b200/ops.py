@@ -418,6 +418,17 @@ def act_bwd(hpre: Optional[torch.Tensor], da: Optional[torch.Tensor], act: str =
     return dh, a
 
 
+def residual_dropout(x: torch.Tensor, y: torch.Tensor, drop: Tuple[float, int, int] = (0.0, 0, 0)) -> torch.Tensor:
+    """x + dropout(y) (snuffy.py:108,110); the mask is the one act_bwd(None, g, drop=drop) applies in the backward."""
+    x, y = _f32(x, "x"), _f32(y, "y")
+    if x.shape != y.shape:
+        raise ValueError(f"residual_dropout: shapes differ ({tuple(x.shape)} vs {tuple(y.shape)})")
+    out = torch.empty_like(x)
+    check(lib.snuffy_residual_dropout(x.data_ptr(), y.data_ptr(), float(drop[0]), drop[1] & _U64, drop[2] & _U64, x.numel(),
+                                      out.data_ptr(), _stream()), "snuffy_residual_dropout")
+    return out
+
+
 def colsum(x: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x [rows, d] (row stride allowed), w [rows, C] or None -> [C, d]: out[c] = sum_rows w[row, c] * x[row]."""
     if x.dim() != 2 or x.stride(1) != 1:

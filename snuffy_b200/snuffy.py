@@ -101,13 +101,16 @@ def forward_packed(milnet: MILNet, x: torch.Tensor, cu_seqlens):
         kr = int(layer.big_lambda * layer.random_patch_share)
         if min(lens) < kt + kr:
             raise ValueError(f"forward_packed: every bag needs >= {kt + kr} patches (shortest has {min(lens)})")
-        if top is None:                                                                  # c is the same for every layer
-            flags = torch.zeros(T, dtype=torch.uint8, device=x.device)
-            top = ops.select_topk_varlen(classes.view(T, 1), cu, B, max_n, kt, flags).view(B, kt)
-        sel = top
-        if kr > 0:
-            seed, offset = engine._RANDOM.next()
-            sel = torch.cat((top, ops.select_random_varlen(flags, cu, B, max_n, kr, seed, offset)), dim=1)
+        if layer.forced_selection is not None:                                           # tests / parity: LOCAL rows [B, Ksel]
+            sel = layer.forced_selection.to(device=x.device, dtype=torch.int64).view(B, -1) + cu[:-1, None]
+        else:
+            if top is None:                                                              # c is the same for every layer
+                flags = torch.zeros(T, dtype=torch.uint8, device=x.device)
+                top = ops.select_topk_varlen(classes.view(T, 1), cu, B, max_n, kt, flags).view(B, kt)
+            sel = top
+            if kr > 0:
+                seed, offset = engine._RANDOM.next()
+                sel = torch.cat((top, ops.select_random_varlen(flags, cu, B, max_n, kr, seed, offset)), dim=1)
         ksel = sel.shape[1]
         h, _, _ = engine.encoder_layer_forward(h, 1, T, sel.reshape(1, B * ksel).contiguous(), layer.layer_weights(),
                                                layer.self_attn.h, layer.feed_forward.activation_name,
