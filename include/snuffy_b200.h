@@ -249,10 +249,13 @@ int snuffy_softmax_cols_bwd(const float* A, const float* dA, int64_t N, int64_t 
 
 /* ---- training-loop glue on the device (caller side of the path: train.py:828-846, 468-473)                  */
 /* loss = w BCEwL(bag, y) + (1 - w) BCEwL(max_n classes, y), its gradients and the mixed prediction in one launch.
- * terms: 2*B*C floats, ticket: one zeroed uint32; loss[3] = (mixed, bag term, max term).                        */
+ * terms: 2*B*C floats, ticket: one zeroed uint32; loss[3] = (mixed, bag term, max term).  w_dev (optional): the mix
+ * weight read from the device (train.py:804 `single_weight_parameter`, learnable with --soft_average); dw (optional):
+ * gscale * d loss / d w.  The arg-max follows torch.max: a NaN score wins and propagates into the loss.          */
 int snuffy_mil_loss(const float* classes, const float* bag, const float* label, const float* weight,
-                    int64_t B, int64_t N, int64_t C, float w, float gscale, float* terms, uint32_t* ticket,
-                    float* loss, float* pred, float* dclasses, float* dbag, snuffy_stream_t stream);
+                    int64_t B, int64_t N, int64_t C, float w, const float* w_dev, float gscale, float* terms,
+                    uint32_t* ticket, float* loss, float* pred, float* dclasses, float* dbag, float* dw,
+                    snuffy_stream_t stream);
 /* Random draws under CUDA-graph replay.  Every (seed, offset) pair of this header (dropout, random patches) may be given
  * INDIRECTLY: seed bit 63 set  =>  `offset` is the address of a device uint64 step counter and the draw used is
  * (seed & 0xFFFFFFFF, *counter + ((seed >> 32) & 0x7FFFFFFF)).  snuffy_rng_advance(counter, delta) is enqueued as the
@@ -266,6 +269,13 @@ int snuffy_sumsq(const float* x, int64_t n, float* partials, float* out, snuffy_
 int snuffy_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int64_t step, float gscale,
                       const float* gnorm_sq, float max_norm, snuffy_stream_t stream);
+/* The same step as a node of a captured CUDA graph: the 1-based step count, the number of contributing ranks (optional;
+ * the update divides by it and is skipped at 0) and the learning rate (optional) are read from the device; clamp_lo <=
+ * clamp_hi clamps the updated values (train.py:852-854: the learnable mix weight stays in [0, 1]).               */
+int snuffy_adamw_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                          float beta2, float eps, float weight_decay, const int64_t* step_dev,
+                          const float* contributors, const float* lr_dev, float gscale, const float* gnorm_sq,
+                          float max_norm, float clamp_lo, float clamp_hi, snuffy_stream_t stream);
 
 /* dst[offsets[i] .. +sizes[i]) = srcs[i][0 .. sizes[i])  for n tensors (host arrays of device pointers / element counts):
  * one launch per 32 tensors packs the per-parameter gradients into the flat all-reduce / optimizer buffer.         */

@@ -8,5 +8,7 @@ names by putting ``dropin/`` first on ``sys.path``).
 from . import _lib  # noqa: F401  (fails loudly if the native library is missing)
 from . import dp, dsmil, engine, ops, patch_outputs, snuffy, snuffy_multiclass, store  # noqa: F401
 
-__all__ = ["snuffy", "snuffy_multiclass", "dsmil", "ops", "engine", "dp", "store"]
+from .dp import invalidate_weight_caches  # noqa: F401,E402  (call after editing parameters through `.data` / raw pointers)
+
+__all__ = ["snuffy", "snuffy_multiclass", "dsmil", "ops", "engine", "dp", "store", "invalidate_weight_caches"]
 __version__ = "0.1.0"

@@ -74,12 +74,14 @@ _SIGNATURES = {
     "snuffy_gemm_tc_actgrad": (c_int, [P, I, P, I, I, I, I, c_int, P, I, c_int, c_float, c_uint64, c_uint64, P, I, P, I, P]),
     "snuffy_attn_seg_bwd": (c_int, [P, P, I, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P, I, P]),
     "snuffy_softmax_cols_bwd": (c_int, [P, P, I, I, c_float, P, P]),
-    "snuffy_mil_loss": (c_int, [P, P, P, P, I, I, I, c_float, c_float, P, P, P, P, P, P, P]),
+    "snuffy_mil_loss": (c_int, [P, P, P, P, I, I, I, c_float, P, c_float, P, P, P, P, P, P, P, P]),
     "snuffy_rng_advance": (c_int, [P, c_uint64, P]),
     "snuffy_sumsq_blocks": (c_int64, [I]),
     "snuffy_sumsq": (c_int, [P, I, P, P, P]),
     "snuffy_pack_f32": (c_int, [P, P, P, I, P, P]),
     "snuffy_adamw_flat": (c_int, [P, P, P, P, I, c_float, c_float, c_float, c_float, c_float, I, c_float, P, c_float, P]),
+    "snuffy_adamw_flat_dev": (c_int, [P, P, P, P, I, c_float, c_float, c_float, c_float, c_float, P, P, P, c_float, P, c_float,
+                                     c_float, c_float, P]),
     "snuffy_patch_probs": (c_int, [P, I, P, P]),
     "snuffy_froc_detections": (c_int, [P, I, P, P, I, I, c_float, c_int, c_int, P, P, P, P]),
 }

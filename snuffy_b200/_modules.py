@@ -290,9 +290,13 @@ class EncoderLayerBase(nn.Module):
                 s[1].norm.weight, s[1].norm.bias)
 
     def layer_weights(self) -> LayerWeights:
+        """Kernel operands derived from the parameters (fused Q|V weight, LN-folded and transposed planes).  In train mode
+        they are rebuilt on every forward (parameters change every step, and an update through `p.data` or a raw pointer
+        does not bump `p._version`); in eval mode they are cached until a parameter is replaced or updated in place through
+        autograd-visible ops.  After editing `p.data` of an eval-mode model call `snuffy_b200.invalidate_weight_caches`."""
         ps = self._params()
         key = tuple((p.data_ptr(), p._version) for p in ps)
-        if self._wcache is None or self._wcache[0] != key:
+        if self.training or self._wcache is None or self._wcache[0] != key:
             self._wcache = (key, LayerWeights(*[p.detach() for p in ps]))
         return self._wcache[1]
 

@@ -14,14 +14,21 @@ __device__ __forceinline__ float bce_logits(float z, float y) {
     return fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z)));
 }
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+// arg-max order of torch.max: larger value first, NaN above everything (it propagates into the loss), ties to the lower index
+__device__ __forceinline__ bool max_takes(float v, int64_t n, float best, int64_t bi) {
+    const bool vn = v != v, bn = best != best;
+    if (vn || bn) return vn && (!bn || n < bi);
+    return v > best || (v == best && n < bi);
+}
 
 // grid = B*C CTAs: CTA (b, c) finds max_n classes[b, n, c] (ties: lowest n) and writes its two loss terms; the last CTA
 // (ticket) folds them in a fixed order into loss[0..2] = (mixed, bag term, max term) and zeroes the ticket.
 __global__ void __launch_bounds__(256)
 mil_loss_kernel(const float* __restrict__ classes, const float* __restrict__ bag, const float* __restrict__ label,
-                const float* __restrict__ weight, int64_t N, int C, int BC, float w, float gscale,
-                float* __restrict__ terms, unsigned int* __restrict__ ticket, float* __restrict__ loss,
-                float* __restrict__ pred, float* __restrict__ dclasses, float* __restrict__ dbag) {
+                const float* __restrict__ weight, int64_t N, int C, int BC, float w, const float* __restrict__ w_dev,
+                float gscale, float* __restrict__ terms, unsigned int* __restrict__ ticket, float* __restrict__ loss,
+                float* __restrict__ pred, float* __restrict__ dclasses, float* __restrict__ dbag, float* __restrict__ dw) {
+    if (w_dev) w = __ldg(w_dev);                                     // learnable mix weight (train.py:804, --soft_average)
     __shared__ float s_val[8];
     __shared__ int64_t s_idx[8];
     __shared__ int s_last;
@@ -31,19 +38,19 @@ mil_loss_kernel(const float* __restrict__ classes, const float* __restrict__ bag
     float best = -INFINITY; int64_t bi = 0x7fffffffffffffffll;
     for (int64_t n = threadIdx.x; n < N; n += blockDim.x) {
         const float v = col[n * C];
-        if (v > best || (v == best && n < bi)) { best = v; bi = n; }
+        if (max_takes(v, n, best, bi)) { best = v; bi = n; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int64_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        if (max_takes(ov, oi, best, bi)) { best = ov; bi = oi; }
     }
     if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 1; k < 8; ++k)
-            if (s_val[k] > best || (s_val[k] == best && s_idx[k] < bi)) { best = s_val[k]; bi = s_idx[k]; }
+            if (max_takes(s_val[k], s_idx[k], best, bi)) { best = s_val[k]; bi = s_idx[k]; }
         const float y = label[bc], zb = bag[bc];
         const float wt = weight ? weight[c] : 1.f;                   // nn.BCEWithLogitsLoss(weight) (train.py:245-246)
         terms[bc * 2] = wt * bce_logits(zb, y);
@@ -62,6 +69,7 @@ mil_loss_kernel(const float* __restrict__ classes, const float* __restrict__ bag
     for (int k = 0; k < BC; ++k) { lb += __ldcg(terms + k * 2); lm += __ldcg(terms + k * 2 + 1); }
     lb /= (float)BC; lm /= (float)BC;                               // reduction = 'mean'
     loss[0] = w * lb + (1.f - w) * lm; loss[1] = lb; loss[2] = lm;
+    if (dw) dw[0] = gscale * (lb - lm);                              // d loss / d w
     *ticket = 0;
 }
 
@@ -95,7 +103,19 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partials, int npart
 __global__ void __launch_bounds__(256)
 adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                   float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
-                  const float* __restrict__ gnorm_sq, float max_norm) {
+                  const float* __restrict__ gnorm_sq, float max_norm, const long long* __restrict__ step_dev,
+                  const float* __restrict__ contributors, const float* __restrict__ lr_dev, float clamp_lo, float clamp_hi) {
+    if (step_dev) {                                                  // captured step: the count lives on the device
+        const double t = (double)*step_dev;
+        bc1 = 1.f - (float)pow((double)beta1, t);
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+    }
+    if (lr_dev) lr = __ldg(lr_dev);
+    if (contributors) {                                              // ranks that had a bag this step (sum all-reduced with the gradient)
+        const float cnt = __ldg(contributors);
+        if (!(cnt > 0.f)) return;
+        gscale /= cnt;
+    }
     float coef = gscale;
     if (gnorm_sq) coef *= fminf(1.f, max_norm / (sqrtf(gnorm_sq[0]) * fabsf(gscale) + 1e-6f));   // clip_grad_norm_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -105,6 +125,7 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
         const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
         m[i] = mi; v[i] = vi;
         pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+        if (clamp_lo <= clamp_hi) pi = fminf(fmaxf(pi, clamp_lo), clamp_hi);      // train.py:852-854 (mix weight in [0, 1])
         p[i] = pi;
     }
 }
@@ -120,13 +141,14 @@ extern "C" {
 // classes [B, N, C], bag / label [B, C], weight [C] or null; workspace: 2*B*C floats + one zeroed uint32 ticket.
 // Outputs: loss[3] = (mixed, bag term, max term); optional pred [B, C] (train.py:840-844); optional gradients scaled by
 // gscale: dbag [B, C] and dclasses [B, N, C] (caller-zeroed; only the arg-max rows are written).
+// w_dev (optional): the mix weight is read from the device (a learnable parameter); dw (optional): d loss / d w * gscale.
 int snuffy_mil_loss(const float* classes, const float* bag, const float* label, const float* weight, int64_t B,
-                    int64_t N, int64_t C, float w, float gscale, float* terms, uint32_t* ticket, float* loss, float* pred,
-                    float* dclasses, float* dbag, cudaStream_t stream) {
+                    int64_t N, int64_t C, float w, const float* w_dev, float gscale, float* terms, uint32_t* ticket,
+                    float* loss, float* pred, float* dclasses, float* dbag, float* dw, cudaStream_t stream) {
     SNUFFY_REQUIRE(classes && bag && label && terms && ticket && loss, "snuffy_mil_loss: null pointer");
     SNUFFY_REQUIRE(B >= 1 && N >= 1 && C >= 1 && B * C <= 65535, "snuffy_mil_loss: bad dimensions");
-    mil_loss_kernel<<<(unsigned)(B * C), 256, 0, stream>>>(classes, bag, label, weight, N, (int)C, (int)(B * C), w, gscale,
-                                                          terms, ticket, loss, pred, dclasses, dbag);
+    mil_loss_kernel<<<(unsigned)(B * C), 256, 0, stream>>>(classes, bag, label, weight, N, (int)C, (int)(B * C), w, w_dev,
+                                                          gscale, terms, ticket, loss, pred, dclasses, dbag, dw);
     return check_launch("snuffy_mil_loss");
 }
 
@@ -165,8 +187,28 @@ int snuffy_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, f
     const int64_t cap = 8 * (int64_t)sm_count();
     if (blocks > cap) blocks = cap;
     adamw_flat_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
-                                                           gscale, gnorm_sq, max_norm);
+                                                           gscale, gnorm_sq, max_norm, nullptr, nullptr, nullptr, 1.f, 0.f);
     return check_launch("snuffy_adamw_flat");
+}
+
+// The same step with everything that changes from step to step read from the device, so that it can be a node of a captured
+// CUDA graph: step_dev (int64, the 1-based step count; bump it with snuffy_rng_advance(step_dev, 1) before this call),
+// contributors (optional float: number of ranks whose gradient is in the sum; the update divides by it and is skipped when
+// it is 0), lr_dev (optional float replacing `lr`, for schedulers).  clamp_lo <= clamp_hi clamps the updated parameters
+// (train.py:852-854 keeps the learnable mix weight in [0, 1]); pass clamp_lo > clamp_hi for none.
+int snuffy_adamw_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, const int64_t* step_dev, const float* contributors,
+                          const float* lr_dev, float gscale, const float* gnorm_sq, float max_norm, float clamp_lo,
+                          float clamp_hi, cudaStream_t stream) {
+    SNUFFY_REQUIRE(p && g && m && v && n >= 0 && step_dev, "snuffy_adamw_flat_dev: bad arguments");
+    if (n == 0) return 0;
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = 8 * (int64_t)sm_count();
+    if (blocks > cap) blocks = cap;
+    adamw_flat_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, gscale,
+                                                           gnorm_sq, max_norm, reinterpret_cast<const long long*>(step_dev),
+                                                           contributors, lr_dev, clamp_lo, clamp_hi);
+    return check_launch("snuffy_adamw_flat_dev");
 }
 
 }  // extern "C"

@@ -131,10 +131,15 @@ def select_multiclass(c: torch.Tensor, big_lambda: int, random_patch_share: floa
         ops.select_topk(c, kt, flags)
         uniq, counts = ops.compact_flags(flags, C * kt)
         if C == 1:
-            ref = kt                                         # one class: no duplicates, no sync needed
-        else:
-            ref = int(counts.min().item())                   # shapes depend on it: one sync per forward
+            ref = biggest = kt                               # one class: no duplicates, no sync needed
+        else:                                                # shapes depend on it: one sync per forward (both numbers at once)
+            ref, biggest = (int(v) for v in torch.stack((counts.min(), counts.max())).tolist())
         ref = min(ref, N - ref)
+        if N - biggest < ref:
+            # a bag whose union of per-class top sets leaves fewer than `ref` other rows: the reference raises from
+            # np.random.choice(..., replace=False) (snuffy_multiclass.py:152-155); never sample flagged rows silently
+            raise ValueError(f"snuffy_multiclass: cannot draw {ref} random patches outside a top set of {biggest} rows "
+                             f"in a bag of {N} (np.random.choice without replacement would fail in the reference)")
         if cache is not None:
             cache.update(uniq=uniq, ref=ref, flags=flags)
     if ref <= 0:

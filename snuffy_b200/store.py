@@ -8,8 +8,9 @@ optional per-patch labels / positions), read through ``numpy.memmap`` straight i
   write_store(path, bags, labels, names)           list of [N_i, d] float32 arrays -> <path>.bin + <path>.json
   csv_to_store(bags_csv, path, num_classes)        the reference's two-level CSV layout -> store (utils.py:138-183)
   BagStore(path)                                   len / bag(i) / label(i) / lengths
-  PinnedPrefetcher(store, order, device)           double-buffered H2D on a copy stream: bag i+1 is copied while bag i
-                                                   is computed (the reference does a pageable .to(device) per bag, train.py:255)
+  PinnedPrefetcher(store, order, device)           a staging thread + copy stream keep the next bags in flight (memmap ->
+                                                   pinned -> device) while the current one is computed; no host-side wait on
+                                                   the consumer's kernels (the reference: pageable .to(device) per bag, train.py:255)
 
 Host-side code: no CUDA kernels here; the prefetcher only issues cudaMemcpyAsync through torch.
 """
@@ -111,45 +112,89 @@ class BagStore:
 
 
 class PinnedPrefetcher:
-    """Iterates (slide id, bag [1, N, d] on the device, label [1, C] on the device) over `order`, with the next bag's
-    memmap -> pinned -> device copy in flight on a side stream while the caller computes on the current one."""
+    """Iterates (slide id, bag [1, N, d] on the device, label [1, C] on the device) over `order`.
 
-    def __init__(self, store: BagStore, order: Iterable[int], device, max_rows: Optional[int] = None):
+    A background thread stages the bags AHEAD of the consumer: memmap -> pinned buffer (host memcpy, GIL released by numpy),
+    then cudaMemcpyAsync on a copy stream.  Nothing on the consumer's side ever blocks the host:
+      * a pinned buffer is reused once ITS OWN previous H2D copy has completed (`_copied`, waited on by the staging thread —
+        a DMA, not the consumer's compute);
+      * a device buffer is reused once the consumer's kernels on it have run — a GPU-side `wait_event(_free)` on the copy
+        stream, not a host synchronize;
+      * the consumer's stream waits (GPU side) for `_ready` of the slot it is handed.
+    So while the GPU computes on bag k, bags k+1 .. k+slots-1 are being read, staged and copied (the reference does a pageable
+    `.to(device)` per bag on the training thread, train.py:255-256)."""
+
+    def __init__(self, store: BagStore, order: Iterable[int], device, max_rows: Optional[int] = None, slots: int = 3):
         self.store, self.order, self.device = store, list(order), torch.device(device)
+        if slots < 2:
+            raise ValueError("PinnedPrefetcher needs at least 2 slots")
         cap = int(max_rows if max_rows is not None else (max(store.lengths[self.order]) if self.order else 0))
         c = len(store.index["labels"][0])
-        self._pinned = [torch.empty(cap, store.d, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self._dev = [torch.empty(cap, store.d, dtype=torch.float32, device=self.device) for _ in range(2)]
-        self._lab = [torch.empty(1, c, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.slots = slots
+        self._pinned = [torch.empty(cap, store.d, dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self._pinned_lab = [torch.empty(1, c, dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self._dev = [torch.empty(cap, store.d, dtype=torch.float32, device=self.device) for _ in range(slots)]
+        self._lab = [torch.empty(1, c, dtype=torch.float32, device=self.device) for _ in range(slots)]
         self._copy = torch.cuda.Stream(device=self.device)
-        self._ready = [torch.cuda.Event() for _ in range(2)]
-        self._free = [torch.cuda.Event() for _ in range(2)]
+        self._ready = [torch.cuda.Event() for _ in range(slots)]     # H2D of the slot done       (consumer stream waits)
+        self._copied = [torch.cuda.Event() for _ in range(slots)]    # same instant, for the host (staging thread waits)
+        self._free = [torch.cuda.Event() for _ in range(slots)]      # consumer's work on the slot enqueued (copy stream waits)
         self.h2d_bytes = 0
 
     def _stage(self, slot: int, i: int) -> int:
         bag = self.store.bag(i)
         n = bag.shape[0]
-        self._free[slot].synchronize()                       # the pinned buffer is reusable once its last H2D has been consumed
+        self._copied[slot].synchronize()                     # pinned buffer: its previous H2D has finished (never the compute)
         self._pinned[slot][:n].numpy()[...] = bag            # memmap -> pinned (the only host copy)
+        self._pinned_lab[slot].numpy()[...] = self.store.label(i).reshape(1, -1)
         with torch.cuda.stream(self._copy):
+            self._copy.wait_event(self._free[slot])          # device buffer: GPU-side wait for the consumer's kernels
             self._dev[slot][:n].copy_(self._pinned[slot][:n], non_blocking=True)
-            self._lab[slot].copy_(torch.from_numpy(self.store.label(i)).view(1, -1), non_blocking=True)
+            self._lab[slot].copy_(self._pinned_lab[slot], non_blocking=True)
             self._ready[slot].record(self._copy)
+            self._copied[slot].record(self._copy)
         self.h2d_bytes += n * self.store.d * 4
         return n
 
     def __iter__(self) -> Iterator[Tuple[int, torch.Tensor, torch.Tensor]]:
+        import queue
+        import threading
         if not self.order:
             return
-        cur = torch.cuda.current_stream(self.device)
-        for ev in self._free:
-            ev.record(cur)
-        n_next = self._stage(0, self.order[0])
-        for k, i in enumerate(self.order):
-            slot, n = k & 1, n_next
-            if k + 1 < len(self.order):
-                n_next = self._stage(slot ^ 1, self.order[k + 1])
-            cur.wait_event(self._ready[slot])
-            yield i, self._dev[slot][:n].view(1, n, self.store.d), self._lab[slot]
-            self._free[slot].record(cur)                     # work enqueued by the caller on `cur` has consumed the buffers
+        free_q: "queue.Queue" = queue.Queue()
+        ready_q: "queue.Queue" = queue.Queue()
+        for s in range(self.slots):
+            free_q.put(s)
+        stop = threading.Event()
 
+        def stager():
+            try:
+                torch.cuda.set_device(self.device)
+                for i in self.order:
+                    slot = free_q.get()
+                    if stop.is_set() or slot is None:
+                        return
+                    ready_q.put((i, slot, self._stage(slot, i)))
+                ready_q.put(None)
+            except BaseException as exc:                     # surfaces in the consumer
+                ready_q.put(exc)
+
+        worker = threading.Thread(target=stager, name="snuffy-prefetch", daemon=True)
+        worker.start()
+        cur = torch.cuda.current_stream(self.device)
+        try:
+            while True:
+                item = ready_q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                i, slot, n = item
+                cur.wait_event(self._ready[slot])
+                yield i, self._dev[slot][:n].view(1, n, self.store.d), self._lab[slot]
+                self._free[slot].record(cur)                 # work enqueued by the caller on `cur` has consumed the buffers
+                free_q.put(slot)
+        finally:
+            stop.set()
+            free_q.put(None)
+            worker.join(timeout=30)

@@ -22,6 +22,22 @@ def test_shard_slides_round_robin_covers_every_slide_once():
         dp.shard_slides(4, 5, 4)
 
 
+def test_steps_per_epoch_follows_the_largest_shard():
+    """Length-balanced bins can differ a lot in slide count: every rank runs as many steps as the LARGEST shard has slides
+    (the shorter ones join with idle steps), so no slide is dropped and no rank misses a collective."""
+    lengths = [100, 1, 1, 1, 1, 1]
+    shards = [dp.shard_slides(6, r, 2, lengths) for r in range(2)]
+    assert sorted(len(s_) for s_ in shards) == [1, 5]
+    assert dp.steps_per_epoch(6, 2, lengths=lengths) == 5
+    assert dp.steps_per_epoch(6, 2) == 3 and dp.steps_per_epoch(7, 2) == 4 and dp.steps_per_epoch(0, 4) == 0
+    assert dp.steps_per_epoch(7, 2, bags_per_step=2) == 2
+    rs = np.random.RandomState(1)
+    for _ in range(20):
+        n, w = int(rs.randint(1, 40)), int(rs.randint(1, 9))
+        ln = rs.randint(1, 1000, n)
+        assert dp.steps_per_epoch(n, w, lengths=ln) == max(len(dp.shard_slides(n, r, w, ln)) for r in range(w))
+
+
 def test_shard_slides_length_balanced():
     rs = np.random.RandomState(7)
     lengths = np.exp(rs.uniform(np.log(1000), np.log(50000), 64)).astype(int)      # cfg4: N ~ log-uniform[1k, 50k]
@@ -77,14 +93,16 @@ def _worker(rank, world, port, out):
         x = torch.full((2, 6), float(rank + 1))
         model(x).sum().backward()
         local = flat.flat_grad.clone()
+        flat.contributors.fill_(1.0 if rank == 0 else 0.0)                         # rank 1 plays an idle rank
         flat.allreduce_sum()
+        contributors = float(flat.contributors)
         gathered = [torch.zeros_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
         ok = torch.allclose(flat.flat_grad, sum(gathered)) and flat.flat_grad.abs().sum() > 0
         ref = _tiny_model()
         same_start = all(torch.equal(p.detach(), q.detach()) for p, q in zip(model.parameters(), ref.parameters()))
         mine = dp.shard_slides(9, rank, world)
-        out[rank] = (bool(ok), bool(same_start), mine)
+        out[rank] = (bool(ok), bool(same_start), mine, contributors)
     finally:
         dist.destroy_process_group()
 
@@ -95,6 +113,7 @@ def test_flat_gradient_allreduce_gloo_world2():
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out[0][0] and out[1][0] and out[0][1] and out[1][1]
     assert sorted(out[0][2] + out[1][2]) == list(range(9))
+    assert out[0][3] == out[1][3] == 1.0                       # the contributor slot travels with the gradient
 
 
 def test_random_stream_keeps_the_indirect_flag_bit_clear():

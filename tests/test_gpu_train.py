@@ -100,6 +100,96 @@ def test_world1_trainer_follows_the_reference_trajectory():
         assert (p.detach().double().cpu() - P64[name].detach()).abs().max() < 5e-4, name
 
 
+def test_mil_loss_device_mix_weight_and_nan_scores():
+    """The mix weight as a learnable device tensor (train.py:804, --soft_average): value read on the device, gradient =
+    bag term - max term.  An all-NaN score column gives a NaN loss like torch.max, not an out-of-bounds write."""
+    from snuffy_b200 import dp
+    g = torch.Generator(device="cuda").manual_seed(3)
+    classes = (torch.randn(2, 300, 2, device="cuda", generator=g) * 2).requires_grad_(True)
+    bag = torch.randn(2, 2, device="cuda", generator=g).requires_grad_(True)
+    label = (torch.rand(2, 2, device="cuda", generator=g) > 0.5).float()
+    w = torch.tensor(0.3, device="cuda", requires_grad=True)
+    loss, pred, terms = dp.mil_loss(classes, bag, label, w)
+    (loss * 2.0).backward()
+    c64, b64 = classes.detach().double().requires_grad_(True), bag.detach().double().requires_grad_(True)
+    w64 = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    lb = F.binary_cross_entropy_with_logits(b64, label.double().cpu().cuda())
+    lm = F.binary_cross_entropy_with_logits(c64.max(dim=1)[0], label.double())
+    (2.0 * (w64.cuda() * lb + (1 - w64.cuda()) * lm)).backward()
+    assert abs(float(w.grad) - float(w64.grad)) < 1e-5 and w.grad.shape == w.shape
+    assert (classes.grad.double() - c64.grad).abs().max() < 1e-6 and (bag.grad.double() - b64.grad).abs().max() < 1e-6
+    bad = classes.detach().clone()
+    bad[1, :, 0] = float("nan")
+    loss, _, _ = dp.mil_loss(bad, bag.detach(), label, 0.5)
+    torch.cuda.synchronize()
+    assert torch.isnan(loss)
+    one_nan = classes.detach().clone()
+    one_nan[0, 17, 1] = float("nan")                                   # torch.max propagates a single NaN too
+    assert torch.isnan(dp.mil_loss(one_nan, bag.detach(), label, 0.5)[0])
+
+
+def test_soft_average_trainer_matches_two_group_adamw():
+    """--soft_average: the mix weight is a second AdamW parameter group at lr x 0.1, clamped to [0, 1] after each step
+    (train.py:804, 817-825, 852-854) — DataParallelTrainer(soft_average=True) vs that loop in float64 on the CPU."""
+    from snuffy_b200 import dp, snuffy
+    z, c = load_golden("bin_tiny_relu")
+    params, _ = snuffy_inputs(c)
+    model = load_params(build_snuffy(snuffy, c), params)
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    set_precision(model, "fp32")
+    rs = np.random.RandomState(6)
+    ksel = len(z["ref32_sel"][0])
+    lr, mult = 5e-2, 0.9                                                # large steps so that the clamp at 1 is reached
+    trainer = dp.DataParallelTrainer(model, lr=lr, betas=(0.5, 0.9), weight_decay=5e-3, mix_weight=0.97, soft_average=True,
+                                     single_weight_lr_multiplier=mult)
+    assert trainer.single_weight_parameter.requires_grad and trainer.flat.numel > trainer.flat.model_numel
+    P64 = _params64(params)
+    w64 = torch.tensor(0.97, dtype=torch.float64, requires_grad=True)
+    ropt = torch.optim.AdamW([{"params": [w64], "lr": lr * mult}, {"params": list(P64.values())}], lr=lr, betas=(0.5, 0.9),
+                             weight_decay=5e-3)
+    hit_clamp = False
+    for i in range(5):
+        x = rs.standard_normal((1, c["n"], c["d"])).astype(np.float32)
+        y = 1.0                                                          # bag term > max term or not: w moves either way
+        sels = [rs.permutation(c["n"])[:ksel][None] for _ in range(c["depth"])]
+        force_selections(model, sels)
+        loss = trainer.train_step(torch.from_numpy(x).cuda(), torch.tensor([[y]]))
+        ropt.zero_grad()
+        c64, bag64 = ref_forward(torch.from_numpy(x).double(), P64, c["heads"], c["depth"], c["act"],
+                                 [torch.from_numpy(s_) for s_ in sels])
+        yl = torch.tensor([[y]]).double()
+        rl = w64 * F.binary_cross_entropy_with_logits(bag64.view(1, -1), yl) + \
+            (1 - w64) * F.binary_cross_entropy_with_logits(c64.max(dim=1)[0].view(1, -1), yl)
+        rl.backward(); ropt.step()
+        before_clamp = float(w64)
+        w64.data.clamp_(0, 1)
+        hit_clamp |= before_clamp != float(w64)
+        assert abs(float(loss) - float(rl)) < 5e-4, (i, float(loss), float(rl))
+        assert abs(float(trainer.single_weight_parameter) - float(w64)) < 2e-4, (i, float(trainer.single_weight_parameter), float(w64))
+    assert 0.0 <= float(trainer.single_weight_parameter) <= 1.0 and hit_clamp
+
+
+def test_idle_step_and_uneven_shards_world1():
+    """A rank whose shard ran out joins with train_step(None, None): zero gradient, contributor count 0 -> at world size 1
+    the update is skipped entirely (nobody contributed); a normal step divides by its own count of 1."""
+    from snuffy_b200 import dp, snuffy
+    z, c = load_golden("bin_tiny_relu")
+    params, x = snuffy_inputs(c)
+    model = load_params(build_snuffy(snuffy, c), params)
+    trainer = dp.DataParallelTrainer(model, lr=1e-2)
+    trainer.train_step(torch.from_numpy(x).cuda(), torch.ones(1, 1))
+    assert float(trainer.flat.contributors) == 1.0 and trainer.opt.step_count == 1
+    p1 = trainer.flat.flat_param.clone()
+    assert trainer.train_step(None, None) is None
+    assert float(trainer.flat.contributors) == 0.0
+    assert torch.equal(p1, trainer.flat.flat_param)
+    assert dp.steps_per_epoch(6, 2, lengths=[100, 1, 1, 1, 1, 1]) == 5 and dp.steps_per_epoch(6, 2) == 3
+    steps = dp.train_epoch(trainer, [0, 1], lambda i: (torch.from_numpy(x).cuda(), torch.ones(1, 1)))
+    assert steps == 2 and not torch.equal(p1, trainer.flat.flat_param)
+
+
 def _dp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
@@ -123,7 +213,15 @@ def _dp_worker(rank, world, port, out):
             i = dp.shard_slides(4, rank, world)[step]
             trainer.train_step(torch.from_numpy(bags[i]).cuda(), torch.tensor([[labels[i]]]))
             grads.append(trainer.flat.flat_grad.detach().cpu() / world)      # after the all-reduce: sum over ranks
-        out[rank] = (trainer.flat.flat_param.detach().cpu(), grads[0])
+        # uneven shards: rank 0 has one more bag, rank 1 joins with an idle step -> the update uses rank 0's gradient / 1
+        before = trainer.flat.flat_param.detach().clone()
+        if rank == 0:
+            trainer.train_step(torch.from_numpy(bags[0]).cuda(), torch.tensor([[labels[0]]]))
+        else:
+            trainer.train_step(None, None)
+        contributors = float(trainer.flat.contributors)
+        moved = float((trainer.flat.flat_param - before).abs().max())
+        out[rank] = (trainer.flat.flat_param.detach().cpu(), grads[0], contributors, moved)
     finally:
         dist.destroy_process_group()
 
@@ -139,6 +237,7 @@ def test_two_gpu_data_parallel_equals_gradient_averaging():
     out = mgr.dict()
     mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])      # replicas stay bit-identical
+    assert out[0][2] == out[1][2] == 1.0 and out[0][3] == out[1][3] > 0                 # idle rank: one contributor, same update
     z, c = load_golden("bin_tiny_relu")
     params, _ = snuffy_inputs(c)
     model = load_params(build_snuffy(snuffy, c), params)
@@ -249,7 +348,7 @@ def test_graph_replays_draw_fresh_masks_and_match_the_eager_draws():
     torch.manual_seed(77)                                              # < 2^32: the indirect draws use seed & 0xFFFFFFFF
     c, eager, graph = _graph_pair("bin_rand_gelu", dropout=0.1, r=0.5, precision="bf16x3")
     for t in (eager, graph):
-        t.opt.lr, t.opt.weight_decay = 0.0, 0.0                        # parameters stay put
+        t.opt.set_lr(0.0); t.opt.weight_decay = 0.0                     # parameters stay put
     rs = np.random.RandomState(4)
     x = torch.from_numpy(rs.standard_normal((1, c["n"], c["d"])).astype(np.float32)).cuda()
     y = torch.ones(1, 1, device="cuda")

@@ -86,3 +86,32 @@ def test_pinned_prefetcher_feeds_the_model(tmp_path):
             assert torch.equal(bag, ref)
             seen.append(i)
     assert seen == order and pf.h2d_bytes == sum(len(bags[i]) for i in order) * c["d"] * 4
+
+
+@pytest.mark.gpu
+def test_pinned_prefetcher_reuses_slots_without_corruption(tmp_path):
+    """Many more bags than slots, a slow consumer kernel in between and an early exit: every bag arrives intact (a buffer is
+    never overwritten while its copy or the consumer's work on it is pending) and the staging thread shuts down."""
+    import threading
+    rs = np.random.RandomState(5)
+    lens = [int(n) for n in rs.randint(1000, 6000, 14)]
+    bags = _bags(rs, lens, 64)
+    store.write_store(str(tmp_path / "m"), bags, [i & 1 for i in range(len(bags))])
+    st = store.BagStore(str(tmp_path / "m"))
+    order = list(rs.permutation(len(bags)))
+    pf = store.PinnedPrefetcher(st, order, "cuda", slots=2)
+    big = torch.randn(4096, 4096, device="cuda")
+    sums, seen = [], []
+    for i, x, y in pf:
+        _ = big @ big                                     # keeps the compute stream busy while later bags are staged
+        sums.append(x.double().sum())                     # enqueued behind it: reads the slot after the matmul
+        seen.append(i)
+    torch.cuda.synchronize()
+    assert seen == order
+    for i, s_ in zip(seen, sums):
+        assert abs(float(s_) - float(bags[i].astype(np.float64).sum())) < 1e-6 * max(1.0, abs(float(s_)))
+    before = threading.active_count()
+    for k, (i, x, y) in enumerate(store.PinnedPrefetcher(st, order, "cuda")):
+        if k == 2:
+            break
+    assert threading.active_count() <= before
