@@ -126,6 +126,8 @@ class PinnedPrefetcher:
 
     def __init__(self, store: BagStore, order: Iterable[int], device, max_rows: Optional[int] = None, slots: int = 3):
         self.store, self.order, self.device = store, list(order), torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())      # the staging thread needs an explicit index
         if slots < 2:
             raise ValueError("PinnedPrefetcher needs at least 2 slots")
         cap = int(max_rows if max_rows is not None else (max(store.lengths[self.order]) if self.order else 0))

@@ -141,12 +141,12 @@ def test_soft_average_trainer_matches_two_group_adamw():
     set_precision(model, "fp32")
     rs = np.random.RandomState(6)
     ksel = len(z["ref32_sel"][0])
-    lr, mult = 5e-2, 0.9                                                # large steps so that the clamp at 1 is reached
-    trainer = dp.DataParallelTrainer(model, lr=lr, betas=(0.5, 0.9), weight_decay=5e-3, mix_weight=0.97, soft_average=True,
+    lr, mult = 5e-2, 0.9                                                # large steps so that the clamp at 0 is reached
+    trainer = dp.DataParallelTrainer(model, lr=lr, betas=(0.5, 0.9), weight_decay=5e-3, mix_weight=0.03, soft_average=True,
                                      single_weight_lr_multiplier=mult)
     assert trainer.single_weight_parameter.requires_grad and trainer.flat.numel > trainer.flat.model_numel
     P64 = _params64(params)
-    w64 = torch.tensor(0.97, dtype=torch.float64, requires_grad=True)
+    w64 = torch.tensor(0.03, dtype=torch.float64, requires_grad=True)
     ropt = torch.optim.AdamW([{"params": [w64], "lr": lr * mult}, {"params": list(P64.values())}], lr=lr, betas=(0.5, 0.9),
                              weight_decay=5e-3)
     hit_clamp = False
