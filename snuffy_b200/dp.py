@@ -268,12 +268,14 @@ class DataParallelTrainer:
     def __init__(self, model: torch.nn.Module, lr: float = 2e-4, betas=(0.5, 0.9), weight_decay: float = 5e-3,
                  clip_grad: Optional[float] = None, mix_weight: float = 0.5, group=None,
                  forward_fn: Optional[Callable] = None, class_weight: Optional[torch.Tensor] = None,
-                 cuda_graph: bool = False, soft_average: bool = False, single_weight_lr_multiplier: float = 0.1):
+                 cuda_graph: bool = False, soft_average: bool = False, single_weight_lr_multiplier: float = 0.1,
+                 data_parallel: bool = True):
         self.model = model
         self.cuda_graph = bool(cuda_graph)
         self._graph, self._graph_key, self.graph_mode = None, None, None
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # data_parallel=False: a purely local trainer even inside an initialised process group (no broadcast, no all-reduce)
+        self.world = dist.get_world_size(group) if data_parallel and dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         dev = next(model.parameters()).device
         # train.py:804: a 0-dim tensor, clamped to [0, 1], trainable only with --soft_average
@@ -313,7 +315,7 @@ class DataParallelTrainer:
             self.flat.allreduce_sum(self.group)
             ev[1].record()
             self.allreduce_events = ev
-        else:
+        elif self.world > 1:
             self.flat.allreduce_sum(self.group)
         self.opt.step(grad_scale=1.0, use_contributors=True)          # the kernel divides by the contributor count
 
