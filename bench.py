@@ -56,6 +56,26 @@ class ClockSampler:
         self.marks = {}
 
     def _run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:                                             # NVML directly: ~1 ms per sample (nvidia-smi costs ~0.3 s per call)
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and all(t.strip().isdigit() for t in visible.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            bits = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                r = get_reasons(h)
+                row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)]
+                row += ["Active" if r & b else "Not Active" for b in bits]
+                self.rows.append((time.perf_counter(), row))
+                self._stop.wait(0.02)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -100,8 +120,8 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": int(in_region),
                 "power_w_max": max(pw) if pw else None,
-                "window": "nvidia-smi every 0.1 s while the GPU runs the SAME step back to back: an untimed sustain phase "
-                          "(>= 200 steps) followed at once by the K timed steps"}
+                "window": "NVML every 20 ms (nvidia-smi every 0.1 s if NVML is unavailable) while the GPU runs the SAME step back "
+                          "to back: an untimed sustain phase (>= 200 steps) followed at once by the K timed steps"}
 
 
 # ------------------------------------------------------------------ model + data
