@@ -3,26 +3,32 @@
 //   S_j = Q_j Kp_j^T / sqrt(dk)   [N, Ksel]    softmax over the Ksel keys of each query row
 //   O_j = P_j^T V_j               [Ksel, dk]   transposed aggregation: the contraction runs over the N queries
 //
-// Both contractions are split-bf16 3-pass tcgen05.mma (fp32 accumulate in TMEM) so the result matches fp32 to
-// ~2^-16; with fp32 SIMT math this kernel is ~8x compute-bound over its HBM time.
+// Both contractions are split-bf16 tcgen05.mma (fp32 accumulate in TMEM) so the result matches fp32 to ~2^-16; with fp32
+// SIMT math this kernel is ~8x compute-bound over its HBM time.
 //
 // Operands:
-//   Q, V  : the Q|V projection GEMM writes its result directly as split-bf16 A-operand planes over
-//           [B*N, 2d] (csrc/common.cuh).  A (row-tile, head) block of Q is 128 x dk, K-major: the A operand of
-//           S = Q Kp^T.  The same block of V, read through an MN-major descriptor, is the B operand of
-//           O = P^T V (N = dv contiguous in each 16-byte unit, K = query row).  No transposes, one bulk copy each.
+//   Q, V  : the Q|V projection GEMM writes its result directly as split-bf16 A-operand planes over [B*N, 2d]
+//           (csrc/common.cuh).  A (row-tile, head) block of Q is 128 x dk, K-major: the A operand of S = Q Kp^T.  The same
+//           block of V, read through an MN-major descriptor (M = dv contiguous in each 16-byte unit, K = query row), is the
+//           A operand of O^T = V^T P.  No transposes, one bulk copy each.
 //   Kp    : fp32 [B*Ksel, d]; each CTA splits its head's keys into shared memory once per work item.
-//   P     : never leaves the SM: the softmax warps write it as MN-major split-bf16 planes (M = key, K = query).
+//   P     : never leaves the SM: the softmax warps write it as MN-major split-bf16 planes (N = key, K = query).
+//
+// O is accumulated TRANSPOSED: O^T [dv, keys] = sum_queries V^T P has M = dv and N = all keys of the chunk, so one 128-query
+// tile costs 8 k-steps x 2 MMAs of M = 128 (the hi and lo planes of V stacked along M: rows [0, dk) = V_hi^T (P_hi + P_lo),
+// rows [dk, 2 dk) = V_lo^T (P_hi + P_lo)) and N = KP — 1664 tensor clocks at 208 keys, where O = P^T V (M = keys padded to
+// 256, N = dk) needed 64 narrow MMAs that were bound by their shared-memory operand reads (3560 clocks measured).
 //
 // Work item = (bag, head, key chunk, row-tile range).  Per 128-query tile:
-//   warp 0     bulk-copy producer: Q tile, V tile (single buffers, re-armed by tcgen05.commit)
-//   warp 1     MMA issuer:  S(t) = Q Kp^T -> TMEM[0, KP);  O += P(t-1)^T V(t-1) -> TMEM[256, ...): per 128-key block 2 dk
-//              columns, [0, dk) = P_hi^T V_hi + P_lo^T V_hi, [dk, 2 dk) = P_hi^T V_lo (the two V planes are one N = 2 dk operand)
-//   warps 2-9  one query row per thread (AT_PARTS warps per TMEM lane quadrant split the key chunks): row max, then exp ONCE
-//              per score parked back into TMEM (tcgen05.st), then normalise + integer-pipe bf16 split -> P planes in smem;
-//              at the end of the item O -> registers -> per-split partial (folded by fold_partials_kernel).
-// Ksel > 256 (or a wide head): two launches over key chunks, MODE 1 = per-chunk row statistics, MODE 2 = merged statistics,
-// P and P^T V per chunk.  Measured timeline and what bounds each phase: profiles/r01_summary.md (rounds 1c, 1d).
+//   warp 0      bulk-copy producer: Q tile, V tile (single buffers, re-armed by tcgen05.commit)
+//   warp 1      MMA issuer:  S(t) = Q Kp^T -> TMEM[0, KP);  O^T += V(t-1)^T P(t-1) -> TMEM[256, 256 + KP)
+//   warps 2-17  one query row per thread, four warps per TMEM lane quadrant each owning a contiguous range of 8-key groups:
+//               the row's scores are read from TMEM ONCE into registers and S is released at once (the next tile's scores are
+//               computed while this one is normalised); row max and row sum are exchanged between the four parts through
+//               shared memory; exp once per score; normalise + integer-pipe bf16 split -> P planes in smem.
+//               At the end of the item O^T -> registers -> per-split partial (folded by fold_partials_kernel).
+// Ksel > 256: two launches over key chunks, MODE 1 = per-chunk row statistics, MODE 2 = merged statistics, P and V^T P per
+// chunk.  Measured timeline and what bounds each phase: profiles/r02_summary.md (round 1 design: profiles/r01_summary.md).
 #include "tc_ptx.cuh"
 
 namespace snuffy {
@@ -30,12 +36,17 @@ namespace snuffy {
 void launch_fold_partials(const float* part, int splits, int64_t n4, float* out, cudaStream_t stream);
 
 #ifndef AT_PARTS_N
-#define AT_PARTS_N 2
+#define AT_PARTS_N 3
 #endif
-constexpr int AT_PARTS = AT_PARTS_N;     // softmax warps per TMEM lane quadrant (each owns a contiguous range of key chunks)
-constexpr int AT_THREADS = 64 + 128 * AT_PARTS;   // producer + MMA issuer + 4 * AT_PARTS softmax warps
-constexpr int AT_TILE = 128;            // queries per tile (UMMA M)
-constexpr uint32_t AT_O_COL = 256;      // TMEM column of the O accumulators
+constexpr int AT_PARTS = AT_PARTS_N;    // softmax warps per TMEM lane quadrant (each owns a contiguous range of 8-key groups)
+constexpr int AT_VG = (32 + AT_PARTS - 1) / AT_PARTS;       // 8-key groups one thread can own (KP <= 256: 32 groups in all)
+constexpr int AT_NLD = AT_VG / 4;                           // full 32-column TMEM loads per thread
+static_assert(AT_VG % 4 == 0 || AT_VG % 4 == 3, "the tail of a thread's key groups is loaded as 24 columns");
+constexpr int AT_SOFT = 128 * AT_PARTS;             // softmax threads (warps 2 .. 2 + 4 * AT_PARTS - 1)
+constexpr int AT_VWARP = 2 + 4 * AT_PARTS;          // the V producer warp
+constexpr int AT_THREADS = 64 + AT_SOFT + 32;       // Q producer + MMA issuer + softmax warps + V producer
+constexpr int AT_TILE = 128;            // queries per tile (UMMA M of S, K of O^T)
+constexpr uint32_t AT_O_COL = 256;      // TMEM column of the O^T accumulator
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -45,7 +56,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 #ifdef ATTN_DEBUG_TIMING
 // Per-phase clock64 stamps of CTA 0 (tools/attn_timeline.py): [role 0 softmax | 1 mma | 2 producer][tile < 64][8 stamps]
-__device__ long long g_attn_dbg[3 * 64 * 8];
+__device__ long long g_attn_dbg[4 * 64 * 8];
 #define DBG_STAMP(role, t, k) do { if (blockIdx.x == 0 && (t) < 64) g_attn_dbg[((role) * 64 + (t)) * 8 + (k)] = clock64(); } while (0)
 #else
 #define DBG_STAMP(role, t, k) do { } while (0)
@@ -56,6 +67,8 @@ struct AttnTcParams {
     int nkb;                          // k-blocks (of 32 columns) per row tile of the planes = ldk / 32
     int q_kb0, v_kb0;                 // first k-block of Q / V columns (head j adds j * dk / 32)
     const float* Kp;                  // [B*Ksel, d]
+    __nv_bfloat16* k_planes;          // workspace: per (bag, key chunk, head) the K-major split-bf16 B operand of S = Q Kp^T,
+                                      // [hi | lo][dk/8][KP][8], written by attn_key_planes_kernel (zero rows beyond Ksel)
     int B, N, Ksel, KP, h, dk, d;
     int splits, tiles_per_split;
     int nkc, KC;                      // key chunks per (bag, head) and keys per chunk (KC % 16 == 0; KP = padded chunk size)
@@ -68,10 +81,41 @@ struct AttnTcParams {
     const int64_t* cu_seqlens;        // packed variable-length bags: rows [cu[b], cu[b+1]) (null: b*N .. (b+1)*N)
 };
 
-// MODE 0: all keys of a head fit one chunk (Ksel <= 256): scores, softmax and P^T V fused in one pass.
+// Splits the projected keys into the shared-memory image of the attention kernel's K operand, one block per (bag, key chunk,
+// head): the attention CTAs then fetch a head's keys with two bulk copies (issued by the producer warp while the previous
+// work item is still being finished) instead of splitting them themselves at every item start.
+__global__ void __launch_bounds__(256)
+attn_key_planes_kernel(const AttnTcParams p) {
+    const int blk = blockIdx.x;                              // (b * nkc + kc) * h + j
+    const int j = blk % p.h, kc = (blk / p.h) % p.nkc, b = blk / (p.h * p.nkc);
+    const int dk = p.dk, KP = p.KP, key0 = kc * p.KC, kvalid = min(p.KC, p.Ksel - key0);
+    const size_t plane = (size_t)KP * dk;                    // elements of one plane
+    __nv_bfloat16* out = p.k_planes + (size_t)blk * 2 * plane;
+    const int units = KP * (dk / 8);
+    for (int idx = threadIdx.x; idx < units; idx += blockDim.x) {
+        const int key = idx % KP, kg = idx / KP;
+        bf16x8 hi, lo;
+        if (key < kvalid) {
+            const float* src = p.Kp + ((int64_t)b * p.Ksel + key0 + key) * p.d + j * dk + kg * 8;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(src + 4));
+            const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16(f[e], hi.v[e], lo.v[e]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { hi.v[e] = __float2bfloat16_rn(0.f); lo.v[e] = hi.v[e]; }
+        }
+        *reinterpret_cast<bf16x8*>(out + (size_t)idx * 8) = hi;
+        *reinterpret_cast<bf16x8*>(out + plane + (size_t)idx * 8) = lo;
+    }
+}
+
+// MODE 0: all keys of a head fit one chunk (Ksel <= 256): scores, softmax and V^T P fused in one pass.
 // MODE 1: several key chunks, pass 1: per-chunk row statistics only (no P, no V, no O).
-// MODE 2: several key chunks, pass 2: merge the chunk statistics, P for this chunk, O[chunk keys] += P^T V.
-template <int MODE>
+// MODE 2: several key chunks, pass 2: merge the chunk statistics, P for this chunk, O[chunk keys] += V^T P.
+// EXTRA: the attention tensor is written out and / or attention dropout is drawn (kept out of the inference instantiation).
+template <int MODE, bool EXTRA>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const AttnTcParams p) {
     extern __shared__ __align__(1024) unsigned char at_smem[];
@@ -79,22 +123,25 @@ attn_tc_kernel(const AttnTcParams p) {
     const uint32_t P_PLANE = (uint32_t)KP * 256u;            // [KP/8 key groups][128 queries][8 keys] bf16
     const uint32_t QV_PLANE = (uint32_t)AT_TILE * dk * 2u;   // [dk/8][128][8] bf16
     const uint32_t KP_PLANE = (uint32_t)KP * dk * 2u;        // [dk/8][KP][8] bf16
-    // order matters: the second 128-key MMA block reads past KP inside sP; what follows must be mapped smem
-    unsigned char* sP = at_smem;
-    unsigned char* sK = sP + 2 * P_PLANE;
+    // order matters: the M = 128 A operand of O^T = V^T P starts at a V plane and reads 16 groups of 2 KB whatever dk is (rows
+    // beyond the valid ones only feed accumulator lanes nobody reads); what follows sV must be mapped shared memory
+    unsigned char* sK = at_smem;
     unsigned char* sQ = sK + 2 * KP_PLANE;
     unsigned char* sV = sQ + 2 * QV_PLANE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * QV_PLANE);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    float* sRed = reinterpret_cast<float*>(bars + 10);       // [max | sum][AT_PARTS][128 rows] (single-buffered: s_full(t+1) orders all reads of tile t first)
+    unsigned char* sP = sV + 2 * QV_PLANE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_PLANE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    float* sRed = reinterpret_cast<float*>(bars + 13);       // [max | sum][AT_PARTS][128 rows]; the named barriers of a quadrant order its reuse
     const uint32_t b0 = smem_u32(bars);
     const uint32_t q_full = b0, q_empty = b0 + 8, v_full = b0 + 16, v_empty = b0 + 24, s_full = b0 + 32,
-                   s_empty = b0 + 40, p_full = b0 + 48, p_empty = b0 + 56, o_full = b0 + 64;
+                   s_empty = b0 + 40, p_full = b0 + 48, p_empty = b0 + 56, o_full = b0 + 64, k_ready = b0 + 72,
+                   o_empty = b0 + 80, k_empty = b0 + 88;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
         mbar_init(s_full, 1); mbar_init(s_empty, 4 * AT_PARTS); mbar_init(p_full, 4 * AT_PARTS); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+        mbar_init(k_ready, 1); mbar_init(o_empty, 4 * AT_PARTS); mbar_init(k_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -107,8 +154,8 @@ attn_tc_kernel(const AttnTcParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int mblocks = (KP + 127) / 128;
     const int ksteps = dk / 16;
+    const bool stacked = 2 * dk <= 128;     // V_hi | V_lo stacked along M of one MMA (the planes are contiguous in the MN-major layout)
     const int chunks_per_head = dk / PLANE_KB;
     const int64_t chunk_elems = (int64_t)AT_TILE * PLANE_KB;
     const int items = p.B * p.h * p.nkc * p.splits;
@@ -129,37 +176,24 @@ attn_tc_kernel(const AttnTcParams p) {
         const int64_t t1 = min(t_last, t0 + p.tiles_per_split);
         const int ntiles = (int)max((int64_t)0, t1 - t0);
 
-        __syncthreads();                       // previous item: O read out, every MMA retired
-        if (warp >= 2) {
-            // ---- split this head's keys into the K-major B operand of S = Q Kp^T (zero rows beyond Ksel)
-            const int units = KP * (dk / 8);
-            for (int idx = threadIdx.x - 64; idx < units; idx += AT_THREADS - 64) {
-                const int key = idx % KP, kg = idx / KP;
-                bf16x8 hi, lo;
-                if (key < kvalid) {
-                    const float* src = p.Kp + ((int64_t)b * p.Ksel + key0 + key) * p.d + j * dk + kg * 8;
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-                    const float4 c = __ldg(reinterpret_cast<const float4*>(src + 4));
-                    const float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) split_bf16(f[e], hi.v[e], lo.v[e]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { hi.v[e] = __float2bfloat16_rn(0.f); lo.v[e] = hi.v[e]; }
-                }
-                *reinterpret_cast<bf16x8*>(sK + (size_t)idx * 16) = hi;
-                *reinterpret_cast<bf16x8*>(sK + KP_PLANE + (size_t)idx * 16) = lo;
-            }
-            fence_proxy_async_smem();
-        }
-        __syncthreads();
-
+        // No CTA-wide barrier between items: the producers fetch the next item's keys and first Q / V tiles while the softmax
+        // warps still finish this one.  k_empty: the last S MMA of an item has retired (the K planes may be overwritten);
+        // k_ready: the K planes of this item have landed; o_empty: the previous item's O has been read out (the MMA warp
+        // waits before its first O MMA).
         if (warp == 0) {
-            // ------------------------------------------------ producer
+            // ------------------------------------------------ Q producer (its own warp: a Q tile is requested the moment the
+            // S MMAs of the previous tile retire, never behind a wait for the V buffer)
+            if (item_no > 0) mbar_wait(k_empty, (item_no - 1) & 1);
+            if (lane == 0) {
+                const __nv_bfloat16* ksrc = p.k_planes + ((size_t)(b * p.nkc + kc) * p.h + j) * 2 * ((size_t)KP * dk);
+                mbar_expect_tx(k_ready, 2 * KP_PLANE);
+                bulk_g2s(smem_u32(sK), ksrc, KP_PLANE, k_ready);
+                bulk_g2s(smem_u32(sK) + KP_PLANE, ksrc + (size_t)KP * dk, KP_PLANE, k_ready);
+            }
+            __syncwarp();
             for (int t = 0; t < ntiles; ++t, ++it) {
                 const int64_t rt = t0 + t;
                 const __nv_bfloat16* qsrc = p.planes + (rt * p.nkb + p.q_kb0 + j * chunks_per_head) * chunk_elems;
-                const __nv_bfloat16* vsrc = p.planes + (rt * p.nkb + p.v_kb0 + j * chunks_per_head) * chunk_elems;
                 if (lane == 0) DBG_STAMP(2, it, 0);
                 mbar_wait(q_empty, (it & 1) ^ 1);
                 if (lane == 0) DBG_STAMP(2, it, 1);
@@ -168,7 +202,14 @@ attn_tc_kernel(const AttnTcParams p) {
                     bulk_g2s(smem_u32(sQ), qsrc, QV_PLANE, q_full);
                     bulk_g2s(smem_u32(sQ) + QV_PLANE, qsrc + p.plane_stride, QV_PLANE, q_full);
                 }
-                if (MODE != 1) {
+                __syncwarp();
+            }
+        } else if (warp == AT_VWARP) {
+            // ------------------------------------------------ V producer
+            if (MODE != 1) {
+                for (int t = 0; t < ntiles; ++t, ++it) {
+                    const int64_t rt = t0 + t;
+                    const __nv_bfloat16* vsrc = p.planes + (rt * p.nkb + p.v_kb0 + j * chunks_per_head) * chunk_elems;
                     mbar_wait(v_empty, (it & 1) ^ 1);
                     if (lane == 0) DBG_STAMP(2, it, 2);
                     if (lane == 0) {
@@ -176,85 +217,96 @@ attn_tc_kernel(const AttnTcParams p) {
                         bulk_g2s(smem_u32(sV), vsrc, QV_PLANE, v_full);
                         bulk_g2s(smem_u32(sV) + QV_PLANE, vsrc + p.plane_stride, QV_PLANE, v_full);
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         } else if (warp == 1) {
             // ------------------------------------------------ MMA issuer
             const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KP >> 3) << 17) | (8u << 24);
+            // O^T = V^T P: A = V planes (MN-major: 8 consecutive dv per 16-byte unit), B = P planes (MN-major: 8 consecutive keys)
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                    ((uint32_t)(dk >> 3) << 17) | (8u << 24);
-            // N = 2 dk: the hi and lo planes of V are contiguous in the MN-major layout (QV_PLANE = dk/8 groups x SBO), so
-            // P_hi^T [V_hi | V_lo] is ONE MMA whose A operand is read once (P^T V is bound by its shared-memory reads)
-            const uint32_t idesc2w = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                                     ((uint32_t)(dk >> 2) << 17) | (8u << 24);
-            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aP = smem_u32(sP), aV = smem_u32(sV);
-            auto mma2 = [&](uint32_t itp, bool first) {
-                // O[mblk] (+)= P(t)^T V(t): A = P planes (MN-major, M = key), B = V planes (MN-major, N = dv)
-                if (lane == 0) DBG_STAMP(1, itp, 4);
-                mbar_wait(p_full, itp & 1);
-                if (lane == 0) DBG_STAMP(1, itp, 5);
-                mbar_wait(v_full, itp & 1);
-                if (lane == 0) DBG_STAMP(1, itp, 6);
-                tc_fence_after();
-                if (lane == 0) {
-                    for (int mb = 0; mb < mblocks; ++mb) {
-                        // accumulators of key block mb: columns [0, dk) = P_hi^T V_hi + P_lo^T V_hi, [dk, 2 dk) = P_hi^T V_lo
-                        const uint32_t d_tmem = tmem_base + AT_O_COL + (uint32_t)(mb * 2 * dk);
-                        for (int ks = 0; ks < AT_TILE / 16; ++ks) {
-                            const uint32_t pa = aP + mb * (16 * 2048) + ks * 256, va = aV + ks * 256;
-                            const uint64_t p_hi = make_smem_desc(pa, 128, 2048), p_lo = make_smem_desc(pa + P_PLANE, 128, 2048);
-                            const uint64_t v_hi = make_smem_desc(va, 128, 2048), v_lo = make_smem_desc(va + QV_PLANE, 128, 2048);
-                            (void)v_lo;
-                            tc_mma_bf16(d_tmem, p_hi, v_hi, idesc2w, (first && ks == 0) ? 0u : 1u);
-                            tc_mma_bf16(d_tmem, p_lo, v_hi, idesc2, 1u);
+                                    ((uint32_t)(KP >> 3) << 17) | (8u << 24);
+            // Descriptors of k-step 0; a k-step advances the start-address field (bits 0-13, in 16-byte units).  The loops stay
+            // rolled: this warp is paced by the tensor pipe, and a small body keeps the instruction cache for the softmax warps.
+            const uint64_t q_hi0 = make_smem_desc(smem_u32(sQ), 2048, 128), q_lo0 = make_smem_desc(smem_u32(sQ) + QV_PLANE, 2048, 128);
+            const uint64_t k_hi0 = make_smem_desc(smem_u32(sK), KP * 16, 128), k_lo0 = make_smem_desc(smem_u32(sK) + KP_PLANE, KP * 16, 128);
+            const uint64_t p_hi0 = make_smem_desc(smem_u32(sP), 128, 2048), p_lo0 = make_smem_desc(smem_u32(sP) + P_PLANE, 128, 2048);
+            const uint64_t v_hi0 = make_smem_desc(smem_u32(sV), 128, 2048), v_lo0 = make_smem_desc(smem_u32(sV) + QV_PLANE, 128, 2048);
+            const uint64_t q_step = (2 * 2048) >> 4, k_step = (uint64_t)(2 * KP * 16) >> 4, pv_step = 256 >> 4;
+            const uint32_t d_o = tmem_base + AT_O_COL;
+            mbar_wait(k_ready, item_no & 1);
+            // iteration t: S(t) = Q(t) Kp^T, then O^T += V(t-1)^T P(t-1)  (one code site each)
+#pragma unroll 1
+            for (int t = 0; t <= ntiles; ++t) {
+                if (t < ntiles) {
+                    if (lane == 0) DBG_STAMP(1, it, 0);
+                    mbar_wait(q_full, it & 1);
+                    if (lane == 0) DBG_STAMP(1, it, 1);
+                    mbar_wait(s_empty, (it & 1) ^ 1);
+                    if (lane == 0) DBG_STAMP(1, it, 2);
+                    tc_fence_after();
+                    if (lane == 0) {
+#pragma unroll 1
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t qo = q_step * ks, ko = k_step * ks;
+                            tc_mma_bf16(tmem_base, q_lo0 + qo, k_hi0 + ko, idesc1, ks ? 1u : 0u);
+                            tc_mma_bf16(tmem_base, q_hi0 + qo, k_lo0 + ko, idesc1, 1u);
+                            tc_mma_bf16(tmem_base, q_hi0 + qo, k_hi0 + ko, idesc1, 1u);
                         }
+                        tc_commit(q_empty);
+                        tc_commit(s_full);
+                        if (t == ntiles - 1) tc_commit(k_empty);
+                        DBG_STAMP(1, it, 3);
                     }
-                    tc_commit(p_empty);
-                    tc_commit(v_empty);
-                    DBG_STAMP(1, itp, 7);
+                    __syncwarp();
+                    ++it;
                 }
-                __syncwarp();
-            };
-            for (int t = 0; t < ntiles; ++t, ++it) {
-                if (lane == 0) DBG_STAMP(1, it, 0);
-                mbar_wait(q_full, it & 1);
-                if (lane == 0) DBG_STAMP(1, it, 1);
-                mbar_wait(s_empty, (it & 1) ^ 1);
-                if (lane == 0) DBG_STAMP(1, it, 2);
-                tc_fence_after();
-                if (lane == 0) {
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t qa = aQ + ks * 2 * 2048, ka = aK + ks * 2 * (KP * 16);
-                        const uint64_t q_hi = make_smem_desc(qa, 2048, 128), q_lo = make_smem_desc(qa + QV_PLANE, 2048, 128);
-                        const uint64_t k_hi = make_smem_desc(ka, KP * 16, 128), k_lo = make_smem_desc(ka + KP_PLANE, KP * 16, 128);
-                        tc_mma_bf16(tmem_base, q_lo, k_hi, idesc1, ks ? 1u : 0u);
-                        tc_mma_bf16(tmem_base, q_hi, k_lo, idesc1, 1u);
-                        tc_mma_bf16(tmem_base, q_hi, k_hi, idesc1, 1u);
+                if (MODE != 1 && t > 0) {
+                    const uint32_t itp = it - (t < ntiles ? 2 : 1);          // the tile whose P is consumed
+                    if (t == 1 && item_no > 0) mbar_wait(o_empty, (item_no - 1) & 1);     // the previous item's O has been read out
+                    if (lane == 0) DBG_STAMP(1, itp, 4);
+                    mbar_wait(p_full, itp & 1);
+                    if (lane == 0) DBG_STAMP(1, itp, 5);
+                    mbar_wait(v_full, itp & 1);
+                    if (lane == 0) DBG_STAMP(1, itp, 6);
+                    tc_fence_after();
+                    if (lane == 0) {
+#pragma unroll 1
+                        for (int ks = 0; ks < AT_TILE / 16; ++ks) {
+                            const uint64_t o = pv_step * ks;
+                            const uint32_t acc0 = (t == 1 && ks == 0) ? 0u : 1u;
+                            if (stacked) {           // lanes [0, dk): V_hi^T (P_lo + P_hi), lanes [dk, 2 dk): V_lo^T (P_lo + P_hi)
+                                tc_mma_bf16(d_o, v_hi0 + o, p_lo0 + o, idesc2, acc0);
+                                tc_mma_bf16(d_o, v_hi0 + o, p_hi0 + o, idesc2, 1u);
+                            } else {                 // lanes [0, dk): V_lo^T P_hi + V_hi^T P_lo + V_hi^T P_hi
+                                tc_mma_bf16(d_o, v_lo0 + o, p_hi0 + o, idesc2, acc0);
+                                tc_mma_bf16(d_o, v_hi0 + o, p_lo0 + o, idesc2, 1u);
+                                tc_mma_bf16(d_o, v_hi0 + o, p_hi0 + o, idesc2, 1u);
+                            }
+                        }
+                        tc_commit(p_empty);
+                        tc_commit(v_empty);
+                        DBG_STAMP(1, itp, 7);
                     }
-                    tc_commit(q_empty);
-                    tc_commit(s_full);
-                    DBG_STAMP(1, it, 3);
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (MODE != 1 && t > 0) mma2(it - 1, t == 1);
             }
-            if (MODE != 1) {
-                if (ntiles > 0) mma2(it - 1, ntiles == 1);
-                if (lane == 0) tc_commit(o_full);
-                __syncwarp();
+            if (lane == 0) {
+                if (ntiles == 0) mbar_arrive(k_empty);           // nothing was issued: the planes are free at once
+                if (MODE != 1) tc_commit(o_full);
             }
+            __syncwarp();
         } else {
-            // ------------------------------------------------ softmax warps.  Thread = one query row of the tile;
-            // the two warps of a TMEM lane quadrant split the key chunks and exchange (max, sum) through smem.
-            const int quad = warp & 3, half = (warp - 2) >> 2;      // `half` = this warp's part (0 .. AT_PARTS-1) of the key chunks
+            // ------------------------------------------------ softmax warps.  Thread = one query row of the tile; the four
+            // warps of a TMEM lane quadrant own contiguous ranges of 8-key groups and exchange (max, sum) through smem.
+            const int quad = warp & 3, part = (warp - 2) >> 2;      // part 0 .. AT_PARTS-1
             const int rr = quad * 32 + lane;
             const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-            const int nchunks = (KP + 31) / 32;
-            const int cper = (nchunks + AT_PARTS - 1) / AT_PARTS;
-            const int c_lo = min(nchunks, half * cper), c_hi = min(nchunks, c_lo + cper);
+            const int ngroups = KP / 8, gbase = ngroups / AT_PARTS, grem = ngroups % AT_PARTS;
+            const int g0 = part * gbase + min(part, grem);          // first 8-key group of this warp
+            const int ng = gbase + (part < grem ? 1 : 0);           // its group count (<= AT_VG: KP <= 256)
             constexpr int RED = AT_PARTS * 128;
-            const uint32_t bar_id = 1 + quad;                       // named barrier of this quadrant's warp pair
+            const uint32_t bar_id = 1 + quad;                       // named barrier of this quadrant's part warps
             for (int t = 0; t < ntiles; ++t, ++it) {
                 const int64_t g = (t0 + t) * AT_TILE + rr;
                 const bool valid = g >= g_lo && g < g_hi;
@@ -265,44 +317,61 @@ attn_tc_kernel(const AttnTcParams p) {
                 mbar_wait(s_full, it & 1);
                 if (stamp) DBG_STAMP(0, it, 1);
                 tc_fence_after();
-                float mx = -INFINITY, inv = 0.f, mc = 0.f;
-                if (MODE != 2) {
-                    // ---- pass 1: row max over this warp's key chunks
-                    for (int c = c_lo; c < c_hi; ++c) {
-                        float v[32];
-                        tc_ld32(lane_addr + (uint32_t)(c * 32), v);
-                        if (c * 32 + 32 <= kvalid) {
+                // ---- this thread's scores: TMEM -> registers ONCE, then S is free for the next tile's MMAs
+                float v[AT_VG * 8];
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, v[e]);
-                        } else {
+                for (int i = 0; i < AT_NLD; ++i)
+                    if (i == 0 || ng > 4 * i) tc_ld32(lane_addr + (uint32_t)(g0 * 8 + 32 * i), *reinterpret_cast<float(*)[32]>(v + 32 * i));
+                if (AT_VG % 4 == 3 && ng > 4 * AT_NLD) tc_ld24(lane_addr + (uint32_t)(g0 * 8 + 32 * AT_NLD), v + 32 * AT_NLD);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);
+                if (stamp) DBG_STAMP(0, it, 2);
+                // padding keys (the chunk is padded to a multiple of 16) carry Q . 0 = 0: give them -inf once, so that the loops
+                // below need no masks (max ignores them, exp2 turns them into exact zeros)
+                if ((g0 + ng) * 8 > kvalid) {
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) mx = fmaxf(mx, v[e]);
+                    for (int gi = 0; gi < AT_VG; ++gi) {
+                        if (gi < ng && (g0 + gi) * 8 + 8 > kvalid) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) if ((g0 + gi) * 8 + e >= kvalid) v[gi * 8 + e] = -INFINITY;
                         }
                     }
-                    sRed[half * 128 + rr] = mx;
+                }
+                float mx = -INFINITY, inv = 0.f, mc = 0.f;
+                if (MODE != 2) {
+                    // ---- row max over this warp's keys
+#pragma unroll
+                    for (int gi = 0; gi < AT_VG; ++gi) {
+                        if (gi < ng) {
+                            const float* sv = v + gi * 8;
+                            const float m01 = fmaxf(fmaxf(sv[0], sv[1]), sv[2]), m23 = fmaxf(fmaxf(sv[3], sv[4]), sv[5]);
+                            mx = fmaxf(fmaxf(mx, m01), fmaxf(fmaxf(m23, sv[6]), sv[7]));
+                        }
+                    }
+                    sRed[part * 128 + rr] = mx;
                     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AT_PARTS * 32) : "memory");
 #pragma unroll
                     for (int q = 0; q < AT_PARTS; ++q) mx = fmaxf(mx, sRed[q * 128 + rr]);
-                    if (stamp) DBG_STAMP(0, it, 2);
                     if (!valid) mx = 0.f;
                     // rows of a neighbouring bag / padding: exp2(s*c - inf) = 0 -> P = 0 exactly (never inf * 0 = NaN)
                     mc = valid ? mx * p.c_log2 : INFINITY;
-                    // ---- pass 2: exp ONCE per score (the XU pipe is the limiter); MODE 0 parks it in TMEM over S
-                    float sum = 0.f;
-                    for (int c = c_lo; c < c_hi; ++c) {
-                        float v[32];
-                        tc_ld32(lane_addr + (uint32_t)(c * 32), v);
-                        const bool full = c * 32 + 32 <= kvalid;
+                    // ---- exp ONCE per score, in place (padding keys: exp2(-inf) = 0)
+                    float sum = 0.f, sum2 = 0.f;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const float ee = ex2_approx(fmaf(v[e], p.c_log2, -mc));
-                            v[e] = (full || c * 32 + e < kvalid) ? ee : 0.f;
-                            sum += v[e];
+                    for (int gi = 0; gi < AT_VG; ++gi) {
+                        if (gi < ng) {
+                            float* sv = v + gi * 8;
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                sv[e] = ex2_approx(fmaf(sv[e], p.c_log2, -mc));
+                                sv[e + 1] = ex2_approx(fmaf(sv[e + 1], p.c_log2, -mc));
+                                sum += sv[e]; sum2 += sv[e + 1];
+                            }
                         }
-                        if (MODE == 0) tc_st32(lane_addr + (uint32_t)(c * 32), v);
                     }
-                    if (MODE == 0) tc_wait_st();
-                    sRed[RED + half * 128 + rr] = sum;
+                    sum += sum2;
+                    sRed[RED + part * 128 + rr] = sum;
                     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AT_PARTS * 32) : "memory");
                     sum = 0.f;
 #pragma unroll
@@ -310,13 +379,10 @@ attn_tc_kernel(const AttnTcParams p) {
                     if (stamp) DBG_STAMP(0, it, 3);
                     if (MODE == 1) {
                         // per-chunk partial statistics for pass 2 (raw-score max, sum of exp2 relative to it)
-                        if (valid && half == 0) {
+                        if (valid && part == 0) {
                             float* sp = p.stats_part + ((int64_t)kc * p.B * p.h * p.N + srow) * 2;
                             sp[0] = mx; sp[1] = sum;
                         }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(s_empty);
                         continue;
                     }
                     inv = valid ? 1.f / sum : 0.f;
@@ -334,92 +400,125 @@ attn_tc_kernel(const AttnTcParams p) {
                         mx = 0.f;
                     }
                     mc = valid ? mx * p.c_log2 : INFINITY;
+#pragma unroll
+                    for (int gi = 0; gi < AT_VG; ++gi) {
+                        if (gi < ng) {
+                            float* sv = v + gi * 8;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) sv[e] = ex2_approx(fmaf(sv[e], p.c_log2, -mc));
+                        }
+                    }
                 }
-                if (p.stats_out && valid && half == 0 && kc == 0) {
+                if (p.stats_out && valid && part == 0 && kc == 0) {
                     float* so = p.stats_out + srow * 2;
                     so[0] = mx * (p.c_log2 * 0.69314718055994530942f);     // max of the scaled scores (natural units)
                     so[1] = inv;
                 }
                 if (stamp) DBG_STAMP(0, it, 4);
-                mbar_wait(p_empty, (it & 1) ^ 1);            // MMA of the previous tile has consumed P
+                mbar_wait(p_empty, (it & 1) ^ 1);            // the MMAs of the previous tile have consumed P
                 if (stamp) DBG_STAMP(0, it, 5);
-                for (int c = c_lo; c < c_hi; ++c) {
-                    float v[32];
-                    tc_ld32(lane_addr + (uint32_t)(c * 32), v);
-                    if (MODE == 0) {
+                const DrawKey dkey = rng_resolve(p.seed, p.offset);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] *= inv;       // exp(s - max) parked by the sum pass
-                    } else {
-                        const bool full = c * 32 + 32 <= kvalid;
+                for (int gi = 0; gi < AT_VG; ++gi) {
+                    if (gi < ng) {
+                        const int kgp = g0 + gi, kb = kgp * 8;
+                        float w[8];
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const float pe = ex2_approx(fmaf(v[e], p.c_log2, -mc)) * inv;
-                            v[e] = (full || c * 32 + e < kvalid) ? pe : 0.f;
+                        for (int e = 0; e < 8; ++e) w[e] = v[gi * 8 + e] * inv;
+                        if (EXTRA && p.P_out && valid) {
+                            float* po = p.P_out + srow * p.Ksel + key0 + kb;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) if (kb + e < kvalid) po[e] = w[e];
                         }
-                    }
-                    if (p.P_out && valid) {
-                        float* po = p.P_out + srow * p.Ksel + key0 + c * 32;
+                        if (EXTRA && p.drop_p > 0.f && valid) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) po[e] = v[e];
-                    }
-                    if (p.drop_p > 0.f && valid) {
-                        const DrawKey dkey = rng_resolve(p.seed, p.offset);
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const uint64_t idx = ((uint64_t)srow * p.Ksel + key0 + c * 32 + e);
-                            v[e] *= drop_keep_scale(dkey.seed, dkey.offset, idx, p.drop_p);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int kgp = c * 4 + u;
-                        if (kgp * 8 < KP) {
-                            // hi = truncated bf16 (exact), lo = bf16 of the exact remainder: integer/FMA pipes only
-                            uint32_t hw[4], lw[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t ua = __float_as_uint(v[u * 8 + 2 * q]), ub = __float_as_uint(v[u * 8 + 2 * q + 1]);
-                                const float la = v[u * 8 + 2 * q] - __uint_as_float(ua & 0xFFFF0000u);
-                                const float lb = v[u * 8 + 2 * q + 1] - __uint_as_float(ub & 0xFFFF0000u);
-                                hw[q] = __byte_perm(ua, ub, 0x7632);
-                                lw[q] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+                            for (int e = 0; e < 8; ++e) {
+                                const uint64_t idx = ((uint64_t)srow * p.Ksel + key0 + kb + e);
+                                w[e] *= drop_keep_scale(dkey.seed, dkey.offset, idx, p.drop_p);
                             }
-                            *reinterpret_cast<uint4*>(sP + (size_t)kgp * 2048 + rr * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            *reinterpret_cast<uint4*>(sP + P_PLANE + (size_t)kgp * 2048 + rr * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                         }
+                        // hi = truncated bf16 (exact), lo = bf16 of the exact remainder: integer/FMA pipes only
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t ua = __float_as_uint(w[2 * q]), ub = __float_as_uint(w[2 * q + 1]);
+                            const float la = w[2 * q] - __uint_as_float(ua & 0xFFFF0000u);
+                            const float lb = w[2 * q + 1] - __uint_as_float(ub & 0xFFFF0000u);
+                            hw[q] = __byte_perm(ua, ub, 0x7632);
+                            lw[q] = __byte_perm(__float_as_uint(la), __float_as_uint(lb), 0x7632);
+                        }
+                        *reinterpret_cast<uint4*>(sP + (size_t)kgp * 2048 + rr * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(sP + P_PLANE + (size_t)kgp * 2048 + rr * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
                 }
-                tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (stamp) DBG_STAMP(0, it, 6);
-                if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
+                if (lane == 0) mbar_arrive(p_full);
             }
             if (MODE != 1) {
-                // ---- item epilogue: O (TMEM lane = key) -> this split's partial; each half takes one 128-key block
+                // ---- item epilogue: O^T (TMEM lane = dv, column = key) -> this split's partial.  With the stacked operand the
+                // lanes [dk, 2 dk) hold the V_lo contribution of column dv = lane - dk: staged through shared memory (the P planes
+                // are idle now) and added by the lanes [0, dk).
                 mbar_wait(o_full, item_no & 1);
                 tc_fence_after();
-                for (int mb = half; mb < mblocks; mb += AT_PARTS) {
-                    const int key = mb * 128 + rr;
-                    for (int c = 0; c < dk / 32; ++c) {
-                        float v[32];
-                        float v2[32];
-                        tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * 2 * dk + c * 32), v);
-                        tc_ld32(lane_addr + AT_O_COL + (uint32_t)(mb * 2 * dk + dk + c * 32), v2);
+                if (warp == 2 && lane == 0) DBG_STAMP(2, it, 3);
+                const int L = rr;                                    // TMEM lane of this thread
+                float* stage = reinterpret_cast<float*>(sP);         // [KP keys][dk] fp32 (<= the P planes: KP * 512 B)
+                const int ng8 = (kvalid + 7) / 8;
+                float* dst = p.O_part + (((int64_t)split * p.B + b) * p.Ksel + key0) * p.d + j * dk;
+                const bool keep = ntiles > 0;                        // an empty split contributes zeros (its TMEM is stale)
+                if (stacked) {
+                    // lanes [0, dk) (the V_hi rows) store their accumulator transposed, stage[key][dv]; lanes [dk, 2 dk) add
+                    // the V_lo rows of the same dv and write the sum out (a warp writes 128 contiguous bytes per key)
+                    if (L < dk) {
+                        for (int g8 = part; g8 < ng8; g8 += AT_PARTS) {
+                            float o[8];
+                            tc_ld8(lane_addr + AT_O_COL + (uint32_t)(g8 * 8), o);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] += v2[e];
-                        if (key < kvalid) {
-                            float* o = p.O_part + (((int64_t)split * p.B + b) * p.Ksel + key0 + key) * p.d + j * dk + c * 32;
+                            for (int e = 0; e < 8; ++e) stage[(g8 * 8 + e) * dk + L] = o[e];
+                        }
+                    }
+                    asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(AT_SOFT) : "memory");
+                    if (warp == 2 && lane == 0) DBG_STAMP(2, it, 4);
+                    if (L >= dk && L < 2 * dk) {
+                        for (int g8 = part; g8 < ng8; g8 += AT_PARTS) {
+                            float o[8];
+                            tc_ld8(lane_addr + AT_O_COL + (uint32_t)(g8 * 8), o);
+                            float hv[8];
 #pragma unroll
-                            for (int e = 0; e < 32; e += 4) {
-                                float4 w = ntiles > 0 ? make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                *reinterpret_cast<float4*>(o + e) = w;
+                            for (int e = 0; e < 8; ++e) hv[e] = stage[(g8 * 8 + e) * dk + (L - dk)];
+                            float* dg = dst + (int64_t)(g8 * 8) * p.d + (L - dk);
+                            if (g8 * 8 + 8 <= kvalid) {                  // whole group valid (warp-uniform): no per-key branches
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) dg[(int64_t)e * p.d] = keep ? o[e] + hv[e] : 0.f;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) if (g8 * 8 + e < kvalid) dg[(int64_t)e * p.d] = keep ? o[e] + hv[e] : 0.f;
                             }
                         }
                     }
+                } else if (L < dk) {
+                    for (int g8 = part; g8 < ng8; g8 += AT_PARTS) {
+                        float o[8];
+                        tc_ld8(lane_addr + AT_O_COL + (uint32_t)(g8 * 8), o);
+                        float* dg = dst + (int64_t)(g8 * 8) * p.d + L;
+                        if (g8 * 8 + 8 <= kvalid) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) dg[(int64_t)e * p.d] = keep ? o[e] : 0.f;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) if (g8 * 8 + e < kvalid) dg[(int64_t)e * p.d] = keep ? o[e] : 0.f;
+                        }
+                    }
                 }
+                if (warp == 2 && lane == 0) DBG_STAMP(3, it, 4);
+                tc_fence_before();
+                // the staging area is the P planes: nobody may start the next item's P before every reader is done
+                asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(AT_PARTS * 128) : "memory");
+                if (lane == 0) mbar_arrive(o_empty);
+                if (warp == 2 && lane == 0) DBG_STAMP(2, it, 5);
             }
-            tc_fence_before();
         }
     }
     tc_fence_before();
@@ -433,7 +532,12 @@ attn_tc_kernel(const AttnTcParams p) {
 struct AttnTcPlan { int KP, KC, nkc, splits, tiles_per_split, grid; size_t smem; bool ok; };
 
 static size_t attn_tc_smem(int KP, int dk) {
-    return (size_t)2 * KP * 256 + (size_t)2 * KP * dk * 2 + (size_t)4 * AT_TILE * dk * 2 + 128 + 4096;
+    const size_t kq = (size_t)2 * KP * dk * 2 + (size_t)2 * AT_TILE * dk * 2;       // K planes, Q planes
+    const size_t v = (size_t)2 * AT_TILE * dk * 2, pp = (size_t)2 * KP * 256;       // V planes, P planes
+    size_t total = kq + v + pp + 128 + 2 * AT_PARTS * 128 * 4;
+    // the M = 128 A operand of O^T = V^T P reads 16 groups of 2 KB from the start of a V plane (csrc comment at the top)
+    const size_t a_reach = kq + v / 2 + (size_t)16 * 2048 + 16;
+    return total > a_reach ? total : a_reach;
 }
 
 static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d) {
@@ -445,12 +549,9 @@ static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, in
     // tiles fit 227 KB of shared memory
     for (int nkc = 1; nkc <= 512; ++nkc) {
         const int KC = (int)(((Ksel + nkc - 1) / nkc + 15) / 16 * 16);
-        if (KC > 256) continue;
-        if (((KC + 127) / 128) * 2 * dk > 256) continue;      // O accumulators: 2 dk TMEM columns per 128-key block from column 256
+        if (KC > 256) continue;                               // S: KC TMEM columns from 0, O^T: KC columns from 256
         const size_t smem = attn_tc_smem(KC, dk);
         if (smem > 227 * 1024) continue;
-        // the second 128-key MMA block addresses 16 key groups from its base: must stay inside the CTA's window
-        if (KC > 128 && (size_t)(16 + 16) * 2048 + (size_t)KC * 256 > smem) continue;
         pl.nkc = (int)((Ksel + KC - 1) / KC); pl.KC = KC; pl.KP = KC; pl.smem = smem;
         break;
     }
@@ -458,17 +559,17 @@ static AttnTcPlan plan_attn_tc(int64_t B, int64_t N, int64_t Ksel, int64_t h, in
     const int64_t tiles = (N + AT_TILE - 1) / AT_TILE + 1;         // a bag may straddle one extra row tile
     const int64_t per = B * h * pl.nkc;
     // Row tiles per work item: the persistent CTAs take items round-robin, so the launch lasts ceil(items / SMs) rounds of one
-    // item each.  Pick the split that minimises rounds x (tiles per item + per-item overhead: key split, O read-out) plus the
-    // cost of folding `splits` partial outputs, all in units of one tile (~5.5 us at 208 keys x 64) — e.g. 16 slides x 8 heads x
-    // 80 tiles: 10 tiles per item = 7 rounds of 10.6 instead of 5 rounds of 16.6.
-    const double fold_per_split = (double)B * (double)Ksel * (double)d * 4.0 / 4.0e6 / 5.5;
+    // item each.  Pick the split that minimises rounds x (tiles per item + per-item overhead: last O MMAs, O read-out, item
+    // set-up — measured ~10 k clocks against ~5.5 k per tile at 208 keys x 64, profiles/r02_summary.md) plus the cost of
+    // folding `splits` partial outputs, all in units of one tile (~3.6 us).
+    const double fold_per_split = (double)B * (double)Ksel * (double)d * 4.0 / 4.0e6 / 3.6;
     double best = 1e30;
     int best_t = (int)tiles;
     for (int64_t t = 1; t <= tiles; ++t) {
         const int64_t s = (tiles + t - 1) / t;
         if (s > 64) continue;
         const int64_t rounds = (per * s + sm_count() - 1) / sm_count();
-        const double cost = (double)rounds * ((double)t + 0.6) + fold_per_split * (double)s;
+        const double cost = (double)rounds * ((double)t + 1.8) + fold_per_split * (double)s;
         if (cost < best - 1e-9) { best = cost; best_t = (int)t; }
     }
     pl.tiles_per_split = best_t;
@@ -493,6 +594,7 @@ int64_t snuffy_sparse_attn_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int6
     const AttnTcPlan pl = plan_attn_tc(B, N, Ksel, h, d);
     if (!pl.ok) return -1;
     int64_t bytes = (int64_t)pl.splits * B * Ksel * d * 4 + 256;
+    bytes += (int64_t)B * pl.nkc * pl.KP * d * 4;                        // split-bf16 key planes (hi + lo) per (bag, chunk, head)
     if (pl.nkc > 1) bytes += (int64_t)pl.nkc * B * h * N * 2 * 4;
     return bytes;
 }
@@ -522,21 +624,28 @@ static int launch_attn_tc(const void* qv_planes, int64_t plane_stride, int64_t l
     p.nkc = pl.nkc; p.KC = pl.KC;
     p.c_log2 = (float)(1.4426950408889634 / sqrt((double)p.dk));
     p.O_part = reinterpret_cast<float*>(workspace);
-    p.stats_part = p.O_part + (int64_t)pl.splits * B * Ksel * d;
+    p.k_planes = reinterpret_cast<__nv_bfloat16*>(p.O_part + (int64_t)pl.splits * B * Ksel * d);
+    p.stats_part = reinterpret_cast<float*>(p.k_planes + (int64_t)B * pl.nkc * pl.KP * d * 2);
     p.P_out = P_out; p.stats_out = stats_out;
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
     p.cu_seqlens = cu_seqlens;
+    SNUFFY_REQUIRE((uintptr_t)workspace % 16 == 0, "snuffy_sparse_attn_tc_fwd: workspace must be 16-byte aligned");
+    attn_key_planes_kernel<<<(unsigned)(B * pl.nkc * h), 256, 0, stream>>>(p);
+    const bool extra = P_out != nullptr || dropout_p > 0.f;
+#define SNUFFY_ATTN_LAUNCH(MODE_, EXTRA_)                                                                                       \
+    do {                                                                                                                        \
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_tc_kernel<MODE_, EXTRA_>), (int)pl.smem));          \
+        attn_tc_kernel<MODE_, EXTRA_><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);                                             \
+    } while (0)
     if (pl.nkc == 1) {
-        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_tc_kernel<0>), (int)pl.smem));
-        attn_tc_kernel<0><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
+        if (extra) SNUFFY_ATTN_LAUNCH(0, true); else SNUFFY_ATTN_LAUNCH(0, false);
     } else {
-        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_tc_kernel<1>), (int)pl.smem));
-        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_tc_kernel<2>), (int)pl.smem));
-        attn_tc_kernel<1><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
-        attn_tc_kernel<2><<<pl.grid, AT_THREADS, pl.smem, stream>>>(p);
+        SNUFFY_ATTN_LAUNCH(1, false);
+        if (extra) SNUFFY_ATTN_LAUNCH(2, true); else SNUFFY_ATTN_LAUNCH(2, false);
     }
+#undef SNUFFY_ATTN_LAUNCH
     launch_fold_partials(p.O_part, pl.splits, B * Ksel * d / 4, O, stream);
-    return check_launch("snuffy_sparse_attn_tc_fwd", pl.nkc == 1 ? 2 : 3);
+    return check_launch("snuffy_sparse_attn_tc_fwd", pl.nkc == 1 ? 3 : 4);
 }
 
 int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,

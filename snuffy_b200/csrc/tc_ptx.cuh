@@ -29,10 +29,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;           // fast path: no clock read when the phase has already completed
     const long long t0 = clock64();
     while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 8000000000ll) {     // ~4 s: a protocol bug must fail loudly, never hang the box
-            printf("snuffy tcgen05 kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        // ~4 s: a protocol bug must fail loudly (sticky launch failure), never hang the box.  No printf here: a call in this
+        // path makes the compiler spill every live register around it (the attention softmax keeps a row of scores live).
+        if (clock64() - t0 > 8000000000ll) asm volatile("trap;");
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -66,6 +65,35 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 8 consecutive columns of this thread's TMEM lane (load + wait in one asm statement)
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 24 consecutive columns of this thread's TMEM lane (three x8 loads and the wait in ONE asm statement, so that no use of the
+// registers can be scheduled before the wait)
+__device__ __forceinline__ void tc_ld24(uint32_t taddr, float* v) {
+    uint32_t r[24];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%24];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%25];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16, %17, %18, %19, %20, %21, %22, %23}, [%26];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+        : "r"(taddr), "r"(taddr + 8u), "r"(taddr + 16u) : "memory");
+#pragma unroll
+    for (int i = 0; i < 24; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const float (&v)[32]) {
