@@ -291,10 +291,13 @@ attn_tc_kernel(const AttnTcParams p) {
                     __syncwarp();
                 }
             }
-            if (lane == 0) {
-                if (ntiles == 0) mbar_arrive(k_empty);           // nothing was issued: the planes are free at once
-                if (MODE != 1) tc_commit(o_full);
+            if (ntiles == 0) {
+                // an empty split issues nothing, but its hand-shakes still have to stay one phase apart from the consumers':
+                // the softmax warps must have passed the previous item's o_full before this item's o_full is signalled
+                if (MODE != 1 && item_no > 0) mbar_wait(o_empty, (item_no - 1) & 1);
+                if (lane == 0) mbar_arrive(k_empty);             // the planes are free at once
             }
+            if (lane == 0 && MODE != 1) tc_commit(o_full);
             __syncwarp();
         } else {
             // ------------------------------------------------ softmax warps.  Thread = one query row of the tile; the four
