@@ -48,6 +48,20 @@ constexpr int AT_THREADS = 64 + AT_SOFT + 32;       // Q producer + MMA issuer +
 constexpr int AT_TILE = 128;            // queries per tile (UMMA M of S, K of O^T)
 constexpr uint32_t AT_O_COL = 256;      // TMEM column of the O^T accumulator
 
+// n / d for n < 2^31 as a multiply-high and a shift (the item decode runs once per work item in code that is cold in the
+// instruction cache: four integer divisions cost over a thousand clocks there)
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, int d, uint32_t mul, uint32_t shr) {
+    return d == 1 ? n : __umulhi(n, mul) >> shr;
+}
+static void fast_div_setup(int d, uint32_t& mul, uint32_t& shr) {
+    if (d <= 1) { mul = 0; shr = 0; return; }
+    uint32_t lg = 0;
+    while ((1u << lg) < (uint32_t)d) ++lg;                    // ceil(log2 d)
+    const uint64_t pw = 31 + lg;
+    mul = (uint32_t)((((uint64_t)1 << pw) + (uint64_t)d - 1) / (uint64_t)d);
+    shr = (uint32_t)(pw - 32);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -71,6 +85,7 @@ struct AttnTcParams {
                                       // [hi | lo][dk/8][KP][8], written by attn_key_planes_kernel (zero rows beyond Ksel)
     int B, N, Ksel, KP, h, dk, d;
     int splits, tiles_per_split;
+    uint32_t div_mul[3], div_shr[3];  // item -> (split, key chunk, head, bag): division by splits, nkc, h as multiply-high + shift
     int nkc, KC;                      // key chunks per (bag, head) and keys per chunk (KC % 16 == 0; KP = padded chunk size)
     float* stats_part;                // [nkc][B, h, N, 2] per-chunk (row max of raw scores, sum of exp2): MODE 1 -> MODE 2
     float c_log2;                     // log2(e) / sqrt(dk)
@@ -129,7 +144,9 @@ attn_tc_kernel(const AttnTcParams p) {
     unsigned char* sQ = sK + 2 * KP_PLANE;
     unsigned char* sV = sQ + 2 * QV_PLANE;
     unsigned char* sP = sV + 2 * QV_PLANE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_PLANE);
+    // the P region doubles as the fp32 staging area of the O read-out: [up to KP + 31 keys][dk] when the operand is stacked
+    const uint32_t stage_bytes = 2 * dk <= 128 ? ((uint32_t)(KP + 32) * dk * 4u + 127u) & ~127u : 0u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (2 * P_PLANE > stage_bytes ? 2 * P_PLANE : stage_bytes));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     float* sRed = reinterpret_cast<float*>(bars + 13);       // [max | sum][AT_PARTS][128 rows]; the named barriers of a quadrant order its reuse
     const uint32_t b0 = smem_u32(bars);
@@ -163,10 +180,10 @@ attn_tc_kernel(const AttnTcParams p) {
     uint32_t item_no = 0;
 
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_no) {
-        const int split = item % p.splits;
-        const int kc = (item / p.splits) % p.nkc;
-        const int j = (item / (p.splits * p.nkc)) % p.h;
-        const int b = item / (p.splits * p.nkc * p.h);
+        const uint32_t r1 = fast_div((uint32_t)item, p.splits, p.div_mul[0], p.div_shr[0]);
+        const uint32_t r2 = fast_div(r1, p.nkc, p.div_mul[1], p.div_shr[1]);
+        const int b = (int)fast_div(r2, p.h, p.div_mul[2], p.div_shr[2]);
+        const int split = item - (int)r1 * p.splits, kc = (int)(r1 - r2 * p.nkc), j = (int)r2 - b * p.h;
         const int key0 = kc * p.KC;                                         // first key of this chunk
         const int kvalid = min(p.KC, p.Ksel - key0);                        // keys of this chunk (the rest of KP is padding)
         const int64_t g_lo = p.cu_seqlens ? p.cu_seqlens[b] : (int64_t)b * p.N;            // global rows of this bag
@@ -341,25 +358,22 @@ attn_tc_kernel(const AttnTcParams p) {
                         }
                     }
                 }
-                float mx = -INFINITY, inv = 0.f, mc = 0.f;
+                float mx = -INFINITY, inv = 0.f, mc = 0.f, rescale = 1.f;
                 if (MODE != 2) {
-                    // ---- row max over this warp's keys
+                    // ---- row max over this warp's keys, then exp ONCE per score relative to that LOCAL max: the parts of a
+                    // row exchange (max, sum) once and rescale (the factor is folded into the normalisation below)
+                    float ml = -INFINITY;
 #pragma unroll
                     for (int gi = 0; gi < AT_VG; ++gi) {
                         if (gi < ng) {
                             const float* sv = v + gi * 8;
                             const float m01 = fmaxf(fmaxf(sv[0], sv[1]), sv[2]), m23 = fmaxf(fmaxf(sv[3], sv[4]), sv[5]);
-                            mx = fmaxf(fmaxf(mx, m01), fmaxf(fmaxf(m23, sv[6]), sv[7]));
+                            ml = fmaxf(fmaxf(ml, m01), fmaxf(fmaxf(m23, sv[6]), sv[7]));
                         }
                     }
-                    sRed[part * 128 + rr] = mx;
-                    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AT_PARTS * 32) : "memory");
-#pragma unroll
-                    for (int q = 0; q < AT_PARTS; ++q) mx = fmaxf(mx, sRed[q * 128 + rr]);
-                    if (!valid) mx = 0.f;
-                    // rows of a neighbouring bag / padding: exp2(s*c - inf) = 0 -> P = 0 exactly (never inf * 0 = NaN)
-                    mc = valid ? mx * p.c_log2 : INFINITY;
-                    // ---- exp ONCE per score, in place (padding keys: exp2(-inf) = 0)
+                    // rows of a neighbouring bag / padding: exp2(s*c - inf) = 0 -> P = 0 exactly (never inf * 0 = NaN); a part
+                    // that owns only padding keys has ml = -inf: all its exp2(-inf - 0) are exact zeros
+                    const float mcl = !valid ? INFINITY : (ml == -INFINITY ? 0.f : ml * p.c_log2);
                     float sum = 0.f, sum2 = 0.f;
 #pragma unroll
                     for (int gi = 0; gi < AT_VG; ++gi) {
@@ -367,18 +381,23 @@ attn_tc_kernel(const AttnTcParams p) {
                             float* sv = v + gi * 8;
 #pragma unroll
                             for (int e = 0; e < 8; e += 2) {
-                                sv[e] = ex2_approx(fmaf(sv[e], p.c_log2, -mc));
-                                sv[e + 1] = ex2_approx(fmaf(sv[e + 1], p.c_log2, -mc));
+                                sv[e] = ex2_approx(fmaf(sv[e], p.c_log2, -mcl));
+                                sv[e + 1] = ex2_approx(fmaf(sv[e + 1], p.c_log2, -mcl));
                                 sum += sv[e]; sum2 += sv[e + 1];
                             }
                         }
                     }
-                    sum += sum2;
-                    sRed[RED + part * 128 + rr] = sum;
+                    sRed[part * 128 + rr] = ml;
+                    sRed[RED + part * 128 + rr] = sum + sum2;
                     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AT_PARTS * 32) : "memory");
+                    float mq[AT_PARTS];
+#pragma unroll
+                    for (int q = 0; q < AT_PARTS; ++q) { mq[q] = sRed[q * 128 + rr]; mx = fmaxf(mx, mq[q]); }
+                    if (!valid) mx = 0.f;
                     sum = 0.f;
 #pragma unroll
-                    for (int q = 0; q < AT_PARTS; ++q) sum += sRed[RED + q * 128 + rr];
+                    for (int q = 0; q < AT_PARTS; ++q) sum += sRed[RED + q * 128 + rr] * ex2_approx((mq[q] - mx) * p.c_log2);
+                    rescale = ex2_approx((ml - mx) * p.c_log2);          // this part's exponentials relative to the row max
                     if (stamp) DBG_STAMP(0, it, 3);
                     if (MODE == 1) {
                         // per-chunk partial statistics for pass 2 (raw-score max, sum of exp2 relative to it)
@@ -389,6 +408,7 @@ attn_tc_kernel(const AttnTcParams p) {
                         continue;
                     }
                     inv = valid ? 1.f / sum : 0.f;
+                    (void)mc;
                 } else {
                     // ---- merge the chunk statistics of this row (written by the MODE 1 launch)
                     float lsum = 0.f;
@@ -421,13 +441,14 @@ attn_tc_kernel(const AttnTcParams p) {
                 mbar_wait(p_empty, (it & 1) ^ 1);            // the MMAs of the previous tile have consumed P
                 if (stamp) DBG_STAMP(0, it, 5);
                 const DrawKey dkey = rng_resolve(p.seed, p.offset);
+                const float pscale = valid ? inv * rescale : 0.f;
 #pragma unroll
                 for (int gi = 0; gi < AT_VG; ++gi) {
                     if (gi < ng) {
                         const int kgp = g0 + gi, kb = kgp * 8;
                         float w[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) w[e] = v[gi * 8 + e] * inv;
+                        for (int e = 0; e < 8; ++e) w[e] = v[gi * 8 + e] * pscale;
                         if (EXTRA && p.P_out && valid) {
                             float* po = p.P_out + srow * p.Ksel + key0 + kb;
 #pragma unroll
@@ -468,50 +489,49 @@ attn_tc_kernel(const AttnTcParams p) {
                 if (warp == 2 && lane == 0) DBG_STAMP(2, it, 3);
                 const int L = rr;                                    // TMEM lane of this thread
                 float* stage = reinterpret_cast<float*>(sP);         // [KP keys][dk] fp32 (<= the P planes: KP * 512 B)
-                const int ng8 = (kvalid + 7) / 8;
                 float* dst = p.O_part + (((int64_t)split * p.B + b) * p.Ksel + key0) * p.d + j * dk;
                 const bool keep = ntiles > 0;                        // an empty split contributes zeros (its TMEM is stale)
+                const int nch = (kvalid + 31) / 32;                  // 32-key chunks, dealt round-robin to the parts of a quadrant
                 if (stacked) {
                     // lanes [0, dk) (the V_hi rows) store their accumulator transposed, stage[key][dv]; lanes [dk, 2 dk) add
                     // the V_lo rows of the same dv and write the sum out (a warp writes 128 contiguous bytes per key)
                     if (L < dk) {
-                        for (int g8 = part; g8 < ng8; g8 += AT_PARTS) {
-                            float o[8];
-                            tc_ld8(lane_addr + AT_O_COL + (uint32_t)(g8 * 8), o);
+                        for (int c = part; c < nch; c += AT_PARTS) {
+                            float o[32];
+                            tc_ld32(lane_addr + AT_O_COL + (uint32_t)(c * 32), o);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) stage[(g8 * 8 + e) * dk + L] = o[e];
+                            for (int e = 0; e < 32; ++e) stage[(c * 32 + e) * dk + L] = o[e];     // rows up to KP + 31 < 288: inside sP
                         }
                     }
                     asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(AT_SOFT) : "memory");
                     if (warp == 2 && lane == 0) DBG_STAMP(2, it, 4);
                     if (L >= dk && L < 2 * dk) {
-                        for (int g8 = part; g8 < ng8; g8 += AT_PARTS) {
-                            float o[8];
-                            tc_ld8(lane_addr + AT_O_COL + (uint32_t)(g8 * 8), o);
-                            float hv[8];
+                        for (int c = part; c < nch; c += AT_PARTS) {
+                            float o[32];
+                            tc_ld32(lane_addr + AT_O_COL + (uint32_t)(c * 32), o);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) hv[e] = stage[(g8 * 8 + e) * dk + (L - dk)];
-                            float* dg = dst + (int64_t)(g8 * 8) * p.d + (L - dk);
-                            if (g8 * 8 + 8 <= kvalid) {                  // whole group valid (warp-uniform): no per-key branches
+                            for (int e = 0; e < 32; ++e) o[e] = keep ? o[e] + stage[(c * 32 + e) * dk + (L - dk)] : 0.f;
+                            float* dg = dst + (int64_t)(c * 32) * p.d + (L - dk);
+                            if (c * 32 + 32 <= kvalid) {                 // whole chunk valid (warp-uniform): no per-key branches
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) dg[(int64_t)e * p.d] = keep ? o[e] + hv[e] : 0.f;
+                                for (int e = 0; e < 32; ++e) dg[(int64_t)e * p.d] = o[e];
                             } else {
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) if (g8 * 8 + e < kvalid) dg[(int64_t)e * p.d] = keep ? o[e] + hv[e] : 0.f;
+                                for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) dg[(int64_t)e * p.d] = o[e];
                             }
                         }
                     }
                 } else if (L < dk) {
-                    for (int g8 = part; g8 < ng8; g8 += AT_PARTS) {
-                        float o[8];
-                        tc_ld8(lane_addr + AT_O_COL + (uint32_t)(g8 * 8), o);
-                        float* dg = dst + (int64_t)(g8 * 8) * p.d + L;
-                        if (g8 * 8 + 8 <= kvalid) {
+                    for (int c = part; c < nch; c += AT_PARTS) {
+                        float o[32];
+                        tc_ld32(lane_addr + AT_O_COL + (uint32_t)(c * 32), o);
+                        float* dg = dst + (int64_t)(c * 32) * p.d + L;
+                        if (c * 32 + 32 <= kvalid) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) dg[(int64_t)e * p.d] = keep ? o[e] : 0.f;
+                            for (int e = 0; e < 32; ++e) dg[(int64_t)e * p.d] = keep ? o[e] : 0.f;
                         } else {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) if (g8 * 8 + e < kvalid) dg[(int64_t)e * p.d] = keep ? o[e] : 0.f;
+                            for (int e = 0; e < 32; ++e) if (c * 32 + e < kvalid) dg[(int64_t)e * p.d] = keep ? o[e] : 0.f;
                         }
                     }
                 }
@@ -536,7 +556,9 @@ struct AttnTcPlan { int KP, KC, nkc, splits, tiles_per_split, grid; size_t smem;
 
 static size_t attn_tc_smem(int KP, int dk) {
     const size_t kq = (size_t)2 * KP * dk * 2 + (size_t)2 * AT_TILE * dk * 2;       // K planes, Q planes
-    const size_t v = (size_t)2 * AT_TILE * dk * 2, pp = (size_t)2 * KP * 256;       // V planes, P planes
+    const size_t v = (size_t)2 * AT_TILE * dk * 2;                                  // V planes
+    size_t pp = (size_t)2 * KP * 256;                                               // P planes / O staging area
+    if (2 * dk <= 128) { const size_t st = (((size_t)(KP + 32) * dk * 4) + 127) & ~(size_t)127; if (st > pp) pp = st; }
     size_t total = kq + v + pp + 128 + 2 * AT_PARTS * 128 * 4;
     // the M = 128 A operand of O^T = V^T P reads 16 groups of 2 KB from the start of a V plane (csrc comment at the top)
     const size_t a_reach = kq + v / 2 + (size_t)16 * 2048 + 16;
@@ -625,6 +647,9 @@ static int launch_attn_tc(const void* qv_planes, int64_t plane_stride, int64_t l
     p.Kp = Kp; p.B = (int)B; p.N = (int)N; p.Ksel = (int)Ksel; p.KP = pl.KP; p.h = (int)h; p.dk = (int)(d / h); p.d = (int)d;
     p.splits = pl.splits; p.tiles_per_split = pl.tiles_per_split;
     p.nkc = pl.nkc; p.KC = pl.KC;
+    fast_div_setup(p.splits, p.div_mul[0], p.div_shr[0]);
+    fast_div_setup(p.nkc, p.div_mul[1], p.div_shr[1]);
+    fast_div_setup(p.h, p.div_mul[2], p.div_shr[2]);
     p.c_log2 = (float)(1.4426950408889634 / sqrt((double)p.dk));
     p.O_part = reinterpret_cast<float*>(workspace);
     p.k_planes = reinterpret_cast<__nv_bfloat16*>(p.O_part + (int64_t)pl.splits * B * Ksel * d);
