@@ -352,7 +352,7 @@ def kernel_rooflines(model, batch, peaks, device):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16 slides, from the committed `ncu --set full` captures
-TRAFFIC = {"ffn_up": 1587.0e6, "attn": 714.4e6}
+TRAFFIC = {"ffn_up": 1585.0e6, "attn": 673.8e6}      # profiles/r02g_gemm_tc_ncu_full.csv, r02g_attn_ncu_full.csv
 
 
 # ------------------------------------------------------------------ other BASELINE configs, timed once each (rank 0, N = 1)

@@ -2,7 +2,7 @@
 # ncu evidence for one round (B200_PROFILING.md recipe): launch list of a short bench + full captures of the top kernels.
 mkdir -p gpurun_out
 R=${1:-r01}
-BENCH="python bench.py --steps 2 --warmup 3 --no-graph --skip-cpu --skip-kernels --skip-train"
+BENCH="python bench.py --steps 2 --warmup 3 --sustain-steps 0 --no-graph --skip-cpu --skip-kernels --skip-train --skip-extras"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$R.csv $BENCH > gpurun_out/ncu_launch_$R.log 2>&1
 echo "launch list exit $?"
 # the five gemm_tc launches of the second forward: Q|V, key proj, out proj, FFN-up, FFN-down
