@@ -17,8 +17,10 @@ import torch
 from . import engine, ops
 
 
-#: attention backward as dense tcgen05 GEMMs over head-block operands (SNUFFY_B200_ATTN_BWD=simt keeps the SIMT products)
-ATTN_BWD_TC = __import__("os").environ.get("SNUFFY_B200_ATTN_BWD", "tc") != "simt"
+#: attention backward: "fused" (default: one tcgen05 kernel, csrc/attn_bwd_tc.cu, where the shape allows), "tc" (dense tcgen05
+#: GEMMs over block-diagonal head operands + row kernels), "simt" (fp32 SIMT products)
+ATTN_BWD = __import__("os").environ.get("SNUFFY_B200_ATTN_BWD", "fused")
+ATTN_BWD_TC = ATTN_BWD != "simt"
 
 
 def _flat(t: torch.Tensor, d: int) -> torch.Tensor:
@@ -181,7 +183,9 @@ class EncoderLayerFunction(torch.autograd.Function):
             d_wo = ops.matmul_tn(dz, t.o)
         d_o = dx_gemm(dz, w.wo, w.wot_planes, d)                                   # [B*Ksel, d]
         q, v = t.qv[:, :d], t.qv[:, d:]
-        if tc and t.qvp is not None and ATTN_BWD_TC and ops.sparse_attn_bwd_tc_supported(B, N, ksel, heads, d):
+        if tc and t.qvp is not None and ATTN_BWD == "fused" and ops.sparse_attn_bwd_fused_supported(B, N, ksel, heads, d):
+            dq, dv, dkp, dqv = ops.sparse_attn_bwd_fused(t.qvp, t.kp, d_o, t.attn_stats, B, N, ksel, heads, d, t.drop)
+        elif tc and t.qvp is not None and ATTN_BWD_TC and ops.sparse_attn_bwd_tc_supported(B, N, ksel, heads, d):
             dq, dv, dkp, dqv = ops.sparse_attn_bwd_tc(t.qvp, t.qv, t.kp, d_o, t.attn_stats, B, N, ksel, heads, d, t.drop, passes)
         else:
             dq, dv, dkp, dqv = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)

@@ -641,6 +641,31 @@ def block_diag_rows(src: torch.Tensor, h: int) -> torch.Tensor:
     return out
 
 
+_bwd_fused_ws = functools.lru_cache(maxsize=None)(lambda B, N, Ksel, h, d: lib.snuffy_sparse_attn_bwd_tc_workspace(B, N, Ksel, h, d))
+
+
+def sparse_attn_bwd_fused_supported(B: int, N: int, Ksel: int, h: int, d: int) -> bool:
+    return d % 32 == 0 and _bwd_fused_ws(B, N, Ksel, h, d) >= 0
+
+
+def sparse_attn_bwd_fused(qvp: Planes, kp: torch.Tensor, d_o: torch.Tensor, stats: torch.Tensor, B: int, N: int, Ksel: int,
+                          h: int, d: int, drop: Tuple[float, int, int] = (0.0, 0, 0)):
+    """The attention backward as ONE tcgen05 kernel (csrc/attn_bwd_tc.cu) on the forward's Q|V planes and saved statistics.
+    Returns (dQ, dV (column halves of dQV), dKp [B*Ksel, d], dQV [B*N, 2d]) like sparse_attn_bwd."""
+    kp, d_o, stats = _f32(kp, "kp"), _f32(d_o, "d_o"), _f32(stats, "stats")
+    dev = kp.device
+    ws_bytes = _bwd_fused_ws(B, N, Ksel, h, d)
+    if ws_bytes < 0:
+        raise ValueError("shape not served by the fused attention backward")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    dqv = torch.empty(B * N, 2 * d, dtype=torch.float32, device=dev)
+    dkp = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
+    check(lib.snuffy_sparse_attn_bwd_tc(qvp.ptr, qvp.stride, qvp.K, 0, d, kp.data_ptr(), d_o.data_ptr(), stats.data_ptr(), B, N,
+                                        Ksel, h, d, float(drop[0]), drop[1] & _U64, drop[2] & _U64, dqv.data_ptr(), dkp.data_ptr(),
+                                        ws.data_ptr(), ws_bytes, _stream()), "snuffy_sparse_attn_bwd_tc")
+    return dqv[:, :d], dqv[:, d:], dkp, dqv
+
+
 def sparse_attn_bwd_tc_supported(B: int, N: int, Ksel: int, h: int, d: int) -> bool:
     return d % 32 == 0 and (d // h) % 4 == 0 and (h * Ksel) % 8 == 0 and h * Ksel <= 4096
 

@@ -397,3 +397,28 @@ def test_sparse_attention_backward_tensor_core(ops, B, n, ks, h, d, p):
     assert _rel(dq.double(), rq.double()) < 1e-4 and _rel(dv.double(), rv.double()) < 1e-4
     assert _rel(dkp.double(), rkp.double()) < 1e-4
     assert torch.equal(dqv[:, :d], dq) and torch.equal(dqv[:, d:], dv)
+
+
+@pytest.mark.parametrize("B,n,ks,h,d,p", [(1, 1000, 200, 8, 512, 0.0), (2, 300, 64, 2, 64, 0.0), (1, 1000, 200, 8, 512, 0.1),
+                                          (3, 200, 40, 4, 128, 0.1), (1, 500, 208, 4, 256, 0.2), (2, 384, 8, 4, 128, 0.3),
+                                          (1, 130, 100, 2, 192, 0.0), (2, 1000, 50, 1, 128, 0.0)])
+def test_sparse_attention_backward_fused(ops, B, n, ks, h, d, p):
+    """The one-kernel tcgen05 attention backward (csrc/attn_bwd_tc.cu) == the fp32 SIMT backward of the same forward (same
+    saved statistics, same dropout draw): dQ, dV, dKp within 1e-4 of each tensor's max-abs.  Shapes cover bags that start
+    inside a 128-row tile, head sizes 32 / 64 / 96 / 128 (stacked and plain operands) and padded key counts."""
+    assert ops.sparse_attn_bwd_fused_supported(B, n, ks, h, d)
+    g = torch.Generator(device="cuda").manual_seed(n + ks)
+    qv = torch.randn(B * n, 2 * d, device="cuda", generator=g)
+    kp = torch.randn(B * ks, d, device="cuda", generator=g)
+    d_o = torch.randn(B * ks, d, device="cuda", generator=g)
+    q, v = qv[:, :d], qv[:, d:]
+    drop = (p, 5, 9)
+    _, _, stats = ops.sparse_attn(q, v, kp, B, n, ks, h, want_probs=False, want_stats=True)
+    _, qvp, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    dq, dv, dkp, dqv = ops.sparse_attn_bwd_fused(qvp, kp, d_o, stats, B, n, ks, h, d, drop)
+    rq, rv, rkp, _ = ops.sparse_attn_bwd(q, v, kp, d_o, stats, B, n, ks, h, drop)
+    torch.cuda.synchronize()
+    assert _rel(dv.double(), rv.double()) < 1e-4, _rel(dv.double(), rv.double())
+    assert _rel(dq.double(), rq.double()) < 1e-4, _rel(dq.double(), rq.double())
+    assert _rel(dkp.double(), rkp.double()) < 1e-4, _rel(dkp.double(), rkp.double())
+    assert not ops.sparse_attn_bwd_fused_supported(1, 1000, 256, 8, 512)          # Ksel > 224: the GEMM formulation serves it
