@@ -167,8 +167,10 @@ int64_t snuffy_sparse_attn_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int6
 int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0,
                               int64_t v_col0, const float* Kp, int64_t B, int64_t N, int64_t Ksel,
                               int64_t h, int64_t d, float dropout_p, uint64_t seed, uint64_t offset,
-                              float* O, float* P_out, float* stats_out, void* workspace,
+                              float* O, float* P_out, float* stats_out, uint8_t* drop_mask, void* workspace,
                               int64_t workspace_bytes, snuffy_stream_t stream);
+/* drop_mask (optional, with dropout_p > 0): [B, h, N, ceil(Ksel / 8)] bytes, bit e of byte g = keep flag of key 8 g + e —
+ * the draw as the forward made it, read back by snuffy_sparse_attn_bwd_tc instead of hashing every score again.        */
 
 /* ---- a15: DSMIL critical-instance pooling   (dsmil.py:83-91: mm, softmax over dim 0, mm, Conv1d)       */
 int64_t snuffy_dsmil_workspace(int64_t N, int64_t d, int64_t C);
@@ -235,14 +237,15 @@ int snuffy_scatter_add_rows(float* dx, const int64_t* idx, const float* src, int
 /* Backward of snuffy_sparse_attn_tc_fwd in ONE kernel (autograd of snuffy.py:160-168): S and P are recomputed per 128-query
  * tile from the saved (row max, 1 / row sum); dV = P~ dO, G = V dO^T, dS = P o (D o G - V . dV) / sqrt(dk), dQ = dS Kp and
  * dKp^T = Q^T dS (accumulated in TMEM over the tiles) never leave the SM.  dQV [B*N, 2d] = dQ | dV, dKp [B*Ksel, d].
+ * With dropout_p > 0 the keep bits come from `drop_mask` as snuffy_sparse_attn_tc_fwd wrote them.
  * snuffy_sparse_attn_bwd_tc_workspace returns -1 for shapes it does not serve (Ksel > 224, head size not a multiple of 32 or
  * > 128): use the block-diagonal GEMM formulation below.                                                          */
 int64_t snuffy_sparse_attn_bwd_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d);
 int snuffy_sparse_attn_bwd_tc(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0,
                               int64_t v_col0, const float* Kp, const float* dO, const float* stats, int64_t B,
-                              int64_t N, int64_t Ksel, int64_t h, int64_t d, float dropout_p, uint64_t seed,
-                              uint64_t offset, float* dQV, float* dKp, void* workspace, int64_t workspace_bytes,
-                              snuffy_stream_t stream);
+                              int64_t N, int64_t Ksel, int64_t h, int64_t d, float dropout_p,
+                              const uint8_t* drop_mask, float* dQV, float* dKp, void* workspace,
+                              int64_t workspace_bytes, snuffy_stream_t stream);
 /* Attention backward on tensor cores (autograd of snuffy.py:160-168): all heads of a bag are contracted by one dense
  * tcgen05 GEMM against head-block operands Kbd[(j,k), c] = Kp[k, c] on head j's columns, 0 elsewhere.
  * snuffy_attn_seg_bwd: the row-local pieces on S_all [N, h*Ksel] (mode 0: P~, mode 1: G <- dS).  planes != NULL

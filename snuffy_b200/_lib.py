@@ -48,7 +48,7 @@ _SIGNATURES = {
     "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),
     "snuffy_sparse_attn_fwd": (c_int, [P, I, P, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
     "snuffy_sparse_attn_tc_workspace": (c_int64, [I, I, I, I, I]),
-    "snuffy_sparse_attn_tc_fwd": (c_int, [P, I, I, I, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),
+    "snuffy_sparse_attn_tc_fwd": (c_int, [P, I, I, I, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, P, I, P]),
     "snuffy_dsmil_workspace": (c_int64, [I, I, I]),
     "snuffy_dsmil_pool_fwd": (c_int, [P, P, P, P, P, I, I, I, I, P, P, P, P, P, I, P]),
     "snuffy_select_topk_varlen": (c_int, [P, P, I, I, I, I, P, P, P]),
@@ -74,7 +74,7 @@ _SIGNATURES = {
     "snuffy_gemm_tc_actgrad": (c_int, [P, I, P, I, I, I, I, c_int, P, I, c_int, c_float, c_uint64, c_uint64, P, I, P, I, P]),
     "snuffy_attn_seg_bwd": (c_int, [P, P, I, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P, I, P]),
     "snuffy_sparse_attn_bwd_tc_workspace": (c_int64, [I, I, I, I, I]),
-    "snuffy_sparse_attn_bwd_tc": (c_int, [P, I, I, I, I, P, P, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, I, P]),
+    "snuffy_sparse_attn_bwd_tc": (c_int, [P, I, I, I, I, P, P, P, I, I, I, I, I, c_float, P, P, P, P, I, P]),
     "snuffy_softmax_cols_bwd": (c_int, [P, P, I, I, c_float, P, P]),
     "snuffy_mil_loss": (c_int, [P, P, P, P, I, I, I, c_float, P, c_float, P, P, P, P, P, P, P, P]),
     "snuffy_rng_advance": (c_int, [P, c_uint64, P]),

@@ -183,8 +183,10 @@ class EncoderLayerFunction(torch.autograd.Function):
             d_wo = ops.matmul_tn(dz, t.o)
         d_o = dx_gemm(dz, w.wo, w.wot_planes, d)                                   # [B*Ksel, d]
         q, v = t.qv[:, :d], t.qv[:, d:]
-        if tc and t.qvp is not None and ATTN_BWD == "fused" and ops.sparse_attn_bwd_fused_supported(B, N, ksel, heads, d):
-            dq, dv, dkp, dqv = ops.sparse_attn_bwd_fused(t.qvp, t.kp, d_o, t.attn_stats, B, N, ksel, heads, d, t.drop)
+        if tc and t.qvp is not None and ATTN_BWD == "fused" and ops.sparse_attn_bwd_fused_supported(B, N, ksel, heads, d) \
+                and (t.drop[0] == 0 or t.attn_mask is not None):
+            dq, dv, dkp, dqv = ops.sparse_attn_bwd_fused(t.qvp, t.kp, d_o, t.attn_stats, B, N, ksel, heads, d, t.drop[0],
+                                                         t.attn_mask)
         elif tc and t.qvp is not None and ATTN_BWD_TC and ops.sparse_attn_bwd_tc_supported(B, N, ksel, heads, d):
             dq, dv, dkp, dqv = ops.sparse_attn_bwd_tc(t.qvp, t.qv, t.kp, d_o, t.attn_stats, B, N, ksel, heads, d, t.drop, passes)
         else:

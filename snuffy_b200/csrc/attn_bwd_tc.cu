@@ -41,6 +41,13 @@ __device__ __forceinline__ uint32_t fast_div_b(uint32_t n, int d, uint32_t mul, 
     return d == 1 ? n : __umulhi(n, mul) >> shr;
 }
 
+#ifdef ATTN_DEBUG_TIMING
+__device__ long long g_attnb_dbg[64 * 8];          // clock64 stamps of CTA 0, row warp 2 lane 0: [tile < 64][8 stamps]
+#define DBGB(t, k) do { if (blockIdx.x == 0 && warp == 2 && lane == 0 && (t) < 64) g_attnb_dbg[(t) * 8 + (k)] = clock64(); } while (0)
+#else
+#define DBGB(t, k) do { } while (0)
+#endif
+
 struct AttnBwdParams {
     const __nv_bfloat16* planes; int64_t plane_stride;   // the forward's Q|V planes over [rows, ldk]
     int nkb, q_kb0, v_kb0;
@@ -52,7 +59,7 @@ struct AttnBwdParams {
     uint32_t div_mul[2], div_shr[2];                     // item -> (split, head, bag)
     uint32_t d_col, c_col;                               // TMEM columns of D and C
     float c_log2, scale;                                 // log2(e) / sqrt(dk), 1 / sqrt(dk)
-    float drop_p; uint64_t seed, offset;
+    float drop_p; const uint8_t* drop_mask;              // keep bits as the forward drew them: [B, h, N, ceil(Ksel / 8)]
     float* dqv;                                          // [B*N, 2d]: dQ | dV
     float* dkp_part;                                     // [splits][B*Ksel][d]
 };
@@ -62,11 +69,12 @@ __global__ void __launch_bounds__(256)
 attn_bwd_planes_kernel(const AttnBwdParams p) {
     const int blk = blockIdx.x, j = blk % p.h, b = blk / p.h;
     const float* srcm = blockIdx.y ? p.dO : p.Kp;
-    __nv_bfloat16* out = (blockIdx.y ? p.do_planes : p.k_planes) + (size_t)blk * 2 * ((size_t)p.KP * p.dk);
-    const size_t plane = (size_t)p.KP * p.dk;
-    const int units = p.KP * (p.dk / 8);
+    const int KPS = p.KP + 1;                                // padded group stride (see the kernel below)
+    const size_t plane = (size_t)KPS * p.dk;
+    __nv_bfloat16* out = (blockIdx.y ? p.do_planes : p.k_planes) + (size_t)blk * 2 * plane;
+    const int units = KPS * (p.dk / 8);
     for (int idx = threadIdx.x; idx < units; idx += blockDim.x) {
-        const int key = idx % p.KP, kg = idx / p.KP;
+        const int key = idx % KPS, kg = idx / KPS;
         bf16x8 hi, lo;
         if (key < p.Ksel) {
             const float* src = srcm + ((int64_t)b * p.Ksel + key) * p.d + j * p.dk + kg * 8;
@@ -106,7 +114,10 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
     const int dk = p.dk, KP = p.KP;
     const uint32_t P_PLANE = (uint32_t)KP * 256u;            // [KP/8 key groups][128 queries][8 keys] bf16
     const uint32_t QV_PLANE = (uint32_t)AB_TILE * dk * 2u;   // [dk/8][128][8] bf16
-    const uint32_t KP_PLANE = (uint32_t)KP * dk * 2u;        // [dk/8][KP][8] bf16
+    // key / dO planes [dk/8][KP + 1][8] bf16: the 8-column groups are (KP + 1) * 16 bytes apart, an odd number of 16-byte units,
+    // so that the MN-major reads of dV = P~ dO / dQ = dS Kp (one 16-byte unit from each of the dk / 8 groups) spread over the banks
+    const uint32_t KPS = (uint32_t)KP + 1u;
+    const uint32_t KP_PLANE = KPS * dk * 2u;
     // order matters: the M = 128 stacked A operand of dKp^T = Q^T dS reads 16 groups of 2 KB from the start of sQ
     unsigned char* sKD = ab_smem;
     unsigned char* sQ = sKD + 2 * KP_PLANE;
@@ -154,7 +165,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
         const int64_t t0 = t_first + (int64_t)split * p.tiles_per_split;
         const int64_t t1 = min(t_last, t0 + p.tiles_per_split);
         const int ntiles = (int)max((int64_t)0, t1 - t0);
-        const size_t head_planes = ((size_t)b * p.h + j) * 2 * ((size_t)KP * dk);
+        const size_t head_planes = ((size_t)b * p.h + j) * 2 * ((size_t)KPS * dk);
 
         if (warp == 0) {
             // ------------------------------------------------ Q producer
@@ -190,7 +201,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 if (lane == 0) {
                     mbar_expect_tx(kd_full, 2 * KP_PLANE);
                     bulk_g2s(smem_u32(sKD), src, KP_PLANE, kd_full);
-                    bulk_g2s(smem_u32(sKD) + KP_PLANE, src + (size_t)KP * dk, KP_PLANE, kd_full);
+                    bulk_g2s(smem_u32(sKD) + KP_PLANE, src + (size_t)KPS * dk, KP_PLANE, kd_full);
                 }
                 __syncwarp();
             }
@@ -202,14 +213,14 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
             // descriptors of k-step 0 (csrc/tc_ptx.cuh: (address, LBO, SBO)); a k-step advances the start-address field
             const uint64_t q_hi = make_smem_desc(smem_u32(sQ), 2048, 128), q_lo = make_smem_desc(smem_u32(sQ) + QV_PLANE, 2048, 128);
             const uint64_t v_hi = make_smem_desc(smem_u32(sV), 2048, 128), v_lo = make_smem_desc(smem_u32(sV) + QV_PLANE, 2048, 128);
-            const uint64_t kd_hi = make_smem_desc(smem_u32(sKD), KP * 16, 128), kd_lo = make_smem_desc(smem_u32(sKD) + KP_PLANE, KP * 16, 128);
+            const uint64_t kd_hi = make_smem_desc(smem_u32(sKD), KPS * 16, 128), kd_lo = make_smem_desc(smem_u32(sKD) + KP_PLANE, KPS * 16, 128);
             // the same key / dO planes as the MN-major B operand [K = key, N = dv] of dQ = dS Kp and dV = P~ dO
-            const uint64_t kdn_hi = make_smem_desc(smem_u32(sKD), 128, KP * 16), kdn_lo = make_smem_desc(smem_u32(sKD) + KP_PLANE, 128, KP * 16);
+            const uint64_t kdn_hi = make_smem_desc(smem_u32(sKD), 128, KPS * 16), kdn_lo = make_smem_desc(smem_u32(sKD) + KP_PLANE, 128, KPS * 16);
             // P~ / dS planes: K-major A operand [M = query, K = key] of dV / dQ, MN-major B operand [K = query, N = key] of dKp^T
             const uint64_t ps_hi = make_smem_desc(smem_u32(sPS), 2048, 128), ps_lo = make_smem_desc(smem_u32(sPS) + P_PLANE, 2048, 128);
             const uint64_t psn_hi = make_smem_desc(smem_u32(sPS), 128, 2048), psn_lo = make_smem_desc(smem_u32(sPS) + P_PLANE, 128, 2048);
             const uint64_t qn_hi = make_smem_desc(smem_u32(sQ), 128, 2048), qn_lo = make_smem_desc(smem_u32(sQ) + QV_PLANE, 128, 2048);
-            const uint64_t qv_step = (2 * 2048) >> 4, kd_step = (uint64_t)(2 * KP * 16) >> 4, mn_step = 256 >> 4;
+            const uint64_t qv_step = (2 * 2048) >> 4, kd_step = (uint64_t)(2 * KPS * 16) >> 4, mn_step = 256 >> 4;
             const uint32_t tA = tmem_base, tD = tmem_base + p.d_col, tC = tmem_base + p.c_col;
 
             mbar_wait(kd_full, kdc & 1); ++kdc;                                   // this head's key planes
@@ -316,7 +327,8 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
             // this thread's share of the dk output columns of dV / dQ (8-column groups)
             const int cgroups = dk / 8, cbase = cgroups / AB_PARTS, crem = cgroups % AB_PARTS;
             const int c0 = part * cbase + min(part, crem), nc = cbase + (part < crem ? 1 : 0);
-            const DrawKey dkey = rng_resolve(p.seed, p.offset);
+            const int mbytes = (p.Ksel + 7) / 8;
+            const float keep_scale = DROP ? 1.f / (1.f - p.drop_p) : 1.f;
             for (int t = 0; t < ntiles; ++t, ++it) {
                 const int64_t g = (t0 + t) * AB_TILE + rr;
                 const bool valid = g >= g_lo && g < g_hi;
@@ -326,9 +338,18 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 if (valid) st = __ldg(reinterpret_cast<const float2*>(p.stats) + srow);
                 // exp(s / sqrt(dk) - max) / sum = exp2(s c_log2 - max log2 e) * inv; other bags' rows / padding: exactly 0
                 const float mc = valid ? st.x * 1.4426950408889634f : INFINITY, inv = valid ? st.y : 0.f;
+                // keep bits of this thread's keys (byte = one 8-key group), fetched while the S MMAs run
+                uint32_t kbits[(AB_VG + 3) / 4] = {};
+                if (DROP && valid) {
+                    const uint8_t* mrow = p.drop_mask + srow * mbytes + g0;
+#pragma unroll
+                    for (int gi = 0; gi < AB_VG; ++gi)
+                        if (gi < ng && g0 + gi < mbytes) kbits[gi >> 2] |= (uint32_t)__ldg(mrow + gi) << (8 * (gi & 3));
+                }
                 // ---- (a) scores -> registers -> P (kept) -> P~ planes
                 mbar_wait(a_full, 0);
                 tc_fence_after();
+                DBGB(it, 0);
                 float v[AB_VG * 8];
                 tc_ld32(lane_addr + (uint32_t)(g0 * 8), *reinterpret_cast<float(*)[32]>(v));
                 if (ng > 4) tc_ld32(lane_addr + (uint32_t)(g0 * 8 + 32), *reinterpret_cast<float(*)[32]>(v + 32));
@@ -337,15 +358,21 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_free);
+                // padding keys (Q . 0 = 0) get -inf once: exp2 turns them into exact zeros, the loops need no masks
+                if ((g0 + ng) * 8 > p.Ksel) {
+#pragma unroll
+                    for (int gi = 0; gi < AB_VG; ++gi) {
+                        if (gi < ng && (g0 + gi) * 8 + 8 > p.Ksel) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) if ((g0 + gi) * 8 + e >= p.Ksel) v[gi * 8 + e] = -INFINITY;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int gi = 0; gi < AB_VG; ++gi) {
                     if (gi < ng) {
-                        const int kb = (g0 + gi) * 8;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float pe = ex2_approx_b(fmaf(v[gi * 8 + e], p.c_log2, -mc)) * inv;
-                            v[gi * 8 + e] = (kb + 8 <= p.Ksel || kb + e < p.Ksel) ? pe : 0.f;      // padding keys
-                        }
+                        for (int e = 0; e < 8; ++e) v[gi * 8 + e] = ex2_approx_b(fmaf(v[gi * 8 + e], p.c_log2, -mc)) * inv;
                     }
                 }
                 mbar_wait(ps_empty, 1);                          // fill 2 it: dKp^T of the previous tile has consumed dS
@@ -357,7 +384,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             w[e] = v[gi * 8 + e];
-                            if (DROP) w[e] *= drop_keep_scale(dkey.seed, dkey.offset, (uint64_t)srow * p.Ksel + kgp * 8 + e, p.drop_p);
+                            if (DROP) w[e] = (kbits[gi >> 2] >> (8 * (gi & 3) + e)) & 1u ? w[e] * keep_scale : 0.f;
                         }
                         split_store8(w, sPS + (size_t)kgp * 2048 + rr * 16, sPS + P_PLANE + (size_t)kgp * 2048 + rr * 16);
                     }
@@ -365,10 +392,12 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ps_full);
+                DBGB(it, 1);
                 // ---- (b) dV out, delta = V[n, :] . dV[n, :] (this thread: nc groups of 8 columns; the parts exchange)
                 mbar_wait(v_full, it & 1);
                 mbar_wait(d_full, 0);
                 tc_fence_after();
+                DBGB(it, 2);
                 float dpart = 0.f;
                 float* drow = p.dqv + g * (2 * (int64_t)p.d) + j * dk;
                 for (int ci = 0; ci < nc; ++ci) {
@@ -385,10 +414,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                         dpart = fmaf(va, o[2 * q], dpart);
                         dpart = fmaf(vb, o[2 * q + 1], dpart);
                     }
-                    if (valid) {
-                        *reinterpret_cast<float4*>(drow + p.d + cg * 8) = make_float4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<float4*>(drow + p.d + cg * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                    }
+                    if (valid) st_global_v8(drow + p.d + cg * 8, o);
                 }
                 tc_fence_before();
                 sRed[part * 128 + rr] = dpart;
@@ -398,10 +424,12 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 for (int q = 0; q < AB_PARTS; ++q) delta += sRed[q * 128 + rr];
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(d_free); mbar_arrive(v_empty); }
+                DBGB(it, 3);
                 // ---- (c) dS = P o (D o G - delta) / sqrt(dk) -> planes (over P~: dV has consumed it)
                 mbar_wait(a_full, 1);
                 mbar_wait(ps_empty, 0);                          // fill 2 it + 1
                 tc_fence_after();
+                DBGB(it, 4);
 #pragma unroll
                 for (int gi = 0; gi < AB_VG; ++gi) {
                     if (gi < ng) {
@@ -411,7 +439,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             float dp = gv[e];
-                            if (DROP) dp *= drop_keep_scale(dkey.seed, dkey.offset, (uint64_t)srow * p.Ksel + kgp * 8 + e, p.drop_p);
+                            if (DROP) dp = (kbits[gi >> 2] >> (8 * (gi & 3) + e)) & 1u ? dp * keep_scale : 0.f;
                             w[e] = v[gi * 8 + e] * (dp - delta) * p.scale;
                         }
                         split_store8(w, sPS + (size_t)kgp * 2048 + rr * 16, sPS + P_PLANE + (size_t)kgp * 2048 + rr * 16);
@@ -421,21 +449,21 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(a_free); mbar_arrive(ps_full); }
+                DBGB(it, 5);
                 // ---- (d) dQ out
                 mbar_wait(d_full, 1);
                 tc_fence_after();
+                DBGB(it, 6);
                 for (int ci = 0; ci < nc; ++ci) {
                     const int cg = c0 + ci;
                     float o[8];
                     tc_ld8(lane_addr + p.d_col + (uint32_t)(cg * 8), o);
-                    if (valid) {
-                        *reinterpret_cast<float4*>(drow + cg * 8) = make_float4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<float4*>(drow + cg * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                    }
+                    if (valid) st_global_v8(drow + cg * 8, o);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_free);
+                DBGB(it, 7);
             }
             // ---- item epilogue: dKp^T (TMEM lane = dv, column = key) -> this split's partial (like the forward's O^T read-out)
             mbar_wait(c_full, item_no & 1);
@@ -513,7 +541,7 @@ static AttnBwdPlan plan_attn_bwd(int64_t B, int64_t N, int64_t Ksel, int64_t h, 
     if (pl.c_col + (uint32_t)KP > 512u) return pl;                     // TMEM: scores / G, dV / dQ, dKp^T
     size_t stage = (size_t)2 * KP * 256;                               // P~ / dS planes, also the fp32 staging of the dKp read-out
     if (2 * dk <= 128) { const size_t st = (((size_t)(KP + 32) * dk * 4) + 127) & ~(size_t)127; if (st > stage) stage = st; }
-    pl.smem = (size_t)2 * KP * dk * 2 + (size_t)4 * AB_TILE * dk * 2 + stage + 17 * 8 + 16 + AB_PARTS * 128 * 4;
+    pl.smem = (size_t)2 * (KP + 1) * dk * 2 + (size_t)4 * AB_TILE * dk * 2 + stage + 17 * 8 + 16 + AB_PARTS * 128 * 4;
     if (stage != (size_t)2 * KP * 256) return pl;                      // keep the carve-up of the kernel (bars follow 2 P planes)
     if (pl.smem > 227 * 1024) return pl;
     const int64_t tiles = (N + AB_TILE - 1) / AB_TILE + 1;
@@ -547,15 +575,15 @@ extern "C" {
 int64_t snuffy_sparse_attn_bwd_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d) {
     const AttnBwdPlan pl = plan_attn_bwd(B, N, Ksel, h, d);
     if (!pl.ok) return -1;
-    return (int64_t)pl.splits * B * Ksel * d * 4 + (int64_t)2 * B * pl.KP * d * 4 + 256;
+    return (int64_t)pl.splits * B * Ksel * d * 4 + (int64_t)2 * B * (pl.KP + 1) * d * 4 + 256;
 }
 
 // Backward of snuffy_sparse_attn_tc_fwd in one kernel: dQV [B*N, 2d] (dQ | dV), dKp [B*Ksel, d].
 // qv_planes: the forward's Q|V planes; Kp, dO: fp32 [B*Ksel, d]; stats [B, h, N, 2] from the forward (stats_out);
-// (dropout_p, seed, offset): the forward's attention-dropout draw.
+// dropout_p > 0: drop_mask = the keep bits snuffy_sparse_attn_tc_fwd wrote for the same draw.
 int snuffy_sparse_attn_bwd_tc(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,
                               const float* Kp, const float* dO, const float* stats, int64_t B, int64_t N, int64_t Ksel,
-                              int64_t h, int64_t d, float dropout_p, uint64_t seed, uint64_t offset, float* dQV, float* dKp,
+                              int64_t h, int64_t d, float dropout_p, const uint8_t* drop_mask, float* dQV, float* dKp,
                               void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
     SNUFFY_REQUIRE(qv_planes && Kp && dO && stats && dQV && dKp && workspace, "snuffy_sparse_attn_bwd_tc: null pointer");
     const AttnBwdPlan pl = plan_attn_bwd(B, N, Ksel, h, d);
@@ -566,6 +594,7 @@ int snuffy_sparse_attn_bwd_tc(const void* qv_planes, int64_t plane_stride, int64
     SNUFFY_REQUIRE(workspace_bytes >= snuffy_sparse_attn_bwd_tc_workspace(B, N, Ksel, h, d),
                    "snuffy_sparse_attn_bwd_tc: workspace too small");
     SNUFFY_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "snuffy_sparse_attn_bwd_tc: dropout_p out of range");
+    SNUFFY_REQUIRE(dropout_p == 0.f || drop_mask, "snuffy_sparse_attn_bwd_tc: dropout needs the forward's keep-bit mask");
     SNUFFY_REQUIRE((uintptr_t)Kp % 16 == 0 && (uintptr_t)dO % 16 == 0 && (uintptr_t)dQV % 16 == 0 && (uintptr_t)dKp % 16 == 0 &&
                    (uintptr_t)workspace % 16 == 0 && (uintptr_t)stats % 8 == 0 && d % 8 == 0,
                    "snuffy_sparse_attn_bwd_tc: pointers must be 16-byte aligned");
@@ -580,11 +609,11 @@ int snuffy_sparse_attn_bwd_tc(const void* qv_planes, int64_t plane_stride, int64
     p.d_col = pl.d_col; p.c_col = pl.c_col;
     p.c_log2 = (float)(1.4426950408889634 / sqrt((double)p.dk));
     p.scale = (float)(1.0 / sqrt((double)p.dk));
-    p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
+    p.drop_p = dropout_p; p.drop_mask = drop_mask;
     p.dqv = dQV;
     p.dkp_part = reinterpret_cast<float*>(workspace);
     p.k_planes = reinterpret_cast<__nv_bfloat16*>(p.dkp_part + (int64_t)pl.splits * B * Ksel * d);
-    p.do_planes = p.k_planes + (int64_t)B * pl.KP * d * 2;
+    p.do_planes = p.k_planes + (int64_t)B * (pl.KP + 1) * d * 2;
     attn_bwd_planes_kernel<<<dim3((unsigned)(B * h), 2), 256, 0, stream>>>(p);
     if (dropout_p > 0.f) {
         SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&attn_bwd_tc_kernel<true>), (int)pl.smem));
@@ -596,6 +625,12 @@ int snuffy_sparse_attn_bwd_tc(const void* qv_planes, int64_t plane_stride, int64
     launch_fold_partials(p.dkp_part, pl.splits, B * Ksel * d / 4, dKp, stream);
     return check_launch("snuffy_sparse_attn_bwd_tc", 3);
 }
+
+#ifdef ATTN_DEBUG_TIMING
+int snuffy_attn_bwd_debug_read(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_attnb_dbg, sizeof(g_attnb_dbg)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // extern "C"
 #pragma GCC visibility pop

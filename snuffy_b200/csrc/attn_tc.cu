@@ -92,6 +92,7 @@ struct AttnTcParams {
     float* O_part;                    // [splits, B*Ksel, d]
     float* P_out;                     // [B, h, N, Ksel] or null (pre-dropout)
     float* stats_out;                 // [B, h, N, 2] (row max of the scaled scores, 1 / row sum) or null
+    uint8_t* drop_mask;               // [B, h, N, ceil(Ksel / 8)] keep bits of the attention dropout (bit e of byte g = key 8 g + e) or null
     float drop_p; uint64_t seed, offset;
     const int64_t* cu_seqlens;        // packed variable-length bags: rows [cu[b], cu[b+1]) (null: b*N .. (b+1)*N)
 };
@@ -455,11 +456,16 @@ attn_tc_kernel(const AttnTcParams p) {
                             for (int e = 0; e < 8; ++e) if (kb + e < kvalid) po[e] = w[e];
                         }
                         if (EXTRA && p.drop_p > 0.f && valid) {
+                            uint32_t bits = 0;
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const uint64_t idx = ((uint64_t)srow * p.Ksel + key0 + kb + e);
-                                w[e] *= drop_keep_scale(dkey.seed, dkey.offset, idx, p.drop_p);
+                                const float m = drop_keep_scale(dkey.seed, dkey.offset, idx, p.drop_p);
+                                w[e] *= m;
+                                bits |= (m != 0.f ? 1u : 0u) << e;
                             }
+                            // the backward kernel reads the draw back instead of hashing every score again (twice)
+                            if (p.drop_mask && kb < kvalid) p.drop_mask[srow * ((p.Ksel + 7) / 8) + ((key0 + kb) >> 3)] = (uint8_t)bits;
                         }
                         // hi = truncated bf16 (exact), lo = bf16 of the exact remainder: integer/FMA pipes only
                         uint32_t hw[4], lw[4];
@@ -629,7 +635,8 @@ int64_t snuffy_sparse_attn_tc_workspace(int64_t B, int64_t N, int64_t Ksel, int6
 static int launch_attn_tc(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,
                           const float* Kp, int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d,
                           float dropout_p, uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
-                          void* workspace, int64_t workspace_bytes, const int64_t* cu_seqlens, cudaStream_t stream) {
+                          uint8_t* drop_mask, void* workspace, int64_t workspace_bytes, const int64_t* cu_seqlens,
+                          cudaStream_t stream) {
     SNUFFY_REQUIRE(qv_planes && Kp && O && workspace, "snuffy_sparse_attn_tc_fwd: null pointer");
     const AttnTcPlan pl = plan_attn_tc(B, N, Ksel, h, d);
     SNUFFY_REQUIRE(pl.ok, "snuffy_sparse_attn_tc_fwd: unsupported shape (h=%lld d=%lld Ksel=%lld)", (long long)h,
@@ -654,7 +661,7 @@ static int launch_attn_tc(const void* qv_planes, int64_t plane_stride, int64_t l
     p.O_part = reinterpret_cast<float*>(workspace);
     p.k_planes = reinterpret_cast<__nv_bfloat16*>(p.O_part + (int64_t)pl.splits * B * Ksel * d);
     p.stats_part = reinterpret_cast<float*>(p.k_planes + (int64_t)B * pl.nkc * pl.KP * d * 2);
-    p.P_out = P_out; p.stats_out = stats_out;
+    p.P_out = P_out; p.stats_out = stats_out; p.drop_mask = drop_mask;
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
     p.cu_seqlens = cu_seqlens;
     SNUFFY_REQUIRE((uintptr_t)workspace % 16 == 0, "snuffy_sparse_attn_tc_fwd: workspace must be 16-byte aligned");
@@ -679,9 +686,9 @@ static int launch_attn_tc(const void* qv_planes, int64_t plane_stride, int64_t l
 int snuffy_sparse_attn_tc_fwd(const void* qv_planes, int64_t plane_stride, int64_t ldk, int64_t q_col0, int64_t v_col0,
                               const float* Kp, int64_t B, int64_t N, int64_t Ksel, int64_t h, int64_t d,
                               float dropout_p, uint64_t seed, uint64_t offset, float* O, float* P_out, float* stats_out,
-                              void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+                              uint8_t* drop_mask, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
     return launch_attn_tc(qv_planes, plane_stride, ldk, q_col0, v_col0, Kp, B, N, Ksel, h, d, dropout_p, seed, offset, O, P_out,
-                          stats_out, workspace, workspace_bytes, nullptr, stream);
+                          stats_out, drop_mask, workspace, workspace_bytes, nullptr, stream);
 }
 
 // Packed variable-length bags (inference): the planes cover the packed [T, ldk] rows, bag b = rows
@@ -693,7 +700,7 @@ int snuffy_sparse_attn_tc_varlen_fwd(const void* qv_planes, int64_t plane_stride
                                      cudaStream_t stream) {
     SNUFFY_REQUIRE(cu_seqlens, "snuffy_sparse_attn_tc_varlen_fwd: null cu_seqlens");
     return launch_attn_tc(qv_planes, plane_stride, ldk, q_col0, v_col0, Kp, B, max_n, Ksel, h, d, 0.f, 0, 0, O, nullptr, nullptr,
-                          workspace, workspace_bytes, cu_seqlens, stream);
+                          nullptr, workspace, workspace_bytes, cu_seqlens, stream);
 }
 
 #ifdef ATTN_DEBUG_TIMING

@@ -130,6 +130,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 // holds 8 consecutive M (or N) elements, 8 consecutive k are 16 B apart, LBO = byte stride between 8-k groups,
 // SBO = byte stride between 8-element groups along M/N  (cute::UMMA canonical "INTERLEAVE" MN layout).
 
+// one 32-byte store (a whole sector: no partial-sector write for row-strided outputs)
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace snuffy

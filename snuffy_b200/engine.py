@@ -243,6 +243,7 @@ class LayerTape:
     drop_ff: Tuple[float, int, int] = (0.0, 0, 0)     # feed-forward hidden dropout                     snuffy.py:225
     drop_enc2: Tuple[float, int, int] = (0.0, 0, 0)   # sublayer[1] dropout on the FFN output           snuffy.py:110
     qvp: Optional[Planes] = None                      # Q|V as operand planes (tensor-core attention backward)
+    attn_mask: Optional[torch.Tensor] = None          # keep bits of the attention dropout as the forward drew them
 
 
 def tc_supported(d: int) -> bool:
@@ -328,11 +329,13 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     def draw(p):
         return (float(p),) + _RANDOM.next() if p > 0.0 else (0.0, 0, 0)
     drop, drop_enc1, drop_ff, drop_enc2 = draw(attn_dropout), draw(enc_dropout), draw(ff_dropout), draw(enc_dropout)
+    attn_mask = None
     if varlen is not None:
         o, probs, attn_stats = ops.sparse_attn_tc_varlen(qvp, kp, cu, bags, max_n, ksel_bag, heads, d), None, None
     elif attn_tc:
-        o, probs, attn_stats = ops.sparse_attn_tc(qvp, kp, B, N, Ksel, heads, d, want_probs=want_probs, want_stats=save,
-                                                  dropout_p=drop[0], seed=drop[1], offset=drop[2])
+        o, probs, attn_stats, attn_mask = ops.sparse_attn_tc(qvp, kp, B, N, Ksel, heads, d, want_probs=want_probs,
+                                                             want_stats=save, dropout_p=drop[0], seed=drop[1], offset=drop[2],
+                                                             want_mask=True)
     else:
         o, probs, attn_stats = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, N, Ksel, heads, want_probs=want_probs,
                                                want_stats=save, dropout_p=drop[0], seed=drop[1], offset=drop[2])
@@ -368,5 +371,5 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     if save:
         tape = LayerTape(sel=sel, row_map=row_map, xs=xs, xs_new=xs_new, kp=kp, qv=qv, o=o, ln1_stats=ln1_stats,
                          ln2_stats=ln2_stats, attn_stats=attn_stats, h_pre=h_pre, x_in=x, drop=drop, drop_enc1=drop_enc1,
-                         drop_ff=drop_ff, drop_enc2=drop_enc2, qvp=qvp if precision != "fp32" else None)
+                         drop_ff=drop_ff, drop_enc2=drop_enc2, qvp=qvp if precision != "fp32" else None, attn_mask=attn_mask)
     return x_next, probs, tape

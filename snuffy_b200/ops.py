@@ -308,8 +308,9 @@ def sparse_attn_tc_supported(B: int, N: int, Ksel: int, h: int, d: int) -> bool:
 
 def sparse_attn_tc(qv_planes: Planes, kp: torch.Tensor, B: int, N: int, Ksel: int, h: int, d: int, *,
                    want_probs: bool = True, want_stats: bool = False, dropout_p: float = 0.0, seed: int = 0,
-                   offset: int = 0):
-    """Tensor-core sparse attention on the Q|V planes written by the projection GEMM (planes over [B*N, 2d])."""
+                   offset: int = 0, want_mask: bool = False):
+    """Tensor-core sparse attention on the Q|V planes written by the projection GEMM (planes over [B*N, 2d]).
+    want_mask (with dropout): also returns the keep bits of the draw, [B, h, N, ceil(Ksel / 8)] uint8, for the fused backward."""
     kp = _f32(kp, "kp")
     dev = kp.device
     ws_bytes = lib.snuffy_sparse_attn_tc_workspace(B, N, Ksel, h, d)
@@ -319,9 +320,12 @@ def sparse_attn_tc(qv_planes: Planes, kp: torch.Tensor, B: int, N: int, Ksel: in
     o = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
     probs = torch.empty(B, h, N, Ksel, dtype=torch.float32, device=dev) if want_probs else None
     stats = torch.empty(B, h, N, 2, dtype=torch.float32, device=dev) if want_stats else None
+    mask = torch.empty(B, h, N, (Ksel + 7) // 8, dtype=torch.uint8, device=dev) if want_mask and dropout_p > 0 else None
     check(lib.snuffy_sparse_attn_tc_fwd(qv_planes.ptr, qv_planes.stride, qv_planes.K, 0, d, kp.data_ptr(), B, N, Ksel, h, d,
                                         float(dropout_p), seed & _U64, offset & _U64, o.data_ptr(), _ptr(probs),
-                                        _ptr(stats), ws.data_ptr(), ws_bytes, _stream()), "snuffy_sparse_attn_tc_fwd")
+                                        _ptr(stats), _ptr(mask), ws.data_ptr(), ws_bytes, _stream()), "snuffy_sparse_attn_tc_fwd")
+    if want_mask:
+        return o, probs, stats, mask
     return o, probs, stats
 
 
@@ -649,10 +653,13 @@ def sparse_attn_bwd_fused_supported(B: int, N: int, Ksel: int, h: int, d: int) -
 
 
 def sparse_attn_bwd_fused(qvp: Planes, kp: torch.Tensor, d_o: torch.Tensor, stats: torch.Tensor, B: int, N: int, Ksel: int,
-                          h: int, d: int, drop: Tuple[float, int, int] = (0.0, 0, 0)):
-    """The attention backward as ONE tcgen05 kernel (csrc/attn_bwd_tc.cu) on the forward's Q|V planes and saved statistics.
-    Returns (dQ, dV (column halves of dQV), dKp [B*Ksel, d], dQV [B*N, 2d]) like sparse_attn_bwd."""
+                          h: int, d: int, dropout_p: float = 0.0, mask: Optional[torch.Tensor] = None):
+    """The attention backward as ONE tcgen05 kernel (csrc/attn_bwd_tc.cu) on the forward's Q|V planes, saved statistics and
+    (with dropout) keep bits.  Returns (dQ, dV (column halves of dQV), dKp [B*Ksel, d], dQV [B*N, 2d]) like sparse_attn_bwd."""
     kp, d_o, stats = _f32(kp, "kp"), _f32(d_o, "d_o"), _f32(stats, "stats")
+    if dropout_p > 0 and (mask is None or mask.dtype != torch.uint8 or not mask.is_contiguous()
+                          or mask.numel() != B * h * N * ((Ksel + 7) // 8)):
+        raise ValueError("sparse_attn_bwd_fused: dropout needs the forward's keep-bit mask [B, h, N, ceil(Ksel / 8)] uint8")
     dev = kp.device
     ws_bytes = _bwd_fused_ws(B, N, Ksel, h, d)
     if ws_bytes < 0:
@@ -661,8 +668,8 @@ def sparse_attn_bwd_fused(qvp: Planes, kp: torch.Tensor, d_o: torch.Tensor, stat
     dqv = torch.empty(B * N, 2 * d, dtype=torch.float32, device=dev)
     dkp = torch.empty(B * Ksel, d, dtype=torch.float32, device=dev)
     check(lib.snuffy_sparse_attn_bwd_tc(qvp.ptr, qvp.stride, qvp.K, 0, d, kp.data_ptr(), d_o.data_ptr(), stats.data_ptr(), B, N,
-                                        Ksel, h, d, float(drop[0]), drop[1] & _U64, drop[2] & _U64, dqv.data_ptr(), dkp.data_ptr(),
-                                        ws.data_ptr(), ws_bytes, _stream()), "snuffy_sparse_attn_bwd_tc")
+                                        Ksel, h, d, float(dropout_p), _ptr(mask) if dropout_p > 0 else None, dqv.data_ptr(),
+                                        dkp.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "snuffy_sparse_attn_bwd_tc")
     return dqv[:, :d], dqv[:, d:], dkp, dqv
 
 

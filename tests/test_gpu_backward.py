@@ -413,9 +413,12 @@ def test_sparse_attention_backward_fused(ops, B, n, ks, h, d, p):
     d_o = torch.randn(B * ks, d, device="cuda", generator=g)
     q, v = qv[:, :d], qv[:, d:]
     drop = (p, 5, 9)
-    _, _, stats = ops.sparse_attn(q, v, kp, B, n, ks, h, want_probs=False, want_stats=True)
     _, qvp, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
-    dq, dv, dkp, dqv = ops.sparse_attn_bwd_fused(qvp, kp, d_o, stats, B, n, ks, h, d, drop)
+    # the tensor-core forward leaves the statistics and, with dropout, the keep bits of its draw for the backward
+    _, _, stats, mask = ops.sparse_attn_tc(qvp, kp, B, n, ks, h, d, want_probs=False, want_stats=True, dropout_p=p, seed=5,
+                                           offset=9, want_mask=True)
+    assert (mask is None) == (p == 0)
+    dq, dv, dkp, dqv = ops.sparse_attn_bwd_fused(qvp, kp, d_o, stats, B, n, ks, h, d, p, mask)
     rq, rv, rkp, _ = ops.sparse_attn_bwd(q, v, kp, d_o, stats, B, n, ks, h, drop)
     torch.cuda.synchronize()
     assert _rel(dv.double(), rv.double()) < 1e-4, _rel(dv.double(), rv.double())
