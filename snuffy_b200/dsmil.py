@@ -27,11 +27,42 @@ class BClassifier(nn.Module):
             self.v = nn.Identity()
         self.fcc = nn.Conv1d(output_class, output_class, kernel_size=input_size)
 
+    #: "bf16x3" (default: the q / v MLPs on the tcgen05 split-bf16 GEMM, fp32 to ~2^-16) | "fp32" (SIMT, exact)
+    precision = "bf16x3"
+
+    def _planes(self, lin: nn.Linear):
+        """B-operand planes of a Linear weight, cached until the parameter is replaced or updated in place."""
+        cache = self.__dict__.setdefault("_wplanes", {})
+        key = (lin.weight.data_ptr(), lin.weight._version)
+        hit = cache.get(id(lin))
+        if hit is None or hit[0] != key:
+            cache[id(lin)] = hit = (key, ops.weight_planes(lin.weight.detach()))
+        return hit[1]
+
+    def _tc(self, feats: torch.Tensor) -> bool:
+        # worth it (and exercised) for real bags only: thousands of rows, feature size a multiple of the 32-column plane block
+        return self.precision != "fp32" and feats.shape[1] % 32 == 0 and feats.shape[0] >= 1024
+
+    def _mlp(self, x, layers):
+        """[(Linear, activation name), ...] applied to x [rows, K]: tcgen05 GEMMs with the activation in the epilogue (each
+        layer hands its output to the next as operand planes), or the exact-fp32 SIMT GEMM."""
+        if not self._tc(x):
+            for lin, act in layers:
+                x = ops.linear_f32(x, lin.weight.detach(), lin.bias.detach(), act=act)
+            return x
+        rows = x.shape[0]
+        _, xp, _ = ops.ln_rows(x, None, None, apply_ln=False, want_planes=True)
+        out = None
+        for i, (lin, act) in enumerate(layers):
+            last = i == len(layers) - 1
+            out, _, xp = ops.gemm_tc(xp, self._planes(lin), M=rows, N=lin.weight.shape[0], K=lin.weight.shape[1], passes=3,
+                                     bias=lin.bias.detach(), act=act, want_out=last, want_planes=not last)
+        return out
+
     def _q(self, feats: torch.Tensor) -> torch.Tensor:
         if isinstance(self.q, nn.Sequential):
-            hdn = ops.linear_f32(feats, self.q[0].weight.detach(), self.q[0].bias.detach(), act="relu")
-            return ops.linear_f32(hdn, self.q[2].weight.detach(), self.q[2].bias.detach(), act="tanh")
-        return ops.linear_f32(feats, self.q.weight.detach(), self.q.bias.detach())
+            return self._mlp(feats, [(self.q[0], "relu"), (self.q[2], "tanh")])
+        return self._mlp(feats, [(self.q, "none")])
 
     def forward(self, feats, c):  # N x K, N x C
         _require_cuda(feats, "dsmil.BClassifier")
@@ -45,7 +76,7 @@ class BClassifier(nn.Module):
         if isinstance(self.v, nn.Sequential):
             if self.training and self.v[0].p > 0:
                 raise NotImplementedError("dsmil value dropout in train mode needs the autograd path")
-            v = ops.linear_f32(feats, self.v[1].weight.detach(), self.v[1].bias.detach(), act="relu")
+            v = self._mlp(feats, [(self.v[1], "relu")])
         else:
             v = feats
         q = self._q(feats)
