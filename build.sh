@@ -17,6 +17,10 @@ for f in "$SRC"/*.cu; do
     pids+=($!)
   fi
 done
-for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+fail=0
+for p in "${pids[@]:-}"; do
+  if [[ -n "$p" ]] && ! wait "$p"; then fail=1; fi
+done
+if [[ $fail -ne 0 ]]; then echo "build.sh: a compile step failed" >&2; exit 1; fi
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xlinker --exclude-libs,ALL -o "$OUT" build/*.o
 echo "built $OUT"

@@ -3,7 +3,7 @@
 //   forward   S_j = Q_j Kp_j^T / sqrt(dk),  P = softmax_keys(S),  P~ = dropout(P),  O_j = P~^T V_j
 //   backward  dV = P~ dO            [N, dk]      (per 128-query tile, nothing to reduce)
 //             G  = V dO^T           [N, Ksel]    = dP~
-//             dS = P o (D o G - delta) / sqrt(dk),   delta[n] = sum_k P~[n, k] G[n, k] = V[n, :] . dV[n, :]
+//             dS = P o (D o G - delta) / sqrt(dk),   delta[n] = sum_k P~[n, k] G[n, k]
 //             dQ = dS Kp            [N, dk]
 //             dKp = dS^T Q          [Ksel, dk]   accumulated over the row tiles in TMEM, transposed: dKp^T = Q^T dS  (the
 //                                                forward's O^T = V^T P with Q in place of V and dS in place of P)
@@ -17,7 +17,7 @@
 //   warps 2-13  row warps (one query row per thread, three warps per TMEM lane quadrant owning contiguous 8-key groups)
 // Per tile (TMEM: A = [0, KP) scores then G, D = dk columns for dV then dQ, C = KP columns for dKp^T):
 //   S = Q Kp^T -> A | rows: S -> registers, P from the saved statistics, P~ planes -> smem | buffer <- dO | G = V dO^T -> A |
-//   dV = P~ dO -> D | rows: dV out, delta = V . dV | rows: dS = P o (D o G - delta) / sqrt(dk) planes -> smem (over P~) |
+//   dV = P~ dO -> D | rows: delta (first pass over G), dS in place of P (second pass), dV out, dS planes -> smem (over P~) |
 //   buffer <- Kp | dQ = dS Kp -> D, dKp^T += Q^T dS -> C | rows: dQ out.
 #include "tc_ptx.cuh"
 
@@ -133,7 +133,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1 + 4 * AB_PARTS);
+        mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
         mbar_init(kd_full, 1); mbar_init(kd_empty, 1); mbar_init(a_full, 1); mbar_init(a_free, 4 * AB_PARTS);
         mbar_init(ps_full, 4 * AB_PARTS); mbar_init(ps_empty, 1); mbar_init(d_full, 1); mbar_init(d_free, 4 * AB_PARTS);
         mbar_init(c_full, 1); mbar_init(c_free, 4 * AB_PARTS);
@@ -269,7 +269,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 tc_fence_after();
                 if (lane == 0) {
 #pragma unroll 1
-                    for (int ks = 0; ks < kksteps; ++ks) {
+                    for (int ks = 0; ks < kksteps; ++ks) {         // rolled: any unrolling of this loop crashes nvcc 12.9 (cicc segfault)
                         const uint64_t po = qv_step * ks, ko = mn_step * ks;
                         tc_mma_bf16(tD, ps_lo + po, kdn_hi + ko, idescD, ks ? 1u : 0u);
                         tc_mma_bf16(tD, ps_hi + po, kdn_lo + ko, idescD, 1u);
@@ -288,7 +288,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 tc_fence_after();
                 if (lane == 0) {
 #pragma unroll 1
-                    for (int ks = 0; ks < kksteps; ++ks) {
+                    for (int ks = 0; ks < kksteps; ++ks) {         // rolled: any unrolling of this loop crashes nvcc 12.9 (cicc segfault)
                         const uint64_t po = qv_step * ks, ko = mn_step * ks;
                         tc_mma_bf16(tD, ps_lo + po, kdn_hi + ko, idescD, ks ? 1u : 0u);
                         tc_mma_bf16(tD, ps_hi + po, kdn_lo + ko, idescD, 1u);
@@ -393,72 +393,99 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ps_full);
                 DBGB(it, 1);
-                // ---- (b) dV out, delta = V[n, :] . dV[n, :] (this thread: nc groups of 8 columns; the parts exchange)
-                mbar_wait(v_full, it & 1);
-                mbar_wait(d_full, 0);
+                // ---- (c1) delta[n] = sum_k P~[n, k] G[n, k]: first pass over G (this thread's keys), one exchange between the parts.
+                // (Taken from the very G values that enter dS below, so that a saturated row cancels exactly.)
+                mbar_wait(a_full, 1);
                 tc_fence_after();
                 DBGB(it, 2);
                 float dpart = 0.f;
-                float* drow = p.dqv + g * (2 * (int64_t)p.d) + j * dk;
-                for (int ci = 0; ci < nc; ++ci) {
-                    const int cg = c0 + ci;
-                    float o[8];
-                    tc_ld8(lane_addr + p.d_col + (uint32_t)(cg * 8), o);
-                    const uint4 vh = *reinterpret_cast<const uint4*>(sV + (size_t)cg * 2048 + rr * 16);
-                    const uint4 vl = *reinterpret_cast<const uint4*>(sV + QV_PLANE + (size_t)cg * 2048 + rr * 16);
-                    const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float va = __uint_as_float(hh[q] << 16) + __uint_as_float(ll[q] << 16);
-                        const float vb = __uint_as_float(hh[q] & 0xFFFF0000u) + __uint_as_float(ll[q] & 0xFFFF0000u);
-                        dpart = fmaf(va, o[2 * q], dpart);
-                        dpart = fmaf(vb, o[2 * q + 1], dpart);
+                for (int gi = 0; gi < AB_VG; ++gi) {
+                    if (gi < ng) {
+                        float gv[8];
+                        tc_ld8(lane_addr + (uint32_t)((g0 + gi) * 8), gv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float pt = v[gi * 8 + e];
+                            if (DROP) pt = (kbits[gi >> 2] >> (8 * (gi & 3) + e)) & 1u ? pt * keep_scale : 0.f;
+                            dpart = fmaf(pt, gv[e], dpart);
+                        }
                     }
-                    if (valid) st_global_v8(drow + p.d + cg * 8, o);
                 }
-                tc_fence_before();
                 sRed[part * 128 + rr] = dpart;
                 asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AB_PARTS * 32) : "memory");
                 float delta = 0.f;
 #pragma unroll
                 for (int q = 0; q < AB_PARTS; ++q) delta += sRed[q * 128 + rr];
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(d_free); mbar_arrive(v_empty); }
                 DBGB(it, 3);
-                // ---- (c) dS = P o (D o G - delta) / sqrt(dk) -> planes (over P~: dV has consumed it)
-                mbar_wait(a_full, 1);
-                mbar_wait(ps_empty, 0);                          // fill 2 it + 1
-                tc_fence_after();
-                DBGB(it, 4);
+                // ---- (c2) dS = P o (D o G - delta) / sqrt(dk), in place of P (second pass over G)
 #pragma unroll
                 for (int gi = 0; gi < AB_VG; ++gi) {
                     if (gi < ng) {
-                        const int kgp = g0 + gi;
-                        float gv[8], w[8];
-                        tc_ld8(lane_addr + (uint32_t)(kgp * 8), gv);
+                        float gv[8];
+                        tc_ld8(lane_addr + (uint32_t)((g0 + gi) * 8), gv);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             float dp = gv[e];
                             if (DROP) dp = (kbits[gi >> 2] >> (8 * (gi & 3) + e)) & 1u ? dp * keep_scale : 0.f;
-                            w[e] = v[gi * 8 + e] * (dp - delta) * p.scale;
+                            v[gi * 8 + e] *= (dp - delta) * p.scale;
                         }
-                        split_store8(w, sPS + (size_t)kgp * 2048 + rr * 16, sPS + P_PLANE + (size_t)kgp * 2048 + rr * 16);
                     }
                 }
                 tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_free);
+                DBGB(it, 4);
+                // ---- (b) dV out (its MMAs ran beside the two passes above)
+                float* drow = p.dqv + g * (2 * (int64_t)p.d) + j * dk;
+                mbar_wait(d_full, 0);
+                tc_fence_after();
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    if (ci < nc) {
+                        float o[8];
+                        tc_ld8(lane_addr + p.d_col + (uint32_t)((c0 + ci) * 8), o);
+                        if (valid) st_global_v8(drow + p.d + (c0 + ci) * 8, o);
+                    }
+                }
+                for (int ci = 3; ci < nc; ++ci) {                // head sizes above 64: the rest, rolled
+                    float o[8];
+                    tc_ld8(lane_addr + p.d_col + (uint32_t)((c0 + ci) * 8), o);
+                    if (valid) st_global_v8(drow + p.d + (c0 + ci) * 8, o);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_free);
+                // ---- dS planes over P~ (dV has consumed it)
+                mbar_wait(ps_empty, 0);                          // fill 2 it + 1
+#pragma unroll
+                for (int gi = 0; gi < AB_VG; ++gi) {
+                    if (gi < ng) {
+                        const int kgp = g0 + gi;
+                        split_store8(*reinterpret_cast<const float(*)[8]>(v + gi * 8), sPS + (size_t)kgp * 2048 + rr * 16,
+                                     sPS + P_PLANE + (size_t)kgp * 2048 + rr * 16);
+                    }
+                }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(a_free); mbar_arrive(ps_full); }
+                if (lane == 0) mbar_arrive(ps_full);
                 DBGB(it, 5);
                 // ---- (d) dQ out
                 mbar_wait(d_full, 1);
                 tc_fence_after();
                 DBGB(it, 6);
-                for (int ci = 0; ci < nc; ++ci) {
-                    const int cg = c0 + ci;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    if (ci < nc) {
+                        float o[8];
+                        tc_ld8(lane_addr + p.d_col + (uint32_t)((c0 + ci) * 8), o);
+                        if (valid) st_global_v8(drow + (c0 + ci) * 8, o);
+                    }
+                }
+                for (int ci = 3; ci < nc; ++ci) {
                     float o[8];
-                    tc_ld8(lane_addr + p.d_col + (uint32_t)(cg * 8), o);
-                    if (valid) st_global_v8(drow + cg * 8, o);
+                    tc_ld8(lane_addr + p.d_col + (uint32_t)((c0 + ci) * 8), o);
+                    if (valid) st_global_v8(drow + (c0 + ci) * 8, o);
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -140,7 +140,31 @@ def t_attn_bwd():
     return bool(ok), (B, n, ks, h, d, p)
 
 
-tests = [t_gemm_tc, t_splitk, t_attn, t_select, t_ln, t_blockdiag, t_splitk_blockdiag, t_actgrad, t_attn_bwd]
+def t_attn_bwd_fused():
+    """Training forward (statistics + keep bits) and the one-kernel backward vs the fp32 SIMT backward of the same draw."""
+    dk = int(rs.choice([32, 64, 96, 128])); h = int(rs.randint(1, 9)); d = dk * h
+    # ks >= 2: with ONE key P is identically 1 and the true dQ / dKp are exactly 0; the kernel's P (from the saved statistics)
+    # is 1 +- 1 ulp, which leaves rounding noise where the reference has zeros
+    B = int(rs.randint(1, 4)); n = int(rs.randint(1, 900)); ks = int(rs.randint(2, 225)); p = float(rs.choice([0.0, 0.15, 0.5]))
+    if not ops.sparse_attn_bwd_fused_supported(B, n, ks, h, d) or not ops.sparse_attn_tc_supported(B, n, ks, h, d):
+        return True, None
+    qv = torch.randn(B * n, 2 * d, device="cuda"); kp = torch.randn(B * ks, d, device="cuda"); d_o = torch.randn(B * ks, d, device="cuda")
+    _, qvp, _ = ops.ln_rows(qv, None, None, apply_ln=False, want_planes=True, zero_planes=True)
+    o, _, stats, mask = ops.sparse_attn_tc(qvp, kp, B, n, ks, h, d, want_probs=False, want_stats=True, dropout_p=p, seed=3,
+                                           offset=runs, want_mask=True)
+    o_ref, _, _ = ops.sparse_attn(qv[:, :d], qv[:, d:], kp, B, n, ks, h, want_probs=False, dropout_p=p, seed=3, offset=runs)
+    dq, dv, dkp, _ = ops.sparse_attn_bwd_fused(qvp, kp, d_o, stats, B, n, ks, h, d, p, mask)
+    rq, rv, rkp, _ = ops.sparse_attn_bwd(qv[:, :d], qv[:, d:], kp, d_o, stats, B, n, ks, h, (p, 3, runs))
+    floor = 1e-2 * float(rv.abs().max())
+    close = lambda a, b: float((a.double() - b.double()).abs().max()) <= 1e-4 * max(float(b.abs().max()), floor)
+    ok = close(o, o_ref) and close(dq, rq) and close(dv, rv) and close(dkp, rkp)
+    return bool(ok), (B, n, ks, h, d, p)
+
+
+tests = [t_gemm_tc, t_splitk, t_attn, t_select, t_ln, t_blockdiag, t_splitk_blockdiag, t_actgrad, t_attn_bwd, t_attn_bwd_fused,
+         t_attn, t_attn_bwd_fused]
+if os.environ.get("ONLY"):
+    tests = [t for t in tests if t.__name__ in os.environ["ONLY"].split(",")]
 t0 = time.time()
 while time.time() - t0 < budget:
     fn = tests[runs % len(tests)]
