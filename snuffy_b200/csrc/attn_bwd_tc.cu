@@ -125,7 +125,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
     unsigned char* sPS = sV + 2 * QV_PLANE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPS + 2 * P_PLANE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    float* sRed = reinterpret_cast<float*>(bars + 17);       // [AB_PARTS][128]
+    float* sRed0 = reinterpret_cast<float*>(bars + 17);      // [tile parity][AB_PARTS][128] (one exchange barrier per tile: see attn_tc.cu)
     const uint32_t b0 = smem_u32(bars);
     const uint32_t q_full = b0, q_empty = b0 + 8, v_full = b0 + 16, v_empty = b0 + 24, kd_full = b0 + 32, kd_empty = b0 + 40,
                    a_full = b0 + 48, a_free = b0 + 56, ps_full = b0 + 64, ps_empty = b0 + 72, d_full = b0 + 80, d_free = b0 + 88,
@@ -412,6 +412,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
                         }
                     }
                 }
+                float* sRed = sRed0 + (it & 1) * AB_PARTS * 128;
                 sRed[part * 128 + rr] = dpart;
                 asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(AB_PARTS * 32) : "memory");
                 float delta = 0.f;
@@ -495,6 +496,7 @@ attn_bwd_tc_kernel(const AttnBwdParams p) {
             // ---- item epilogue: dKp^T (TMEM lane = dv, column = key) -> this split's partial (like the forward's O^T read-out)
             mbar_wait(c_full, item_no & 1);
             tc_fence_after();
+            asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(AB_SOFT) : "memory");      // as in attn_tc.cu: the order c_full implies, made visible
             {
                 const int L = rr;
                 float* stage = reinterpret_cast<float*>(sPS);        // [key][dk] fp32; every MMA that read sPS has retired
@@ -568,7 +570,7 @@ static AttnBwdPlan plan_attn_bwd(int64_t B, int64_t N, int64_t Ksel, int64_t h, 
     if (pl.c_col + (uint32_t)KP > 512u) return pl;                     // TMEM: scores / G, dV / dQ, dKp^T
     size_t stage = (size_t)2 * KP * 256;                               // P~ / dS planes, also the fp32 staging of the dKp read-out
     if (2 * dk <= 128) { const size_t st = (((size_t)(KP + 32) * dk * 4) + 127) & ~(size_t)127; if (st > stage) stage = st; }
-    pl.smem = (size_t)2 * (KP + 1) * dk * 2 + (size_t)4 * AB_TILE * dk * 2 + stage + 17 * 8 + 16 + AB_PARTS * 128 * 4;
+    pl.smem = (size_t)2 * (KP + 1) * dk * 2 + (size_t)4 * AB_TILE * dk * 2 + stage + 17 * 8 + 16 + 2 * AB_PARTS * 128 * 4;
     if (stage != (size_t)2 * KP * 256) return pl;                      // keep the carve-up of the kernel (bars follow 2 P planes)
     if (pl.smem > 227 * 1024) return pl;
     const int64_t tiles = (N + AB_TILE - 1) / AB_TILE + 1;

@@ -149,7 +149,9 @@ attn_tc_kernel(const AttnTcParams p) {
     const uint32_t stage_bytes = 2 * dk <= 128 ? ((uint32_t)(KP + 32) * dk * 4u + 127u) & ~127u : 0u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (2 * P_PLANE > stage_bytes ? 2 * P_PLANE : stage_bytes));
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    float* sRed = reinterpret_cast<float*>(bars + 13);       // [max | sum][AT_PARTS][128 rows]; the named barriers of a quadrant order its reuse
+    // [tile parity][max | sum][AT_PARTS][128 rows]: with ONE exchange barrier per tile a fast warp could otherwise write tile
+    // t + 1's values while a slow one still reads tile t's; writes to parity p of tile t + 2 come after the barrier of tile t + 1
+    float* sRed0 = reinterpret_cast<float*>(bars + 13);
     const uint32_t b0 = smem_u32(bars);
     const uint32_t q_full = b0, q_empty = b0 + 8, v_full = b0 + 16, v_empty = b0 + 24, s_full = b0 + 32,
                    s_empty = b0 + 40, p_full = b0 + 48, p_empty = b0 + 56, o_full = b0 + 64, k_ready = b0 + 72,
@@ -333,6 +335,7 @@ attn_tc_kernel(const AttnTcParams p) {
                 const bool valid = g >= g_lo && g < g_hi;
                 const int n = (int)(g - g_lo);
                 const int64_t srow = ((int64_t)b * p.h + j) * p.N + n;      // row of the [B, h, N, *] statistics
+                float* sRed = sRed0 + (it & 1) * 2 * RED;
                 const bool stamp = warp == 2 && lane == 0;
                 if (stamp) DBG_STAMP(0, it, 0);
                 mbar_wait(s_full, it & 1);
@@ -492,6 +495,9 @@ attn_tc_kernel(const AttnTcParams p) {
                 // are idle now) and added by the lanes [0, dk).
                 mbar_wait(o_full, item_no & 1);
                 tc_fence_after();
+                // o_full already orders every warp's P stores before the staging stores below (P stores -> p_full -> the MMAs ->
+                // their commit); this barrier states the same order among the softmax warps in a form compute-sanitizer can see
+                asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(AT_SOFT) : "memory");
                 if (warp == 2 && lane == 0) DBG_STAMP(2, it, 3);
                 const int L = rr;                                    // TMEM lane of this thread
                 float* stage = reinterpret_cast<float*>(sP);         // [KP keys][dk] fp32 (<= the P planes: KP * 512 B)
@@ -565,7 +571,7 @@ static size_t attn_tc_smem(int KP, int dk) {
     const size_t v = (size_t)2 * AT_TILE * dk * 2;                                  // V planes
     size_t pp = (size_t)2 * KP * 256;                                               // P planes / O staging area
     if (2 * dk <= 128) { const size_t st = (((size_t)(KP + 32) * dk * 4) + 127) & ~(size_t)127; if (st > pp) pp = st; }
-    size_t total = kq + v + pp + 128 + 2 * AT_PARTS * 128 * 4;
+    size_t total = kq + v + pp + 128 + 4 * AT_PARTS * 128 * 4;
     // the M = 128 A operand of O^T = V^T P reads 16 groups of 2 KB from the start of a V plane (csrc comment at the top)
     const size_t a_reach = kq + v / 2 + (size_t)16 * 2048 + 16;
     return total > a_reach ? total : a_reach;

@@ -124,7 +124,7 @@ def t_actgrad():
 
 def t_attn_bwd():
     dk = int(rs.choice([16, 32, 64, 96])); h = int(rs.randint(1, 9)); d = dk * h
-    B = int(rs.randint(1, 3)); n = int(rs.randint(1, 600)); ks = int(rs.randint(1, 300)); p = float(rs.choice([0.0, 0.15]))
+    B = int(rs.randint(1, 3)); n = int(rs.randint(1, 600)); ks = int(rs.randint(2, 300)); p = float(rs.choice([0.0, 0.15]))   # ks >= 2: see t_attn_bwd_fused
     if not ops.sparse_attn_bwd_tc_supported(B, n, ks, h, d):
         return True, None
     qv = torch.randn(B * n, 2 * d, device="cuda"); kp = torch.randn(B * ks, d, device="cuda"); d_o = torch.randn(B * ks, d, device="cuda")
