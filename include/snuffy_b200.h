@@ -115,6 +115,20 @@ int64_t snuffy_gemm_tc_splitk_workspace(int64_t M, int64_t N, int64_t ksplit);
 int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const void* B_planes,
                           int64_t b_plane_stride, int64_t M, int64_t N, int64_t K, int passes, int64_t ksplit,
                           float* out, void* workspace, int64_t workspace_bytes, snuffy_stream_t stream);
+/* All derived weight operands of a layer (or several) in one launch: what a training step re-derives from the updated
+ * parameters before each forward (the reference re-reads nn.Linear.weight directly, snuffy.py:188, 225).  kind 0: planes of
+ * src [rows, cols] (plane row = src row); kind 1: planes of src^T (plane row = src column, k = src row); kind 2: fp32 copy
+ * to (float*)dst + dst_row0.  Several jobs may fill disjoint row tiles of one plane set (Wq and Wv -> the fused Q|V
+ * operand): dst_row0 is the first plane row, a multiple of plane_rc, dst_k0 the first k (a multiple of 32) and k_total the
+ * contraction length of the whole plane set; padding rows / k of the job's tiles are zeroed.                          */
+#define SNUFFY_MAX_PLANE_JOBS 16
+typedef struct {
+    const float* src; int64_t ld, rows, cols;
+    int32_t kind, plane_rc;
+    int64_t dst_row0, dst_k0, k_total;
+    void* dst; int64_t plane_stride;
+} snuffy_plane_job_t;
+int snuffy_weight_planes_batch(const snuffy_plane_job_t* jobs, int64_t n_jobs, snuffy_stream_t stream);
 /* Operand planes of X^T for fp32 X [R, C] (plane row = column of X, k = row of X) with an optional prologue:
  * mode 0 plain, 1 LayerNorm from saved (mean, rstd) through row_map, 2 dropout(act(x)).  Feeds the transposed
  * operands of dW = dY^T X (autograd of nn.Linear at snuffy.py:188, 225) to snuffy_gemm_tc_splitk.                   */

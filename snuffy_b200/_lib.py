@@ -17,6 +17,15 @@ ACT_IDS = {"none": 0, "relu": 1, "gelu": 2, "leakyrelu": 3, "selu": 4, "tanh": 5
 
 P = c_void_p
 I = c_int64
+
+
+class PlaneJob(ctypes.Structure):
+    """snuffy_plane_job_t (include/snuffy_b200.h)."""
+    _fields_ = [("src", c_void_p), ("ld", c_int64), ("rows", c_int64), ("cols", c_int64), ("kind", ctypes.c_int32),
+                ("plane_rc", ctypes.c_int32), ("dst_row0", c_int64), ("dst_k0", c_int64), ("k_total", c_int64), ("dst", c_void_p), ("plane_stride", c_int64)]
+
+
+MAX_PLANE_JOBS = 16
 # name -> (restype, argtypes).  Order follows include/snuffy_b200.h.
 _SIGNATURES = {
     "snuffy_version": (c_int, []),
@@ -44,6 +53,7 @@ _SIGNATURES = {
     "snuffy_gemm_tc_splitk_workspace": (c_int64, [I, I, I]),
     "snuffy_gemm_tc_splitk": (c_int, [P, I, P, I, I, I, I, c_int, I, P, P, I, P]),
     "snuffy_gemm_tc_awindow": (c_int, [P, I, I, I, P, I, I, I, I, c_int, P, I, P]),
+    "snuffy_weight_planes_batch": (c_int, [ctypes.POINTER(PlaneJob), I, P]),
     "snuffy_planes_t_fwd": (c_int, [P, I, I, I, c_int, c_int, P, P, P, P, P, c_int, c_float, c_uint64, c_uint64, P, I, P]),
     "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),
     "snuffy_sparse_attn_fwd": (c_int, [P, I, P, I, P, I, I, I, I, I, c_float, c_uint64, c_uint64, P, P, P, P, I, P]),

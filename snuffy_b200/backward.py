@@ -129,8 +129,9 @@ class EncoderLayerFunction(torch.autograd.Function):
         tc = precision != "fp32" and engine.tc_supported(d) and dff % 8 == 0
         passes = 1 if precision == "bf16x1" else 3
         if tc:
-            w.prepare(precision)
-            w.prepare_backward()
+            if not w.prepare_train():
+                w.prepare(precision)
+                w.prepare_backward()
             rc_d, rc_ff = ops._block_n(d), ops._block_n(dff)
 
         def dx_gemm(dy, w_f32, wt_planes, n_in):                # dX = dY . W        (W = nn.Linear.weight [out, in])

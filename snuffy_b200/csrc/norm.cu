@@ -5,6 +5,7 @@
 //   ln_mean_head  : final LN -> mean over ALL N tokens -> linear head (snuffy.py:86,71), one pass
 //                   over x, deterministic two-level reduction, no atomics on data.
 #include "common.cuh"
+#include "../../include/snuffy_b200.h"
 
 namespace snuffy {
 
@@ -612,6 +613,89 @@ planes_t_kernel(const PlanesTParams p) {
         *reinterpret_cast<bf16x8*>(p.planes + p.plane_stride + off) = l;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// All derived weight operands of a layer in ONE launch.  A training step re-derives them from the updated parameters every
+// step: per layer the planes of Wq|Wv, W1, W2, Wk, Wo and of their transposes, the fused Q|V bias: ten conversions, two
+// concatenations and the zero fills of the padded plane sets were ~19 launches of 2-8 us.  Each CTA converts one
+// 128-plane-row x 32-k block of one job and writes the padding itself.
+struct PlaneJobs {
+    snuffy_plane_job_t job[SNUFFY_MAX_PLANE_JOBS];
+    int32_t cta0[SNUFFY_MAX_PLANE_JOBS + 1];               // first CTA of each job
+    int32_t n;
+};
+
+__global__ void __launch_bounds__(256)
+weight_planes_batch_kernel(const __grid_constant__ PlaneJobs P) {
+    __shared__ __align__(16) float tile[32][132];
+    const int t = threadIdx.x, bid = blockIdx.x;
+    int j = 0;
+    while (j + 1 < P.n && bid >= P.cta0[j + 1]) ++j;
+    const snuffy_plane_job_t& jb = P.job[j];
+    const int local = bid - P.cta0[j];
+    if (jb.kind == 2) {                                     // fp32 copy (fused bias): 1024 floats per CTA
+        const int64_t total = jb.rows * jb.cols;
+        float* dst = reinterpret_cast<float*>(jb.dst) + jb.dst_row0;
+        for (int64_t i = (int64_t)local * 1024 + t; i < min(total, (int64_t)(local + 1) * 1024); i += 256) dst[i] = jb.src[i];
+        return;
+    }
+    const int rc = jb.plane_rc;
+    const int64_t prows = jb.kind == 0 ? jb.rows : jb.cols;      // plane rows this job fills
+    const int64_t kdim = jb.kind == 0 ? jb.cols : jb.rows;       // contraction length of the plane set
+    const int64_t nkb = plane_kblocks(kdim), nkb_set = plane_kblocks(jb.k_total), kb_set0 = jb.dst_k0 / PLANE_KB;
+    const int64_t kb = local % nkb, rb = local / nkb;
+    __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(jb.dst);
+    if (jb.kind == 1) {                                     // transposed: k runs over the rows of src
+        const int64_t r0 = kb * 32, c0 = rb * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = t + i * 256, row = idx >> 5, c4 = (idx & 31) * 4;
+            const int64_t r = r0 + row, c = c0 + c4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < jb.rows && c < jb.cols) {
+                const float* src = jb.src + r * jb.ld;
+                if (c + 3 < jb.cols) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(src + c));
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                } else {
+                    for (int q = 0; q < 4; ++q) if (c + q < jb.cols) v[q] = src[c + q];
+                }
+            }
+            *reinterpret_cast<float4*>(&tile[row][c4]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int u = t + i * 256, kg = u >> 7, rl = u & 127;
+        const int64_t prl = rb * 128 + rl;                  // plane row inside the job
+        bf16x8 h, l;
+        if (jb.kind == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split_bf16(tile[kg * 8 + q][rl], h.v[q], l.v[q]);
+        } else {
+            const int64_t k0 = kb * 32 + kg * 8;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (prl < prows && k0 < kdim) {
+                const float* src = jb.src + prl * jb.ld + k0;
+                if (k0 + 7 < kdim) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                } else {
+                    for (int q = 0; q < 8; ++q) if (k0 + q < kdim) v[q] = src[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split_bf16(v[q], h.v[q], l.v[q]);
+        }
+        const int64_t prow = jb.dst_row0 + prl;
+        const int64_t rt = prow / rc, rr = prow % rc;
+        const int64_t off = ((rt * nkb_set + kb_set0 + kb) * 4 + kg) * (int64_t)rc * 8 + rr * 8;
+        *reinterpret_cast<bf16x8*>(planes + off) = h;
+        *reinterpret_cast<bf16x8*>(planes + jb.plane_stride + off) = l;
+    }
+}
 }  // namespace snuffy
 
 #pragma GCC visibility push(default)
@@ -633,5 +717,36 @@ extern "C" int snuffy_planes_t_fwd(const float* x, int64_t ldx, int64_t R, int64
     SNUFFY_REQUIRE(grid.y <= 65535, "snuffy_planes_t_fwd: too many rows for one launch");
     planes_t_kernel<<<grid, 256, 0, stream>>>(p);
     return check_launch("snuffy_planes_t_fwd");
+}
+extern "C" int snuffy_weight_planes_batch(const snuffy_plane_job_t* jobs, int64_t n_jobs, cudaStream_t stream) {
+    using namespace snuffy;
+    SNUFFY_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= SNUFFY_MAX_PLANE_JOBS, "snuffy_weight_planes_batch: 1..16 jobs per launch");
+    PlaneJobs P;
+    int64_t ctas = 0;
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        const snuffy_plane_job_t& jb = jobs[j];
+        SNUFFY_REQUIRE(jb.src && jb.dst && jb.rows >= 1 && jb.cols >= 1 && jb.kind >= 0 && jb.kind <= 2,
+                       "snuffy_weight_planes_batch: bad job");
+        P.job[j] = jb;
+        P.cta0[j] = (int32_t)ctas;
+        if (jb.kind == 2) {
+            SNUFFY_REQUIRE(jb.ld == jb.cols, "snuffy_weight_planes_batch: copy jobs take contiguous rows");
+            ctas += (jb.rows * jb.cols + 1023) / 1024;
+            continue;
+        }
+        SNUFFY_REQUIRE(jb.plane_rc == 128 || jb.plane_rc == 256, "snuffy_weight_planes_batch: plane_rc must be 128 or 256");
+        SNUFFY_REQUIRE(jb.dst_row0 % jb.plane_rc == 0, "snuffy_weight_planes_batch: jobs start on a row tile");
+        SNUFFY_REQUIRE(jb.dst_k0 % PLANE_KB == 0 && jb.dst_k0 + (jb.kind == 0 ? jb.cols : jb.rows) <= jb.k_total,
+                       "snuffy_weight_planes_batch: jobs start on a k block inside the plane set");
+        SNUFFY_REQUIRE(jb.ld % 4 == 0 && (uintptr_t)jb.src % 16 == 0 && (uintptr_t)jb.dst % 16 == 0 && jb.plane_stride % 8 == 0,
+                       "snuffy_weight_planes_batch: rows must be 16-byte aligned");
+        const int64_t prows = jb.kind == 0 ? jb.rows : jb.cols, kdim = jb.kind == 0 ? jb.cols : jb.rows;
+        ctas += plane_rtiles(prows, jb.plane_rc) * (jb.plane_rc / 128) * plane_kblocks(kdim);
+    }
+    P.cta0[n_jobs] = (int32_t)ctas;
+    P.n = (int32_t)n_jobs;
+    SNUFFY_REQUIRE(ctas < (1ll << 30), "snuffy_weight_planes_batch: too much work for one launch");
+    weight_planes_batch_kernel<<<(unsigned)ctas, 256, 0, stream>>>(P);
+    return check_launch("snuffy_weight_planes_batch");
 }
 #pragma GCC visibility pop

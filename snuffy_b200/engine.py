@@ -205,6 +205,33 @@ class LayerWeights:
             self.wk_planes = ops.weight_planes(self.wk.detach())
             self.wo_planes = ops.weight_planes(self.wo.detach())
 
+    def prepare_train(self) -> bool:
+        """Everything a tensor-core training step derives from the parameters (prepare + prepare_backward) in one launch;
+        False when the shapes need the per-operand path (Q and V halves that do not start on a row tile)."""
+        if self.wqv_planes is not None and self.w2t_planes is not None:
+            return True
+        d, dff, dev = self.wq.shape[1], self.w1.shape[0], self.wq.device
+        rc_qv, rc_d, rc_ff = ops._block_n(2 * d), ops._block_n(d), ops._block_n(dff)
+        if d % rc_qv or d % 32 or dff % 8 or self.wqv_planes is not None or self.w2t_planes is not None:
+            return False
+        self.bqv = torch.empty(2 * d, dtype=torch.float32, device=dev)
+        self.wqv_planes = Planes(2 * d, d, rc_qv, dev)
+        self.w1_planes, self.w2_planes = Planes(dff, d, rc_ff, dev), Planes(d, dff, rc_d, dev)
+        self.wk_planes, self.wo_planes = Planes(d, d, rc_d, dev), Planes(d, d, rc_d, dev)
+        self.wqvt_planes = Planes(d, 2 * d, rc_d, dev)
+        self.w1t_planes, self.w2t_planes = Planes(d, dff, rc_d, dev), Planes(dff, d, rc_ff, dev)
+        self.wkt_planes, self.wot_planes = Planes(d, d, rc_d, dev), Planes(d, d, rc_d, dev)
+        ops.weight_planes_batch([
+            ("planes", self.wq, self.wqv_planes, 0), ("planes", self.wv, self.wqv_planes, d),
+            ("planes", self.w1, self.w1_planes, 0), ("planes", self.w2, self.w2_planes, 0),
+            ("planes", self.wk, self.wk_planes, 0), ("planes", self.wo, self.wo_planes, 0),
+            ("planes_t", self.w1, self.w1t_planes, 0), ("planes_t", self.w2, self.w2t_planes, 0),
+            ("planes_t", self.wk, self.wkt_planes, 0), ("planes_t", self.wo, self.wot_planes, 0),
+            # (Wq|Wv)^T: plane row = input feature, k = the 2d outputs: the k blocks of Wv^T follow those of Wq^T
+            ("planes_t", self.wq, self.wqvt_planes, 0, 0), ("planes_t", self.wv, self.wqvt_planes, 0, d),
+            ("copy", self.bq.view(1, d), self.bqv, 0), ("copy", self.bv.view(1, d), self.bqv, d)])
+        return True
+
     def prepare_backward(self) -> None:
         if self.w2t_planes is None:
             self.w2t_planes = ops.weight_planes_t(self.w2.detach())
@@ -289,7 +316,8 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
                 not ops.sparse_attn_tc_supported(bags, max_n, ksel_bag, heads, d):
             raise NotImplementedError("packed variable-length bags: inference on the tensor-core path only "
                                       "(eval mode, return_attn = False, head size a multiple of 32 and <= 128)")
-    w.prepare(precision)
+    if not (save and precision != "fp32" and w.prepare_train()):
+        w.prepare(precision)
     passes = 1 if precision == "bf16x1" else 3
     # Inference shares ONE set of normalised planes z = (x - mean) * rstd between LN1 and LN2 (their affines are folded
     # into the weights); the training tape keeps the two LayerNorms separate (their statistics are saved per sub-layer).

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ._lib import ACT_IDS, check, lib
+from ._lib import ACT_IDS, MAX_PLANE_JOBS, PlaneJob, check, lib
 
 
 _U64 = 2**64 - 1
@@ -534,6 +534,29 @@ def weight_planes_t(weight: torch.Tensor) -> Planes:
     """B-operand planes of W^T for W [out, in]: rows = input features, k = output features (dX = dY . W)."""
     weight = _f32(weight, "weight")
     return planes_t(weight, _block_n(weight.shape[1]))
+
+
+def weight_planes_batch(jobs) -> None:
+    """One launch for a list of conversions (csrc/norm.cu weight_planes_batch_kernel).  Each job is a tuple
+    (kind, src, dst, dst_row0[, dst_k0]): kind "planes" (dst Planes rows [dst_row0, dst_row0 + src rows) = src), "planes_t"
+    (dst Planes rows [dst_row0, ...) = columns of src, k from dst_k0) or "copy" (dst fp32 tensor, dst_row0 = element
+    offset)."""
+    kinds = {"planes": 0, "planes_t": 1, "copy": 2}
+    for start in range(0, len(jobs), MAX_PLANE_JOBS):
+        chunk = jobs[start:start + MAX_PLANE_JOBS]
+        arr = (PlaneJob * len(chunk))()
+        for slot, (kind, src, dst, row0, *k0) in zip(arr, chunk):
+            src = _f32(src, "src")
+            if src.dim() != 2 or src.stride(1) != 1:
+                raise ValueError("weight_planes_batch: sources are row-major fp32 matrices")
+            slot.src, slot.ld, slot.rows, slot.cols, slot.kind, slot.dst_row0 = src.data_ptr(), src.stride(0), src.shape[0], \
+                src.shape[1], kinds[kind], row0
+            if kind == "copy":
+                slot.plane_rc, slot.dst, slot.plane_stride, slot.dst_k0, slot.k_total = 0, dst.data_ptr(), 0, 0, 0
+            else:
+                slot.plane_rc, slot.dst, slot.plane_stride = dst.rc, dst.ptr, dst.stride
+                slot.dst_k0, slot.k_total = (k0[0] if k0 else 0), dst.K
+        check(lib.snuffy_weight_planes_batch(arr, len(chunk), _stream()), "snuffy_weight_planes_batch")
 
 
 def gemm_tc_splitk(a: Planes, b: Planes, *, M: int, N: int, K: int, passes: int = 3) -> torch.Tensor:

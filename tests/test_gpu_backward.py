@@ -425,3 +425,28 @@ def test_sparse_attention_backward_fused(ops, B, n, ks, h, d, p):
     assert _rel(dq.double(), rq.double()) < 1e-4, _rel(dq.double(), rq.double())
     assert _rel(dkp.double(), rkp.double()) < 1e-4, _rel(dkp.double(), rkp.double())
     assert not ops.sparse_attn_bwd_fused_supported(1, 1000, 256, 8, 512)          # Ksel > 224: the GEMM formulation serves it
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,dff", [(512, 2048), (256, 520), (768, 3072), (96, 200)])
+def test_weight_planes_batch_matches_single_conversions(ops, d, dff):
+    """One launch for every derived operand of a training step = the per-operand conversions, byte for byte
+    (padding rows / k included), and LayerWeights.prepare_train = prepare + prepare_backward."""
+    from snuffy_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(d)
+    mk = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    ps = [mk(d, d), mk(d), mk(d, d), mk(d), mk(d, d), mk(d), mk(d, d), mk(d), mk(dff, d), mk(dff), mk(d, dff), mk(d),
+          mk(d), mk(d), mk(d), mk(d)]
+    a, b = engine.LayerWeights(*ps), engine.LayerWeights(*ps)
+    a.prepare("bf16x3"); a.prepare_backward()
+    served = b.prepare_train()
+    assert served == (d % ops._block_n(2 * d) == 0 and d % 32 == 0)
+    if not served:
+        return
+    torch.cuda.synchronize()
+    for name in ("wqv_planes", "w1_planes", "w2_planes", "wk_planes", "wo_planes", "wqvt_planes", "w1t_planes", "w2t_planes",
+                 "wkt_planes", "wot_planes"):
+        pa, pb = getattr(a, name), getattr(b, name)
+        assert (pa.rows, pa.K, pa.rc, pa.stride) == (pb.rows, pb.K, pb.rc, pb.stride), name
+        assert torch.equal(pa.buf.view(torch.int16), pb.buf.view(torch.int16)), name
+    assert torch.equal(a.bqv, b.bqv)
