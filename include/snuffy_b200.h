@@ -129,6 +129,15 @@ typedef struct {
     void* dst; int64_t plane_stride;
 } snuffy_plane_job_t;
 int snuffy_weight_planes_batch(const snuffy_plane_job_t* jobs, int64_t n_jobs, snuffy_stream_t stream);
+/* dW[M, N] = dY^T X straight from the ROW planes of dY [R, M] and X [R, N] (128 rows per chunk, as the GEMM epilogues and
+ * snuffy_ln_rows_fwd write them) through MN-major tcgen05 descriptors: no transposed copy of either operand (autograd of
+ * nn.Linear.weight at snuffy.py:188, 225).  M % 128 == 0, N % snuffy_gemm_tc_block_n(N) == 0; plane rows R .. ceil16(R)
+ * must be zero when R % 16 != 0 (snuffy_planes_zero_rows).  Workspace: snuffy_gemm_tc_splitk_workspace(M, N, ksplit).   */
+int snuffy_gemm_tc_splitk_rows(const void* dY_planes, int64_t a_plane_stride, const void* X_planes,
+                               int64_t b_plane_stride, int64_t M, int64_t N, int64_t R, int passes, int64_t ksplit,
+                               float* out, void* workspace, int64_t workspace_bytes, snuffy_stream_t stream);
+int snuffy_planes_zero_rows(void* planes, int64_t plane_stride, int64_t K, int plane_rc, int64_t row0, int64_t row1,
+                            snuffy_stream_t stream);
 /* Operand planes of X^T for fp32 X [R, C] (plane row = column of X, k = row of X) with an optional prologue:
  * mode 0 plain, 1 LayerNorm from saved (mean, rstd) through row_map, 2 dropout(act(x)).  Feeds the transposed
  * operands of dW = dY^T X (autograd of nn.Linear at snuffy.py:188, 225) to snuffy_gemm_tc_splitk.                   */

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "snuffy_gemm_tc_splitk_workspace": (c_int64, [I, I, I]),
     "snuffy_gemm_tc_splitk": (c_int, [P, I, P, I, I, I, I, c_int, I, P, P, I, P]),
     "snuffy_gemm_tc_awindow": (c_int, [P, I, I, I, P, I, I, I, I, c_int, P, I, P]),
+    "snuffy_gemm_tc_splitk_rows": (c_int, [P, I, P, I, I, I, I, c_int, I, P, P, I, P]),
+    "snuffy_planes_zero_rows": (c_int, [P, I, I, c_int, I, I, P]),
     "snuffy_weight_planes_batch": (c_int, [ctypes.POINTER(PlaneJob), I, P]),
     "snuffy_planes_t_fwd": (c_int, [P, I, I, I, c_int, c_int, P, P, P, P, P, c_int, c_float, c_uint64, c_uint64, P, I, P]),
     "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),

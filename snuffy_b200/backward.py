@@ -21,6 +21,8 @@ from . import engine, ops
 #: GEMMs over block-diagonal head operands + row kernels), "simt" (fp32 SIMT products)
 ATTN_BWD = __import__("os").environ.get("SNUFFY_B200_ATTN_BWD", "fused")
 ATTN_BWD_TC = ATTN_BWD != "simt"
+#: weight gradients of the three all-row projections straight from row planes (MN-major descriptors); "0" = from transposed copies
+DW_BY_ROWS = __import__("os").environ.get("SNUFFY_B200_DW_BY_ROWS", "1") != "0"
 
 
 def _flat(t: torch.Tensor, d: int) -> torch.Tensor:
@@ -133,6 +135,7 @@ class EncoderLayerFunction(torch.autograd.Function):
                 w.prepare(precision)
                 w.prepare_backward()
             rc_d, rc_ff = ops._block_n(d), ops._block_n(dff)
+        by_rows = tc and DW_BY_ROWS and t.a_planes is not None
 
         def dx_gemm(dy, w_f32, wt_planes, n_in):                # dX = dY . W        (W = nn.Linear.weight [out, in])
             if not tc:
@@ -149,13 +152,19 @@ class EncoderLayerFunction(torch.autograd.Function):
             # dh = (gf W2) * act'(h_pre) * mask in the epilogue of the product, as fp32 and as the next product's operand planes
             _, gfp, _ = ops.ln_rows(gf, None, None, apply_ln=False, want_planes=True)
             dh, dh_planes = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes, drop=t.drop_ff)
+            # weight gradients contract over the rows: straight from the row planes both sides already exist as (the forward's
+            # GEMM operands, this pass's dX operands) when the shapes tile; else from transposed copies
+            if by_rows and ops.gemm_tc_splitk_rows_supported(d, dff) and ops.gemm_tc_splitk_rows_supported(dff, d):
+                d_w2 = ops.gemm_tc_splitk_rows(gfp, t.a_planes, M=d, N=dff, R=rows, passes=passes)     # gf^T . dropout(act(h_pre))
+                d_w1 = ops.gemm_tc_splitk_rows(dh_planes, t.u2_planes, M=dff, N=d, R=rows, passes=passes)   # dh^T . LN2(y)
+            else:
+                d_w2 = ops.gemm_tc_splitk(ops.planes_t(gf, 128), ops.planes_t(t.h_pre, rc_ff, mode=2, act=act, drop=t.drop_ff),
+                                          M=d, N=dff, K=rows, passes=passes)
+                d_w1 = ops.gemm_tc_splitk(ops.planes_t(dh, 128),
+                                          ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln2_stats, gamma=w.g2, beta=w.be2,
+                                                       row_map=t.row_map, alt=t.xs_new),
+                                          M=dff, N=d, K=rows, passes=passes)
             del gfp
-            d_w2 = ops.gemm_tc_splitk(ops.planes_t(gf, 128), ops.planes_t(t.h_pre, rc_ff, mode=2, act=act, drop=t.drop_ff),
-                                      M=d, N=dff, K=rows, passes=passes)           # gf^T . dropout(act(h_pre))
-            d_w1 = ops.gemm_tc_splitk(ops.planes_t(dh, 128),
-                                      ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln2_stats, gamma=w.g2, beta=w.be2,
-                                                   row_map=t.row_map, alt=t.xs_new),
-                                      M=dff, N=d, K=rows, passes=passes)           # dh^T . LN2(y)
         else:
             da = dx_gemm(gf, w.w2, w.w2t_planes, dff)                              # [rows, dff]
             dh, a = ops.act_bwd(t.h_pre, da, act, t.drop_ff, want_dh=True, want_a=True)
@@ -200,11 +209,16 @@ class EncoderLayerFunction(torch.autograd.Function):
         d_bqv = ops.colsum(dqv).view(-1)
         d_bq, d_bv = d_bqv[:d], d_bqv[d:]
         if tc:
-            d_wqv = ops.gemm_tc_splitk(ops.planes_t(dqv, 128),
-                                       ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln1_stats, gamma=w.g1, beta=w.be1),
-                                       M=2 * d, N=d, K=rows, passes=passes)        # [dQ | dV]^T . LN1(x)
+            _, dqvp, _ = ops.ln_rows(dqv, None, None, apply_ln=False, want_planes=True)
+            if by_rows and ops.gemm_tc_splitk_rows_supported(2 * d, d):
+                d_wqv = ops.gemm_tc_splitk_rows(dqvp, t.u1_planes, M=2 * d, N=d, R=rows, passes=passes)   # [dQ | dV]^T . LN1(x)
+            else:
+                d_wqv = ops.gemm_tc_splitk(ops.planes_t(dqv, 128),
+                                           ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln1_stats, gamma=w.g1, beta=w.be1),
+                                           M=2 * d, N=d, K=rows, passes=passes)
             d_wq, d_wv = d_wqv[:d], d_wqv[d:]
-            du1 = dx_gemm(dqv, None, w.wqvt_planes, d)                             # dQ Wq + dV Wv
+            du1, _, _ = ops.gemm_tc(dqvp, w.wqvt_planes, M=rows, N=d, K=2 * d, passes=passes)   # dQ Wq + dV Wv
+            del dqvp
         else:
             u1, _, _ = ops.ln_rows(t.x_in, w.g1, w.be1, want_f32=True)
             d_wq, d_wv = ops.matmul_tn(dq, u1), ops.matmul_tn(dv, u1)

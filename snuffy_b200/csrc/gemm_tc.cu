@@ -8,6 +8,8 @@
 // flip top-K indices.  Operands arrive as pre-tiled planes (common.cuh): every pipeline stage
 // is a contiguous chunk in HBM moved by one cp.async.bulk per plane, landing directly in the SWIZZLE_NONE
 // K-major core-matrix layout the UMMA shared-memory descriptor describes.  No tensor maps, no swizzle.
+// The weight-gradient form (gemm_tc_kernel<BN, true>) contracts over the ROWS of two activation plane sets instead: its
+// stages are strided tiles of those planes, fetched by one tensor-map TMA per operand and read through MN-major descriptors.
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0      bulk-copy producer (+ TMEM alloc/dealloc)          full/empty mbarrier ring
@@ -15,6 +17,8 @@
 //   warps 2..9  epilogue: tcgen05.ld -> bias/activation -> (a) split-bf16 planes for the next GEMM, written
 //               straight from the row-owner register layout (512 B coalesced per warp store), and/or
 //               (b) fp32 rows (+ residual read through row_map) transposed through shared memory.
+#include <stdlib.h>
+#include <cuda.h>                      // CUtensorMap (types only: the encoder is looked up through the runtime, no -lcuda)
 #include "tc_ptx.cuh"
 
 namespace snuffy {
@@ -60,6 +64,10 @@ struct TcGemmParams {
     // K window of the A planes: the operand is columns [a_kb_off*32, ...) of a wider plane set with a_nkb k-blocks per row
     // tile (e.g. Q or V inside the [rows, 2d] planes the Q|V projection wrote)
     int a_nkb, a_kb_off;
+    // MN-major form (gemm_tc_kernel<BN, true>): both operands are ROW planes of activations ([rows, features], 128 rows per
+    // chunk) contracted over their rows: A = planes of dY [K rows, M features], B = planes of X [K rows, N features], k-blocks
+    // of 32 rows; a_nkb / b_nkb = feature k-blocks per row tile of each plane set
+    int b_nkb;
 };
 
 // out of line on purpose: 32 inlined copies of the activation switch per chunk bloat the epilogue (instruction-cache misses
@@ -86,9 +94,9 @@ __host__ __device__ __forceinline__ bool tile_live(int M, int N, int bn, int dia
     return r_lo / diag_m <= c_hi / diag_n && c_lo / diag_n <= r_hi / diag_m;
 }
 
-template <int BN>
+template <int BN, bool MN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const TcGemmParams p) {
+gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
     using Cfg = TcCfg<BN>;
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     unsigned char* stage_base = tc_smem;
@@ -133,7 +141,20 @@ gemm_tc_kernel(const TcGemmParams p) {
             const __nv_bfloat16* b_src = p.B + (int64_t)nt * p.num_kb * b_chunk;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                if (lane == 0) {
+                if (MN) {
+                    // 32 rows of (128 | BN) features of both planes: one tensor-map tile per operand.  The row planes are
+                    // [row tile][8-feature group][row 0..127][8]: the box takes, for each of the tile's groups, the 512-byte
+                    // run of these 32 rows and lays them down group after group, hi plane then lo plane = the canonical
+                    // MN-major operand (8 k = 128 B apart, 8 features = 512 B apart).
+                    if (lane == 0) {
+                        const uint32_t bar = full0 + 8 * stage;
+                        const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
+                        const uint32_t sb = sa + 2 * TC_A_PLANE_BYTES;
+                        mbar_expect_tx(bar, Cfg::STAGE_BYTES);
+                        tma_load_4d(sa, &tm_a, (kb & 3) * 256, 16 * mt, kb >> 2, 0, bar);
+                        tma_load_4d(sb, &tm_b, (kb & 3) * 256, (BN / 8) * nt, kb >> 2, 0, bar);
+                    }
+                } else if (lane == 0) {
                     const uint32_t bar = full0 + 8 * stage;
                     const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + 2 * TC_A_PLANE_BYTES;
@@ -152,8 +173,11 @@ gemm_tc_kernel(const TcGemmParams p) {
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
         constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)(TC_BM >> 4) << 24);
-        constexpr uint32_t LBO_A = TC_BM * 16, LBO_B = BN * 16, SBO = 128;
+                                   ((uint32_t)(TC_BM >> 4) << 24) | (MN ? ((1u << 15) | (1u << 16)) : 0u);
+        // K-major: LBO = between the two k-halves of a K = 16 step, SBO = between 8-row groups; MN-major: LBO = between 8-k
+        // groups (128 B), SBO = between 8-feature groups (512 B), a K = 16 step = 256 B
+        constexpr uint32_t LBO_A = MN ? 128 : TC_BM * 16, LBO_B = MN ? 128 : BN * 16, SBO = MN ? 512 : 128;
+        constexpr uint32_t KS_A = MN ? 256 : 2 * LBO_A, KS_B = MN ? 256 : 2 * LBO_B;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -170,13 +194,16 @@ gemm_tc_kernel(const TcGemmParams p) {
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + 2 * TC_A_PLANE_BYTES;
+                    // MN: the contraction runs over rows, whose planes are not padded with zeros: the last block stops at K
+                    const int nks = MN ? min(PLANE_KB / 16, (p.K - kb * PLANE_KB + 15) / 16) : PLANE_KB / 16;
 #pragma unroll
                     for (int ks = 0; ks < PLANE_KB / 16; ++ks) {
-                        const uint64_t a_hi = make_smem_desc(sa + ks * 2 * LBO_A, LBO_A, SBO);
-                        const uint64_t b_hi = make_smem_desc(sb + ks * 2 * LBO_B, LBO_B, SBO);
+                        if (MN && ks >= nks) break;
+                        const uint64_t a_hi = make_smem_desc(sa + ks * KS_A, LBO_A, SBO);
+                        const uint64_t b_hi = make_smem_desc(sb + ks * KS_B, LBO_B, SBO);
                         if (use_lo) {
-                            const uint64_t a_lo = make_smem_desc(sa + TC_A_PLANE_BYTES + ks * 2 * LBO_A, LBO_A, SBO);
-                            const uint64_t b_lo = make_smem_desc(sb + Cfg::B_PLANE_BYTES + ks * 2 * LBO_B, LBO_B, SBO);
+                            const uint64_t a_lo = make_smem_desc(sa + TC_A_PLANE_BYTES + ks * KS_A, LBO_A, SBO);
+                            const uint64_t b_lo = make_smem_desc(sb + Cfg::B_PLANE_BYTES + ks * KS_B, LBO_B, SBO);
                             // small cross terms first, the dominant hi.hi term last
                             tc_mma_bf16(d_tmem, a_lo, b_hi, IDESC, (kb > kb0 || ks) ? 1u : 0u);
                             tc_mma_bf16(d_tmem, a_hi, b_lo, IDESC, 1u);
@@ -400,8 +427,9 @@ extern "C" {
 
 // Rows-per-chunk (= BLOCK_N of the kernel that will consume them) a [N, K] weight should be tiled with.
 int snuffy_gemm_tc_block_n(int64_t N) {
+    static const int64_t narrow_max_n = [] { const char* e = getenv("SNUFFY_B200_BN128_MAX_N"); return e ? atoll(e) : 0ll; }();
     const int64_t n128 = (N + 127) / 128;
-    return (n128 % 2 == 0) ? 256 : 128;
+    return (n128 % 2 == 0 && N > narrow_max_n) ? 256 : 128;
 }
 
 // bf16 elements in ONE plane of a [rows, K] operand tiled with rc rows per chunk
@@ -410,16 +438,60 @@ int64_t snuffy_plane_elems(int64_t rows, int64_t K, int rc) { return plane_elems
 // C = epilogue(A . B^T) with A, B given as split-bf16 planes (A tiled with 128 rows per chunk, B with
 // snuffy_gemm_tc_block_n(N)).  Outputs (each optional, at least one): fp32 `out` [M, ldc] (+ residual, optionally
 // redirected through row_map), fp32 `preact`, and `out_planes` = the activated result as A planes with K_next = N.
-static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const char* who, int force_bn = 0) {
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static TensorMapEncodeTiledFn fn = [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return reinterpret_cast<TensorMapEncodeTiledFn>(sym);
+    }();
+    return fn;
+}
+
+// Row planes of an [R, F] activation (128 rows per chunk) as a 4-D tensor: (element of a group's 128-row run, 8-feature group,
+// row tile, hi / lo plane); one box = 32 rows x `groups` groups x both planes.
+static int row_planes_tensor_map(CUtensorMap* tm, const void* planes, int64_t plane_stride, int64_t R, int64_t F, int groups) {
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    SNUFFY_REQUIRE(enc, "snuffy_gemm_tc_splitk_rows: cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t ngroups = (cuuint64_t)plane_kblocks(F) * 4;
+    const cuuint64_t dims[4] = {(cuuint64_t)TC_BM * 8, ngroups, (cuuint64_t)plane_rtiles(R, TC_BM), 2};
+    const cuuint64_t strides[3] = {(cuuint64_t)TC_BM * 16, ngroups * TC_BM * 16, (cuuint64_t)plane_stride * 2};   // bytes
+    const cuuint32_t box[4] = {256, (cuuint32_t)groups, 1, 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(planes), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("snuffy_gemm_tc_splitk_rows: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        return 1;
+    }
+    return 0;
+}
+
+static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const char* who, int force_bn = 0,
+                          const CUtensorMap* tm_a = nullptr, const CUtensorMap* tm_b = nullptr) {
     const int bn = force_bn ? force_bn : snuffy_gemm_tc_block_n(N);
     const int total = p.m_tiles * p.n_tiles * p.ksplit;
     const int grid = total < sm_count() ? total : sm_count();
-    if (bn == 256) {
+    static const CUtensorMap none{};
+    const bool mn = tm_a != nullptr;
+    if (mn && bn == 256) {
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<256, true>), (int)TcCfg<256>::SMEM_BYTES));
+        gemm_tc_kernel<256, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p, *tm_a, *tm_b);
+    } else if (mn) {
+        SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<128, true>), (int)TcCfg<128>::SMEM_BYTES));
+        gemm_tc_kernel<128, true><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(p, *tm_a, *tm_b);
+    } else if (bn == 256) {
         SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<256>), (int)TcCfg<256>::SMEM_BYTES));
-        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p);
+        gemm_tc_kernel<256><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p, none, none);
     } else {
         SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<128>), (int)TcCfg<128>::SMEM_BYTES));
-        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(p);
+        gemm_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM_BYTES, stream>>>(p, none, none);
     }
     return check_launch(who);
 }
@@ -612,6 +684,47 @@ int snuffy_gemm_tc_splitk(const void* A_planes, int64_t a_plane_stride, const vo
                           int64_t workspace_bytes, cudaStream_t stream) {
     return gemm_tc_splitk_full(A_planes, a_plane_stride, B_planes, b_plane_stride, 0, M, N, K, passes, ksplit, 0, 0, out, workspace,
                                workspace_bytes, stream);
+}
+
+// dW[M, N] = dY^T X straight from the ROW planes of dY [R, M] and X [R, N] (128 rows per chunk, as the GEMM epilogues and
+// snuffy_ln_rows_fwd write them): the contraction runs over the rows, read through MN-major descriptors, so no transposed
+// copy of either operand is made.  M % 128 == 0, N % snuffy_gemm_tc_block_n(N) == 0; rows R .. ceil16(R) of both plane sets
+// must be finite (zero when R % 16 != 0: snuffy_planes_zero_rows).  Workspace as snuffy_gemm_tc_splitk(M, N, R).
+int snuffy_gemm_tc_splitk_rows(const void* dY_planes, int64_t a_plane_stride, const void* X_planes, int64_t b_plane_stride,
+                               int64_t M, int64_t N, int64_t R, int passes, int64_t ksplit, float* out, void* workspace,
+                               int64_t workspace_bytes, cudaStream_t stream) {
+    SNUFFY_REQUIRE(dY_planes && X_planes && out, "snuffy_gemm_tc_splitk_rows: null pointer");
+    const int bn = snuffy_gemm_tc_block_n(N);
+    SNUFFY_REQUIRE(M >= 128 && N >= 128 && R >= 1 && M % TC_BM == 0 && N % bn == 0 && (uintptr_t)out % 16 == 0,
+                   "snuffy_gemm_tc_splitk_rows: M must be a multiple of 128 and N of its column tile");
+    SNUFFY_REQUIRE(passes == 1 || passes == 3, "snuffy_gemm_tc_splitk_rows: passes must be 1 or 3");
+    if (ksplit <= 0) ksplit = snuffy_gemm_tc_auto_ksplit(M, N, R);
+    const int64_t num_kb = plane_kblocks(R);
+    const int64_t per = (num_kb + ksplit - 1) / ksplit;
+    ksplit = (num_kb + per - 1) / per;
+    SNUFFY_REQUIRE(ksplit == 1 || (workspace && workspace_bytes >= snuffy_gemm_tc_splitk_workspace(M, N, ksplit) &&
+                                   (uintptr_t)workspace % 16 == 0), "snuffy_gemm_tc_splitk_rows: workspace too small");
+    TcGemmParams p{};
+    p.A = reinterpret_cast<const __nv_bfloat16*>(dY_planes); p.a_plane_stride = a_plane_stride;
+    p.B = reinterpret_cast<const __nv_bfloat16*>(X_planes); p.b_plane_stride = b_plane_stride;
+    p.M = (int)M; p.N = (int)N; p.K = (int)R;
+    p.m_tiles = (int)(M / TC_BM);
+    p.n_tiles = (int)(N / bn);
+    p.num_kb = (int)num_kb;
+    p.npairs = passes;
+    p.act = ACT_NONE;
+    p.out = ksplit > 1 ? reinterpret_cast<float*>(workspace) : out; p.ldc = N;
+    p.ksplit = (int)ksplit; p.kb_per = (int)per; p.split_stride = M * N;
+    p.a_nkb = (int)plane_kblocks(M); p.b_nkb = (int)plane_kblocks(N);
+    CUtensorMap tm_a, tm_b;
+    if (int rc = row_planes_tensor_map(&tm_a, dY_planes, a_plane_stride, R, M, 16)) return rc;
+    if (int rc = row_planes_tensor_map(&tm_b, X_planes, b_plane_stride, R, N, bn / 8)) return rc;
+    if (int rc = launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_splitk_rows", 0, &tm_a, &tm_b)) return rc;
+    if (ksplit > 1) {
+        launch_fold_partials(reinterpret_cast<const float*>(workspace), (int)ksplit, M * N / 4, out, stream);
+        return check_launch("snuffy_gemm_tc_splitk_rows");
+    }
+    return 0;
 }
 
 // Split-K product of which only the diagonal blocks (row / diag_m == col / diag_n) are wanted: tiles that meet no such block are

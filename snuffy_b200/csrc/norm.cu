@@ -614,6 +614,19 @@ planes_t_kernel(const PlanesTParams p) {
     }
 }
 
+// rows [row0, row1) of a plane set := 0 (both planes): the tail of the last 16-row group when a product contracts over rows
+__global__ void __launch_bounds__(256)
+planes_zero_rows_kernel(__nv_bfloat16* planes, int64_t plane_stride, int64_t K, int rc, int64_t row0, int64_t row1) {
+    const int64_t units = (row1 - row0) * plane_kblocks(K) * 4;
+    const int64_t u = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (u >= units) return;
+    const int64_t row = row0 + u % (row1 - row0), kunit = u / (row1 - row0);
+    const int64_t off = plane_unit_offset(row, kunit * 8, K, rc);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(planes + off) = z;
+    *reinterpret_cast<uint4*>(planes + plane_stride + off) = z;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // All derived weight operands of a layer in ONE launch.  A training step re-derives them from the updated parameters every
 // step: per layer the planes of Wq|Wv, W1, W2, Wk, Wo and of their transposes, the fused Q|V bias: ten conversions, two
@@ -748,5 +761,16 @@ extern "C" int snuffy_weight_planes_batch(const snuffy_plane_job_t* jobs, int64_
     SNUFFY_REQUIRE(ctas < (1ll << 30), "snuffy_weight_planes_batch: too much work for one launch");
     weight_planes_batch_kernel<<<(unsigned)ctas, 256, 0, stream>>>(P);
     return check_launch("snuffy_weight_planes_batch");
+}
+extern "C" int snuffy_planes_zero_rows(void* planes, int64_t plane_stride, int64_t K, int plane_rc, int64_t row0, int64_t row1,
+                                       cudaStream_t stream) {
+    using namespace snuffy;
+    SNUFFY_REQUIRE(planes && K >= 1 && (plane_rc == 128 || plane_rc == 256) && row0 >= 0 && row1 >= row0,
+                   "snuffy_planes_zero_rows: bad arguments");
+    if (row1 == row0) return 0;
+    const int64_t units = (row1 - row0) * plane_kblocks(K) * 4;
+    planes_zero_rows_kernel<<<(unsigned)((units + 255) / 256), 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(planes),
+                                                                               plane_stride, K, plane_rc, row0, row1);
+    return check_launch("snuffy_planes_zero_rows");
 }
 #pragma GCC visibility pop

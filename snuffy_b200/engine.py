@@ -271,6 +271,10 @@ class LayerTape:
     drop_enc2: Tuple[float, int, int] = (0.0, 0, 0)   # sublayer[1] dropout on the FFN output           snuffy.py:110
     qvp: Optional[Planes] = None                      # Q|V as operand planes (tensor-core attention backward)
     attn_mask: Optional[torch.Tensor] = None          # keep bits of the attention dropout as the forward drew them
+    # row planes the forward GEMMs consumed: LN1(x), LN2(y), dropout(act(h)): X operands of the weight-gradient products
+    u1_planes: Optional[Planes] = None
+    u2_planes: Optional[Planes] = None
+    a_planes: Optional[Planes] = None
 
 
 def tc_supported(d: int) -> bool:
@@ -400,4 +404,6 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         tape = LayerTape(sel=sel, row_map=row_map, xs=xs, xs_new=xs_new, kp=kp, qv=qv, o=o, ln1_stats=ln1_stats,
                          ln2_stats=ln2_stats, attn_stats=attn_stats, h_pre=h_pre, x_in=x, drop=drop, drop_enc1=drop_enc1,
                          drop_ff=drop_ff, drop_enc2=drop_enc2, qvp=qvp if precision != "fp32" else None, attn_mask=attn_mask)
+        if precision != "fp32" and not share_z:
+            tape.u1_planes, tape.u2_planes, tape.a_planes = up, yp, hp
     return x_next, probs, tape

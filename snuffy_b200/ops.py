@@ -536,6 +536,29 @@ def weight_planes_t(weight: torch.Tensor) -> Planes:
     return planes_t(weight, _block_n(weight.shape[1]))
 
 
+def gemm_tc_splitk_rows_supported(M: int, N: int) -> bool:
+    return M >= 128 and N >= 128 and M % 128 == 0 and N % _block_n(N) == 0
+
+
+def gemm_tc_splitk_rows(dy: Planes, x: Planes, *, M: int, N: int, R: int, passes: int = 3) -> torch.Tensor:
+    """dW [M, N] = dY^T X from the ROW planes of dY [R, M] and X [R, N] (rc = 128), contracted over the rows through
+    MN-major descriptors: no transposed operand copies."""
+    if dy.rc != 128 or x.rc != 128 or dy.K != M or x.K != N or dy.rows < R or x.rows < R:
+        raise ValueError("gemm_tc_splitk_rows: operands are 128-row planes of [R, M] and [R, N]")
+    dev = dy.buf.device
+    if R % 16:
+        for pl in (dy, x):
+            check(lib.snuffy_planes_zero_rows(pl.ptr, pl.stride, pl.K, pl.rc, R, (R + 15) // 16 * 16, _stream()),
+                  "snuffy_planes_zero_rows")
+    out = torch.empty(M, N, dtype=torch.float32, device=dev)
+    ks = _tc_auto_ksplit(M, N, R)
+    ws_bytes = lib.snuffy_gemm_tc_splitk_workspace(M, N, ks)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    check(lib.snuffy_gemm_tc_splitk_rows(dy.ptr, dy.stride, x.ptr, x.stride, M, N, R, passes, ks, out.data_ptr(), ws.data_ptr(),
+                                         ws_bytes, _stream()), "snuffy_gemm_tc_splitk_rows")
+    return out
+
+
 def weight_planes_batch(jobs) -> None:
     """One launch for a list of conversions (csrc/norm.cu weight_planes_batch_kernel).  Each job is a tuple
     (kind, src, dst, dst_row0[, dst_k0]): kind "planes" (dst Planes rows [dst_row0, dst_row0 + src rows) = src), "planes_t"

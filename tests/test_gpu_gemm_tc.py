@@ -126,6 +126,29 @@ def test_gemm_tc_splitk_weight_gradient(ops, M, N, K):
     assert float((out.double() - ref).abs().max() / ref.abs().max()) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,R", [(512, 2048, 10000), (2048, 512, 10000), (1024, 512, 3000), (128, 256, 40), (256, 384, 777),
+                                   (768, 3072, 6001), (128, 128, 7)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_gemm_tc_splitk_rows_weight_gradient(ops, M, N, R, passes):
+    """dW[M, N] = dY^T X from the ROW planes of dY [R, M] and X [R, N] (MN-major descriptors, no transposed copies) vs fp64
+    and vs the transposed-planes form; R not a multiple of 16 leaves garbage rows in the planes on purpose."""
+    g = torch.Generator(device="cuda").manual_seed(R)
+    dy = torch.randn(R, M, device="cuda", generator=g)
+    x = torch.randn(R, N, device="cuda", generator=g)
+    assert ops.gemm_tc_splitk_rows_supported(M, N)
+    junk = torch.full((64 << 20,), float("nan"), device="cuda")            # recycled by the allocator as the planes' padding
+    del junk
+    _, dyp, _ = ops.ln_rows(dy, None, None, apply_ln=False, want_planes=True)
+    _, xp, _ = ops.ln_rows(x, None, None, apply_ln=False, want_planes=True)
+    out = ops.gemm_tc_splitk_rows(dyp, xp, M=M, N=N, R=R, passes=passes)
+    ref = dy.double().t() @ x.double()
+    tol = 2e-5 if passes == 3 else 2e-2
+    assert float((out.double() - ref).abs().max() / ref.abs().max()) < tol
+    if passes == 3:
+        old = ops.gemm_tc_splitk(ops.planes_t(dy, 128), ops.planes_t(x, ops.lib.snuffy_gemm_tc_block_n(N)), M=M, N=N, K=R)
+        assert float((out - old).abs().max() / ref.abs().max()) < 1e-5
+
+
 def test_weight_planes_t_dx_product(ops):
     g = torch.Generator(device="cuda").manual_seed(3)
     dy = torch.randn(700, 256, device="cuda", generator=g)

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from snuffy_b200 import ops
 
-B, n, d, h, ks = 8, 10000, 512, 8, 200
+B, n, d, h, ks = int(os.environ.get("B", 8)), 10000, 512, 8, 200
+DROP = float(os.environ.get("DROP", 0))       # > 0: the training form (row statistics + keep bits written)
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 x = torch.randn(B * n, d, device=dev, generator=g)
@@ -14,12 +15,15 @@ _, up, _ = ops.ln_rows(x, gam, bet, want_planes=True)
 wp = ops.weight_planes(w)
 _, _, qvp = ops.gemm_tc(up, wp, M=B * n, N=2 * d, K=d, passes=3, want_out=False, want_planes=True)
 kp = torch.randn(B * ks, d, device=dev, generator=g)
+kw = dict(want_probs=False, want_stats=True, dropout_p=DROP, seed=1, offset=2, want_mask=True) if DROP > 0 else dict(want_probs=False)
+if os.environ.get("STATS"):
+    kw = dict(want_probs=False, want_stats=True)
 for _ in range(3):
-    ops.sparse_attn_tc(qvp, kp, B, n, ks, h, d, want_probs=False)
+    ops.sparse_attn_tc(qvp, kp, B, n, ks, h, d, **kw)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
-    ops.sparse_attn_tc(qvp, kp, B, n, ks, h, d, want_probs=False)
+    ops.sparse_attn_tc(qvp, kp, B, n, ks, h, d, **kw)
 e1.record(); torch.cuda.synchronize()
-print("attn_tc ms", e0.elapsed_time(e1) / 10)
+print("attn_tc ms", e0.elapsed_time(e1) / 10, "B", B, kw)
