@@ -148,11 +148,13 @@ int snuffy_planes_t_fwd(const float* x, int64_t ldx, int64_t R, int64_t C, int p
 
 /* A . B^T where A is a 32-aligned K window of a wider A-plane set (e.g. the Q or the V half of the Q|V planes).         */
 /* dX product with the activation backward fused into its epilogue (autograd of snuffy.py:225):
- * result[m, n] = (A . B^T)[m, n] * act'(gate[m, n]) * dropout_mask(m * N + n), as fp32 `out` and / or A-operand planes. */
+ * result[m, n] = (A . B^T)[m, n] * act'(gate[m, n]) * dropout_mask(m * N + n), as fp32 `out` and / or A-operand planes
+ * and / or its column sums `colsum` [N] (the bias gradient; `colsum_partials`: ceil(M / 128) * 4 * N floats).          */
 int snuffy_gemm_tc_actgrad(const void* A_planes, int64_t a_plane_stride, const void* B_planes,
                            int64_t b_plane_stride, int64_t M, int64_t N, int64_t K, int passes, const float* gate,
                            int64_t ldg, int gate_act, float dropout_p, uint64_t seed, uint64_t offset, float* out,
-                           int64_t ldc, void* out_planes, int64_t out_plane_stride, snuffy_stream_t stream);
+                           int64_t ldc, void* out_planes, int64_t out_plane_stride, float* colsum,
+                           float* colsum_partials, snuffy_stream_t stream);
 /* out = A_window . B^T against a block-diagonal B (B[n, k] != 0 only where n / group_n == k / group_k: the head-block
  * operands of the attention backward, autograd of snuffy.py:160-168 with the head split of 187-201): every column tile
  * contracts only over the k-blocks of the groups it touches.

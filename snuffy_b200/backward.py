@@ -149,21 +149,27 @@ class EncoderLayerFunction(torch.autograd.Function):
         d_b2 = ops.colsum(gf).view(-1)
         dh_planes = None
         if tc:
-            # dh = (gf W2) * act'(h_pre) * mask in the epilogue of the product, as fp32 and as the next product's operand planes
+            # dh = (gf W2) * act'(h_pre) * mask in the epilogue of the product, as the next product's operand planes
             _, gfp, _ = ops.ln_rows(gf, None, None, apply_ln=False, want_planes=True)
-            dh, dh_planes = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes, drop=t.drop_ff)
-            # weight gradients contract over the rows: straight from the row planes both sides already exist as (the forward's
-            # GEMM operands, this pass's dX operands) when the shapes tile; else from transposed copies
             if by_rows and ops.gemm_tc_splitk_rows_supported(d, dff) and ops.gemm_tc_splitk_rows_supported(dff, d):
+                # weight gradients contract over the rows: straight from the row planes both sides already exist as (the
+                # forward's GEMM operands, this pass's dX operands); db1 = column sums of dh from the same epilogue, so dh is
+                # never written as fp32
+                dh = None
+                _, dh_planes, d_b1 = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes,
+                                                         drop=t.drop_ff, want_out=False, want_colsum=True)
                 d_w2 = ops.gemm_tc_splitk_rows(gfp, t.a_planes, M=d, N=dff, R=rows, passes=passes)     # gf^T . dropout(act(h_pre))
                 d_w1 = ops.gemm_tc_splitk_rows(dh_planes, t.u2_planes, M=dff, N=d, R=rows, passes=passes)   # dh^T . LN2(y)
             else:
+                dh, dh_planes = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes,
+                                                    drop=t.drop_ff)
                 d_w2 = ops.gemm_tc_splitk(ops.planes_t(gf, 128), ops.planes_t(t.h_pre, rc_ff, mode=2, act=act, drop=t.drop_ff),
                                           M=d, N=dff, K=rows, passes=passes)
                 d_w1 = ops.gemm_tc_splitk(ops.planes_t(dh, 128),
                                           ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln2_stats, gamma=w.g2, beta=w.be2,
                                                        row_map=t.row_map, alt=t.xs_new),
                                           M=dff, N=d, K=rows, passes=passes)
+                d_b1 = ops.colsum(dh).view(-1)
             del gfp
         else:
             da = dx_gemm(gf, w.w2, w.w2t_planes, dff)                              # [rows, dff]
@@ -174,7 +180,7 @@ class EncoderLayerFunction(torch.autograd.Function):
             u2, _, _ = ops.ln_rows(t.x_in, w.g2, w.be2, row_map=t.row_map, alt=t.xs_new, want_f32=True)
             d_w1 = ops.matmul_tn(dh, u2)                                           # [dff, d]
             del u2
-        d_b1 = ops.colsum(dh).view(-1)
+            d_b1 = ops.colsum(dh).view(-1)
         if dh_planes is not None:
             du2, _, _ = ops.gemm_tc(dh_planes, w.w1t_planes, M=rows, N=d, K=dff, passes=passes)
         else:

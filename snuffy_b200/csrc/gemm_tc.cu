@@ -17,7 +17,6 @@
 //   warps 2..9  epilogue: tcgen05.ld -> bias/activation -> (a) split-bf16 planes for the next GEMM, written
 //               straight from the row-owner register layout (512 B coalesced per warp store), and/or
 //               (b) fp32 rows (+ residual read through row_map) transposed through shared memory.
-#include <stdlib.h>
 #include <cuda.h>                      // CUtensorMap (types only: the encoder is looked up through the runtime, no -lcuda)
 #include "tc_ptx.cuh"
 
@@ -52,6 +51,9 @@ struct TcGemmParams {
     float drop_p; uint64_t seed, offset;                   // dropout on the activated value (before the residual)
     // backward of an activation fused into the dX product: v *= act'(gate[m, n]) before the dropout mask (dh = (dY W) * act'(h_pre))
     const float* gate; int64_t ldg; int gate_act;
+    // gate form only: column sums of the result per 32-row block, [m_tiles * 4][N] (folded by the host entry: the bias gradient
+    // db = sum over rows of dh, so dh itself never has to be written as fp32)
+    float* colsum_part;
     // block-diagonal B operand (attention backward against head-block matrices): B[n, k] is non-zero only where
     // n / group_n == k / group_k, so a column tile contracts only over the k-blocks of the groups it touches (group_n == 0: dense)
     int group_n, group_k;
@@ -332,6 +334,12 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                             *reinterpret_cast<bf16x8*>(dst + p.out_plane_stride + u * (TC_BM * 8)) = l;
                         }
                     }
+                    if (p.colsum_part) {                  // lane = column: rows beyond M hold zeros in the buffer
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum += stg[i * 33 + lane];
+                        if (col0 + lane < p.N) p.colsum_part[((int64_t)mt * 4 + quad) * p.N + col0 + lane] = sum;
+                    }
                     __syncwarp();
                     continue;
                 }
@@ -427,9 +435,8 @@ extern "C" {
 
 // Rows-per-chunk (= BLOCK_N of the kernel that will consume them) a [N, K] weight should be tiled with.
 int snuffy_gemm_tc_block_n(int64_t N) {
-    static const int64_t narrow_max_n = [] { const char* e = getenv("SNUFFY_B200_BN128_MAX_N"); return e ? atoll(e) : 0ll; }();
     const int64_t n128 = (N + 127) / 128;
-    return (n128 % 2 == 0 && N > narrow_max_n) ? 256 : 128;
+    return (n128 % 2 == 0) ? 256 : 128;
 }
 
 // bf16 elements in ONE plane of a [rows, K] operand tiled with rc rows per chunk
@@ -500,11 +507,12 @@ static int gemm_tc_full(const void* A_planes, int64_t a_plane_stride, const void
                         int64_t M, int64_t N, int64_t K, int passes, const float* bias, int act, const float* resid,
                         int64_t ldr, const int32_t* row_map, const float* resid_alt, float* out, int64_t ldc,
                         float* preact, void* out_planes, int64_t out_plane_stride, float dropout_p, uint64_t seed,
-                        uint64_t offset, const float* gate, int64_t ldg, int gate_act, cudaStream_t stream) {
+                        uint64_t offset, const float* gate, int64_t ldg, int gate_act, cudaStream_t stream,
+                        float* colsum_part = nullptr) {
     SNUFFY_REQUIRE(!gate || (ldg % 4 == 0 && ldg >= N && (uintptr_t)gate % 16 == 0),
                    "snuffy_gemm_tc_actgrad: the gate matrix must be 16-byte aligned with ldg %% 4 == 0, ldg >= N");
     SNUFFY_REQUIRE(A_planes && B_planes, "snuffy_gemm_tc: null operand");
-    SNUFFY_REQUIRE(out || out_planes || preact, "snuffy_gemm_tc: no output requested");
+    SNUFFY_REQUIRE(out || out_planes || preact || colsum_part, "snuffy_gemm_tc: no output requested");
     SNUFFY_REQUIRE(M >= 1 && N >= 1 && K >= 1, "snuffy_gemm_tc: empty problem");
     SNUFFY_REQUIRE(passes == 1 || passes == 3, "snuffy_gemm_tc: passes must be 1 or 3");
     SNUFFY_REQUIRE(N % 4 == 0 && (!out || (ldc % 4 == 0 && (uintptr_t)out % 16 == 0)) &&
@@ -529,7 +537,7 @@ static int gemm_tc_full(const void* A_planes, int64_t a_plane_stride, const void
     p.drop_p = dropout_p; p.seed = seed; p.offset = offset;
     p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
     p.a_nkb = p.num_kb; p.a_kb_off = 0;
-    p.gate = gate; p.ldg = ldg; p.gate_act = gate_act;
+    p.gate = gate; p.ldg = ldg; p.gate_act = gate_act; p.colsum_part = colsum_part;
     return launch_gemm_tc(p, N, stream, gate ? "snuffy_gemm_tc_actgrad" : "snuffy_gemm_tc");
 }
 
@@ -547,11 +555,19 @@ int snuffy_gemm_tc(const void* A_planes, int64_t a_plane_stride, const void* B_p
 int snuffy_gemm_tc_actgrad(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
                            int64_t M, int64_t N, int64_t K, int passes, const float* gate, int64_t ldg, int gate_act,
                            float dropout_p, uint64_t seed, uint64_t offset, float* out, int64_t ldc, void* out_planes,
-                           int64_t out_plane_stride, cudaStream_t stream) {
+                           int64_t out_plane_stride, float* colsum, float* colsum_partials, cudaStream_t stream) {
     SNUFFY_REQUIRE(gate, "snuffy_gemm_tc_actgrad: null gate");
-    return gemm_tc_full(A_planes, a_plane_stride, B_planes, b_plane_stride, M, N, K, passes, nullptr, ACT_NONE, nullptr, 0, nullptr,
-                        nullptr, out, ldc, nullptr, out_planes, out_plane_stride, dropout_p, seed, offset, gate, ldg, gate_act,
-                        stream);
+    SNUFFY_REQUIRE(!colsum || colsum_partials, "snuffy_gemm_tc_actgrad: column sums need their partials buffer");
+    if (int rc = gemm_tc_full(A_planes, a_plane_stride, B_planes, b_plane_stride, M, N, K, passes, nullptr, ACT_NONE, nullptr, 0,
+                              nullptr, nullptr, out, ldc, nullptr, out_planes, out_plane_stride, dropout_p, seed, offset, gate,
+                              ldg, gate_act, stream, colsum ? colsum_partials : nullptr))
+        return rc;
+    if (colsum) {
+        const int64_t parts = ((M + TC_BM - 1) / TC_BM) * 4;
+        fold_wide_kernel<float><<<(unsigned)((N + 15) / 16), 256, 0, stream>>>(colsum_partials, (int)parts, N, colsum);
+        return check_launch("snuffy_gemm_tc_actgrad");
+    }
+    return 0;
 }
 
 // out[M, N] (fp32, ldc) = A_window . B^T where A is the K window [a_col0, a_col0 + K) of a wider A-plane set over

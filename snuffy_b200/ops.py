@@ -258,16 +258,21 @@ def gemm_tc(a: Planes, b: Planes, *, M: int, N: int, K: int, passes: int = 3, bi
 
 
 def gemm_tc_actgrad(a: Planes, b: Planes, gate: torch.Tensor, act: str, *, M: int, N: int, K: int, passes: int = 3,
-                    drop: Tuple[float, int, int] = (0.0, 0, 0), want_out: bool = True, want_planes: bool = True):
-    """(A . B^T) * act'(gate) * dropout mask in the GEMM epilogue -> (fp32 [M, N] or None, A-operand Planes or None)."""
+                    drop: Tuple[float, int, int] = (0.0, 0, 0), want_out: bool = True, want_planes: bool = True,
+                    want_colsum: bool = False):
+    """(A . B^T) * act'(gate) * dropout mask in the GEMM epilogue -> (fp32 [M, N] or None, A-operand Planes or None[, column
+    sums [N] of the result when want_colsum])."""
     gate = _f32(gate, "gate")
     device = a.buf.device
     out = torch.empty(M, N, dtype=torch.float32, device=device) if want_out else None
     op = Planes(M, N, 128, device) if want_planes else None
+    cs = torch.empty(N, dtype=torch.float32, device=device) if want_colsum else None
+    csp = torch.empty((M + 127) // 128 * 4 * N, dtype=torch.float32, device=device) if want_colsum else None
     check(lib.snuffy_gemm_tc_actgrad(a.ptr, a.stride, b.ptr, b.stride, M, N, K, passes, gate.data_ptr(), gate.shape[-1],
                                      ACT_IDS[act], float(drop[0]), drop[1] & _U64, drop[2] & _U64, _ptr(out), N,
-                                     op.ptr if op else None, op.stride if op else 0, _stream()), "snuffy_gemm_tc_actgrad")
-    return out, op
+                                     op.ptr if op else None, op.stride if op else 0, _ptr(cs), _ptr(csp), _stream()),
+          "snuffy_gemm_tc_actgrad")
+    return (out, op, cs) if want_colsum else (out, op)
 
 
 # ------------------------------------------------------------------ a9: sparse attention

@@ -177,6 +177,11 @@ def test_gemm_tc_actgrad_epilogue(ops, act, M, N, K, p):
     if p > 0:
         zero = (out == 0).float().mean().item()
         assert abs(zero - p) < 0.05 or act == "relu"
+    # the bias gradient from the same epilogue, with neither fp32 nor plane output
+    _, _, cs = ops.gemm_tc_actgrad(ap, bp, gate, act, M=M, N=N, K=K, drop=drop, want_out=False, want_planes=False,
+                                   want_colsum=True)
+    ref = out.double().sum(0)
+    assert float((cs.double() - ref).abs().max()) < 1e-5 * max(1.0, float(out.abs().sum(0).max()))
 
 
 @pytest.mark.parametrize("M,h,gn,gk", [(1000, 8, 200, 64), (300, 4, 24, 32), (257, 2, 40, 32), (500, 8, 64, 200), (384, 4, 16, 8),
