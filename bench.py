@@ -469,6 +469,18 @@ def train_epoch_bench(device, world, rank, slides=TRAIN_SLIDES, warm=3):
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         res["allreduce_ms"] = statistics.median(times[5:])
+        res["allreduce"] = "one kernel over NVLink peer memory (csrc/comm.cu)" if trainer.flat.peer is not None else "nccl"
+        if trainer.flat.peer is not None:                            # NCCL on a buffer of the same size, for comparison
+            other, times = torch.zeros_like(trainer.flat._grad_all), []
+            for _ in range(25):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                e0.record()
+                dist.all_reduce(other)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            res["allreduce_nccl_ms"] = statistics.median(times[5:])
         del trainer
         ms_local, _, _ = run(False)                                   # the same step with no collective, on this rank alone
         t = torch.tensor([ms_local], device=device)

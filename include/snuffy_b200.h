@@ -334,6 +334,23 @@ int snuffy_froc_detections(const float* probs, int64_t prob_stride, const int32_
                            int32_t tile, int32_t half, float* det_prob, int32_t* det_xy, int32_t* count,
                            snuffy_stream_t stream);
 
+/* ---- (e) data-parallel exchange: gradient all-reduce over NVLink peer memory (csrc/comm.cu) ---------------------------
+ * The reference trains one process on one GPU (train.py:249-264); sharding slides over ranks adds ONE exchange per optimizer
+ * step: the sum of the flat gradient.  Every rank allocates one block with snuffy_comm_alloc (plain cudaMalloc, zero filled),
+ * exports it (snuffy_comm_export -> snuffy_comm_handle_bytes() opaque bytes, exchanged by the host through any channel) and
+ * maps its peers' blocks (snuffy_comm_import).  snuffy_peer_allreduce is then one kernel: barrier, every rank sums its slice
+ * of all buffers in rank order reading peer memory directly, writes the sum into all buffers, barrier.  In place, identical
+ * bits on every rank, capturable in a CUDA graph; all ranks must make the same sequence of calls.                        */
+int snuffy_comm_alloc(int64_t bytes, void** ptr);
+int snuffy_comm_free(void* ptr);
+int snuffy_comm_handle_bytes(void);
+int snuffy_comm_export(void* ptr, void* handle_out);
+int snuffy_comm_import(const void* handle, void** ptr);
+int snuffy_comm_close(void* ptr);
+int snuffy_comm_counter_bytes(void);
+int snuffy_peer_allreduce(void* const* bufs, void* const* counters, void* state, int rank, int world, int64_t n,
+                          snuffy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,14 @@ _SIGNATURES = {
     "snuffy_sumsq_blocks": (c_int64, [I]),
     "snuffy_sumsq": (c_int, [P, I, P, P, P]),
     "snuffy_pack_f32": (c_int, [P, P, P, I, P, P]),
+    "snuffy_comm_alloc": (c_int, [I, ctypes.POINTER(c_void_p)]),
+    "snuffy_comm_free": (c_int, [P]),
+    "snuffy_comm_handle_bytes": (c_int, []),
+    "snuffy_comm_export": (c_int, [P, P]),
+    "snuffy_comm_import": (c_int, [P, ctypes.POINTER(c_void_p)]),
+    "snuffy_comm_close": (c_int, [P]),
+    "snuffy_comm_counter_bytes": (c_int, []),
+    "snuffy_peer_allreduce": (c_int, [P, P, P, c_int, c_int, I, P]),
     "snuffy_adamw_flat": (c_int, [P, P, P, P, I, c_float, c_float, c_float, c_float, c_float, I, c_float, P, c_float, P]),
     "snuffy_adamw_flat_dev": (c_int, [P, P, P, P, I, c_float, c_float, c_float, c_float, c_float, P, P, P, c_float, P, c_float,
                                      c_float, c_float, P]),

@@ -17,6 +17,8 @@
 //   warps 2..9  epilogue: tcgen05.ld -> bias/activation -> (a) split-bf16 planes for the next GEMM, written
 //               straight from the row-owner register layout (512 B coalesced per warp store), and/or
 //               (b) fp32 rows (+ residual read through row_map) transposed through shared memory.
+#include <stdlib.h>
+#include <mutex>
 #include <cuda.h>                      // CUtensorMap (types only: the encoder is looked up through the runtime, no -lcuda)
 #include "tc_ptx.cuh"
 
@@ -70,7 +72,17 @@ struct TcGemmParams {
     // chunk) contracted over their rows: A = planes of dY [K rows, M features], B = planes of X [K rows, N features], k-blocks
     // of 32 rows; a_nkb / b_nkb = feature k-blocks per row tile of each plane set
     int b_nkb;
+    // Tail split ("stream-K" for the last, partial wave): items [0, full_items) are whole tiles (times ksplit); the remaining
+    // tail_tiles tiles, which would keep only tail_tiles of the SMs busy for a whole tile time, are cut into tail_s K slices of
+    // tail_per k-blocks, one CTA each.  Slice 0 owns the tile's epilogue; the others hand their raw accumulators over through
+    // tail_part [tail tile][slice - 1][128 x BN values in register order] and count themselves in tail_flags[2 * tile] (8 warps each); the owner adds
+    // them in slice order (deterministic) and re-arms the flags.
+    int full_items, tail_tiles, tail_s, tail_per;
+    float* tail_part; unsigned int* tail_flags;
 };
+
+// One work item of a CTA's persistent loop.
+struct TcItem { int mt, nt, ksp, kb0, kb1, mode, tt, slice; };     // mode -1 skip, 0 whole tile, 1 owning tail slice, 2 other tail slice
 
 // out of line on purpose: 32 inlined copies of the activation switch per chunk bloat the epilogue (instruction-cache misses
 // slow the whole CTA down); ReLU, the common case, is handled inline
@@ -94,6 +106,27 @@ __host__ __device__ __forceinline__ bool tile_live(int M, int N, int bn, int dia
     if (diag_m <= 0) return true;
     const int r_lo = mt * TC_BM, r_hi = min(M, r_lo + TC_BM) - 1, c_lo = nt * bn, c_hi = min(N, c_lo + bn) - 1;
     return r_lo / diag_m <= c_hi / diag_n && c_lo / diag_n <= r_hi / diag_m;
+}
+
+template <int BN>
+__device__ __forceinline__ bool tc_item(const TcGemmParams& p, int it, TcItem& w) {
+    const int idx = blockIdx.x + it * gridDim.x;
+    if (idx < p.full_items) {
+        w.ksp = idx % p.ksplit;
+        const int t2 = idx / p.ksplit;
+        w.mt = t2 / p.n_tiles; w.nt = t2 % p.n_tiles; w.tt = 0; w.slice = 0;
+        w.mode = tile_live(p.M, p.N, BN, p.diag_m, p.diag_n, w.mt, w.nt) ? 0 : -1;
+        tile_kb_range<BN>(p, w.ksp, w.nt, w.kb0, w.kb1);
+        return true;
+    }
+    const int j = idx - p.full_items;
+    if (j >= p.tail_tiles * p.tail_s) return false;
+    w.tt = j / p.tail_s; w.slice = j % p.tail_s; w.ksp = 0;
+    const int t2 = p.full_items + w.tt;                            // the tail split is only planned for ksplit == 1
+    w.mt = t2 / p.n_tiles; w.nt = t2 % p.n_tiles;
+    w.kb0 = w.slice * p.tail_per; w.kb1 = min(p.num_kb, w.kb0 + p.tail_per);
+    w.mode = w.slice == 0 ? 1 : 2;
+    return true;
 }
 
 template <int BN, bool MN = false>
@@ -125,7 +158,6 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
     const bool use_lo = p.npairs > 1;
     const uint32_t stage_tx = use_lo ? Cfg::STAGE_BYTES : (TC_A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
 
@@ -133,12 +165,10 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
         // ------------------------------------------------ producer
         int stage = 0; uint32_t phase = 0;
         const int64_t a_chunk = (int64_t)TC_BM * PLANE_KB, b_chunk = (int64_t)BN * PLANE_KB;   // elements
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
-            const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
-            if (!tile_live(p.M, p.N, BN, p.diag_m, p.diag_n, mt, nt)) continue;
-            int kb0, kb1;
-            tile_kb_range<BN>(p, ksp, nt, kb0, kb1);
+        TcItem w;
+        for (int it = 0; tc_item<BN>(p, it, w); ++it) {
+            if (w.mode < 0) continue;
+            const int mt = w.mt, nt = w.nt, kb0 = w.kb0, kb1 = w.kb1;
             const __nv_bfloat16* a_src = p.A + ((int64_t)mt * p.a_nkb + p.a_kb_off) * a_chunk;
             const __nv_bfloat16* b_src = p.B + (int64_t)nt * p.num_kb * b_chunk;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -182,11 +212,10 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
         constexpr uint32_t KS_A = MN ? 256 : 2 * LBO_A, KS_B = MN ? 256 : 2 * LBO_B;
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
-            if (!tile_live(p.M, p.N, BN, p.diag_m, p.diag_n, t2 / p.n_tiles, t2 % p.n_tiles)) continue;
-            int kb0, kb1;
-            tile_kb_range<BN>(p, ksp, t2 % p.n_tiles, kb0, kb1);
+        TcItem w;
+        for (int it = 0; tc_item<BN>(p, it, w); ++it) {
+            if (w.mode < 0) continue;
+            const int kb0 = w.kb0, kb1 = w.kb1;
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -232,16 +261,28 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
         const int kpad_next = nkb_next * PLANE_KB;
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;           // coalesced phase: 4 rows x 8 float4 per pass
         constexpr int CH = BN / 64;                                // 32-column chunks per half
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int ksp = tile % p.ksplit, t2 = tile / p.ksplit;
-            const int mt = t2 / p.n_tiles, nt = t2 % p.n_tiles;
-            if (!tile_live(p.M, p.N, BN, p.diag_m, p.diag_n, mt, nt)) continue;
+        TcItem w;
+        for (int it = 0; tc_item<BN>(p, it, w); ++it) {
+            if (w.mode < 0) continue;
+            const int mt = w.mt, nt = w.nt, ksp = w.ksp;
             float* const outp = p.out ? p.out + (int64_t)ksp * p.split_stride : nullptr;
             const int rr_own = quad * 32 + lane;                   // row of the tile this thread owns in TMEM
             const int64_t m_own = (int64_t)mt * TC_BM + rr_own;
             const int64_t m_base = (int64_t)mt * TC_BM + quad * 32;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
+            // tail slices: this thread's row of the raw accumulators other slices hand over / this slice hands over
+            // (stored in the register layout [warp][chunk][float4 j][lane]: every warp access is 512 contiguous bytes)
+            float* const part_row = p.tail_part + ((int64_t)w.tt * (p.tail_s - 1) + (w.slice > 0 ? w.slice - 1 : 0)) * (TC_BM * BN) +
+                                    (int64_t)(quad * 2 + half) * (CH * 1024) + lane * 4;
+            if (w.mode == 1) {
+                const unsigned int want = (unsigned int)(p.tail_s - 1) * 8u;
+                unsigned int have;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(p.tail_flags + 2 * w.tt) : "memory");
+                    if (have < want) __nanosleep(64);
+                } while (have < want);
+            }
 #pragma unroll 1
             for (int cc = 0; cc < CH; ++cc) {
                 const int c = half * CH + cc;
@@ -249,6 +290,23 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                 if (col0 >= p.N && col0 >= kpad_next) break;
                 float v[32];
                 tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                if (w.mode == 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        __stcg(reinterpret_cast<float4*>(part_row + cc * 1024 + j * 32), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    continue;
+                }
+                if (w.mode == 1) {
+#pragma unroll 1
+                    for (int sl = 1; sl < p.tail_s; ++sl) {
+                        const float* src = part_row + (int64_t)(sl - 1) * TC_BM * BN + cc * 1024;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 q = __ldcg(reinterpret_cast<const float4*>(src + j * 32));
+                            v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                        }
+                    }
+                }
                 if (p.bias) {
                     if (col0 + 32 <= p.N) {
 #pragma unroll
@@ -412,6 +470,17 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                     __syncwarp();
                 }
             }
+            if (w.mode == 2) {                         // hand-over complete: count this warp in (release)
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(p.tail_flags + 2 * w.tt, 1u);
+            } else if (w.mode == 1) {                  // the last of the owner's warps re-arms the flags for the next launch
+                __syncwarp();
+                if (lane == 0 && atomicAdd(p.tail_flags + 2 * w.tt + 1, 1u) == 7u) {
+                    p.tail_flags[2 * w.tt] = 0u;
+                    p.tail_flags[2 * w.tt + 1] = 0u;
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -480,13 +549,76 @@ static int row_planes_tensor_map(CUtensorMap* tm, const void* planes, int64_t pl
     return 0;
 }
 
+// Hand-over buffers of the tail split: a few per device, each claimed by the first stream that needs one (launches on one
+// stream are ordered, so a buffer is never shared by two running kernels).  Allocated on the first launch outside a stream
+// capture; a launch that finds none (all claimed, or first use inside a capture) simply runs without the tail split.
+struct TailWorkspace { int device; cudaStream_t stream; bool claimed; float* part; unsigned int* flags; };
+constexpr int TAIL_WS_PER_DEVICE = 4, TAIL_WS_MAX = 64;
+constexpr size_t TAIL_PART_BYTES = (size_t)160 * TC_BM * 256 * sizeof(float);      // >= SM count partial tiles
+static TailWorkspace g_tail_ws[TAIL_WS_MAX];
+static int g_tail_ws_n = 0;
+static std::mutex g_tail_ws_mutex;
+
+static TailWorkspace* tail_workspace(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_tail_ws_mutex);
+    TailWorkspace* free_slot = nullptr;
+    bool have_device = false;
+    for (int i = 0; i < g_tail_ws_n; ++i) {
+        TailWorkspace& w = g_tail_ws[i];
+        if (w.device != dev) continue;
+        have_device = true;
+        if (w.claimed && w.stream == stream) return &w;
+        if (!w.claimed && !free_slot) free_slot = &w;
+    }
+    if (!have_device) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
+        if (g_tail_ws_n + TAIL_WS_PER_DEVICE > TAIL_WS_MAX) return nullptr;
+        for (int i = 0; i < TAIL_WS_PER_DEVICE; ++i) {
+            TailWorkspace w{dev, nullptr, false, nullptr, nullptr};
+            if (cudaMalloc(&w.part, TAIL_PART_BYTES) != cudaSuccess || cudaMalloc(&w.flags, 4096) != cudaSuccess ||
+                cudaMemset(w.flags, 0, 4096) != cudaSuccess) {
+                cudaGetLastError();
+                return free_slot;
+            }
+            g_tail_ws[g_tail_ws_n++] = w;
+            if (!free_slot) free_slot = &g_tail_ws[g_tail_ws_n - 1];
+        }
+        cudaDeviceSynchronize();                           // the flags are zero before any stream uses them
+    }
+    if (free_slot) { free_slot->claimed = true; free_slot->stream = stream; }
+    return free_slot;
+}
+
 static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const char* who, int force_bn = 0,
                           const CUtensorMap* tm_a = nullptr, const CUtensorMap* tm_b = nullptr) {
     const int bn = force_bn ? force_bn : snuffy_gemm_tc_block_n(N);
     const int total = p.m_tiles * p.n_tiles * p.ksplit;
-    const int grid = total < sm_count() ? total : sm_count();
+    int grid = total < sm_count() ? total : sm_count();
     static const CUtensorMap none{};
     const bool mn = tm_a != nullptr;
+    p.full_items = total; p.tail_tiles = 0; p.tail_s = 1; p.tail_per = p.num_kb; p.tail_part = nullptr; p.tail_flags = nullptr;
+    static const bool tail_split = [] { const char* e = getenv("SNUFFY_B200_TAIL_SPLIT"); return !e || atoi(e) != 0; }();
+    const int sm = sm_count(), rem = total % sm;
+    if (tail_split && !mn && p.ksplit == 1 && p.diag_m == 0 && p.group_n == 0 && rem > 0 && sm <= 160) {
+        // Measured (tools/time_gemm_shapes.py, 10 000 rows): a hand-over costs ~6 us end to end (128 KB out through L2, fence,
+        // flag, 128 KB back in, before the owner's epilogue can start), so the split only pays when the tile it shortens is
+        // long: K >= 1536 (FFN-down and its dX twin: 73 -> 63 us); at K = 512 / 1024 it loses 1-5 us and is not planned.
+        int sl = p.num_kb >= 48 ? 4 : 1;
+        if (sl > sm / rem) sl = sm / rem;
+        if (sl > p.num_kb / 2) sl = p.num_kb / 2;
+        if (sl >= 2) {
+            if (TailWorkspace* ws = tail_workspace(stream)) {
+                const int per = (p.num_kb + sl - 1) / sl;
+                sl = (p.num_kb + per - 1) / per;                           // every slice owns at least one k-block
+                p.full_items = total - rem; p.tail_tiles = rem; p.tail_s = sl; p.tail_per = per;
+                p.tail_part = ws->part; p.tail_flags = ws->flags;
+                grid = p.full_items > 0 ? sm : rem * sl;
+            }
+        }
+    }
     if (mn && bn == 256) {
         SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<256, true>), (int)TcCfg<256>::SMEM_BYTES));
         gemm_tc_kernel<256, true><<<grid, TC_THREADS, TcCfg<256>::SMEM_BYTES, stream>>>(p, *tm_a, *tm_b);

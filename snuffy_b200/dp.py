@@ -11,6 +11,8 @@ max-instance + 2 x BCE loss (train.py:828-846), the gradient-norm clip and AdamW
 """
 from __future__ import annotations
 
+import os
+import socket
 from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -48,6 +50,102 @@ def steps_per_epoch(num_slides: int, world: int, bags_per_step: int = 1, lengths
 
 
 # ------------------------------------------------------------------ flat parameter / gradient buffers
+class _RawCudaFloats:
+    """Zero-copy view of device memory this package allocated itself (torch.as_tensor reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, numel: int, owner):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+class PeerAllReduce:
+    """The gradient all-reduce of the data-parallel step as ONE kernel over NVLink peer memory (csrc/comm.cu): every rank's
+    gradient buffer lives in a cudaMalloc'd block its peers map through CUDA IPC; each rank sums its slice of all buffers in
+    rank order and writes the sum back into all of them (two-shot), with per-CTA barriers on counters in the same blocks.
+    One node, 2..8 ranks, one GPU per rank.  `setup` is collective and returns None on EVERY rank if any rank cannot map its
+    peers (the trainer then keeps the NCCL all-reduce)."""
+
+    def __init__(self):
+        self.ptr = None
+
+    @classmethod
+    def setup(cls, numel: int, device: torch.device, group=None):
+        import ctypes
+        from . import _lib
+        lib = _lib.lib
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self = cls()
+        self.world, self.rank, self.numel, self.group = world, rank, (numel + 3) // 4 * 4, group
+        ok, err = 2 <= world <= 8 and device.type == "cuda" and os.environ.get("SNUFFY_B200_PEER_ALLREDUCE", "1") != "0", ""
+        counter_bytes = lib.snuffy_comm_counter_bytes()
+        self._data_bytes = (self.numel * 4 + 255) // 256 * 256
+        total = self._data_bytes + counter_bytes + 256
+        handle = b""
+        if ok:
+            try:
+                with torch.cuda.device(device):
+                    base = ctypes.c_void_p()
+                    _lib.check(lib.snuffy_comm_alloc(total, ctypes.byref(base)), "snuffy_comm_alloc")
+                    self.ptr = base.value
+                    hb = ctypes.create_string_buffer(lib.snuffy_comm_handle_bytes())
+                    _lib.check(lib.snuffy_comm_export(self.ptr, hb), "snuffy_comm_export")
+                    handle = hb.raw
+            except Exception as exc:                                   # noqa: BLE001 - any failure means "no peer path"
+                ok, err = False, repr(exc)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ok, handle, socket.gethostname(), device.index), group=group)
+        ok = all(g[0] for g in gathered) and len({g[2] for g in gathered}) == 1 and len({g[3] for g in gathered}) == world
+        self._peers = []
+        bases = [0] * world
+        if ok:
+            try:
+                with torch.cuda.device(device):
+                    for q, g in enumerate(gathered):
+                        if q == rank:
+                            bases[q] = self.ptr
+                            continue
+                        mapped = ctypes.c_void_p()
+                        _lib.check(lib.snuffy_comm_import(g[1], ctypes.byref(mapped)), "snuffy_comm_import")
+                        self._peers.append(mapped.value)
+                        bases[q] = mapped.value
+            except Exception as exc:                                   # noqa: BLE001
+                ok, err = False, repr(exc)
+        flags = [None] * world
+        dist.all_gather_object(flags, ok, group=group)
+        if not all(flags):
+            self.close()
+            if err and rank == 0:
+                print(f"snuffy_b200.dp: peer-memory all-reduce unavailable ({err}); using the NCCL all-reduce", flush=True)
+            return None
+        self._bufs = (ctypes.c_void_p * world)(*bases)
+        self._counters = (ctypes.c_void_p * world)(*[b + self._data_bytes for b in bases])
+        self._state = self.ptr + self._data_bytes + counter_bytes
+        self.device = device
+        self.buffer = torch.as_tensor(_RawCudaFloats(self.ptr, self.numel, self), device=device)
+        return self
+
+    def all_reduce(self) -> None:
+        from . import _lib
+        _lib.check(_lib.lib.snuffy_peer_allreduce(self._bufs, self._counters, self._state, self.rank, self.world, self.numel,
+                                                  torch.cuda.current_stream(self.device).cuda_stream), "snuffy_peer_allreduce")
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                                             # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def close(self) -> None:
+        """Unmap the peers' blocks and free this rank's (call only when no step is in flight: after a synchronize)."""
+        from . import _lib
+        for m in getattr(self, "_peers", []):
+            _lib.lib.snuffy_comm_close(m)
+        self._peers = []
+        if self.ptr:
+            _lib.lib.snuffy_comm_free(self.ptr)
+            self.ptr = None
+
+
 class FlatBuffers:
     """All parameters (and their gradients) of a module as views into two flat fp32 buffers, in
     ``named_parameters()`` order: L*(12 d^2 + 13 d) + 2 d + 2 (d C + C) floats (12.6 MB per layer at d = 512).
@@ -57,7 +155,8 @@ class FlatBuffers:
     step: 1 on a rank that had a bag, 0 on an idle rank; the all-reduce sums it with the gradient, and the optimizer kernel
     divides by it (uneven shards: `steps_per_epoch`)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], extra: Iterable[torch.Tensor] = ()):
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: Iterable[torch.Tensor] = (), peer_group=None):
+        self.peer = None
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -72,7 +171,10 @@ class FlatBuffers:
         self.model_numel = self.offsets[self.n_model_params]                   # the module's parameters: [0, model_numel)
         self._total = total
         self._param_all = torch.zeros(total + 4, dtype=torch.float32, device=dev)
-        self._grad_all = torch.zeros(total + 4, dtype=torch.float32, device=dev)
+        if peer_group is not False and dev.type == "cuda" and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size(peer_group) > 1:
+            self.peer = PeerAllReduce.setup(total + 4, dev, peer_group)           # the gradient buffer lives in peer-mapped memory
+        self._grad_all = self.peer.buffer if self.peer is not None else torch.zeros(total + 4, dtype=torch.float32, device=dev)
         self.flat_param = self._param_all[:total]
         self.flat_grad = self._grad_all[:total]
         self.contributors = self._grad_all[total:total + 1]                    # summed by the all-reduce
@@ -128,7 +230,10 @@ class FlatBuffers:
     def allreduce_sum(self, group=None) -> None:
         """THE collective of the path: one all-reduce of the flat gradient buffer (and its contributor slot)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self._grad_all, op=dist.ReduceOp.SUM, group=group)
+            if self.peer is not None:
+                self.peer.all_reduce()                                          # one kernel over NVLink peer memory (csrc/comm.cu)
+            else:
+                dist.all_reduce(self._grad_all, op=dist.ReduceOp.SUM, group=group)
 
 
 # ------------------------------------------------------------------ fused loss (train.py:828-846)
@@ -280,7 +385,8 @@ class DataParallelTrainer:
         dev = next(model.parameters()).device
         # train.py:804: a 0-dim tensor, clamped to [0, 1], trainable only with --soft_average
         self.single_weight_parameter = torch.tensor(float(mix_weight), device=dev).clamp_(0, 1).requires_grad_(bool(soft_average))
-        self.flat = FlatBuffers(model.parameters(), extra=[self.single_weight_parameter])
+        self.flat = FlatBuffers(model.parameters(), extra=[self.single_weight_parameter],
+                                peer_group=group if self.world > 1 else False)
         if self.world > 1:                                            # identical start on every rank
             dist.broadcast(self.flat.flat_param, src=0, group=group)
         self.opt = FlatAdamW(self.flat, lr=lr, betas=betas, weight_decay=weight_decay, clip_grad=clip_grad,

@@ -36,6 +36,27 @@ def test_gemm_tc_three_pass_matches_fp32(ops, M, N, K):
     assert np.abs(out.cpu().numpy() - simt).max() < 3e-5 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("M,N,K", [(10000, 512, 2048), (1000, 512, 2048), (300, 256, 1536), (19000, 512, 3072), (200, 768, 3072)])
+def test_gemm_tc_tail_split_long_k(ops, M, N, K):
+    """K >= 1536: the tiles of the last, partial wave are cut into K slices that hand their accumulators over to the slice
+    owning the epilogue (bias, residual through row_map, planes).  Against fp64, bit-identical from launch to launch, and the
+    hand-over buffers re-armed for the next call."""
+    a, b, ad, bd, ap, bp = _operands(ops, M, N, K, M + N + K + 7)
+    rs = np.random.RandomState(5)
+    bias = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).cuda()
+    resid = torch.from_numpy(rs.standard_normal((M, N)).astype(np.float32)).cuda()
+    outs = []
+    for _ in range(3):
+        out, _, planes = ops.gemm_tc(ap, bp, M=M, N=N, K=K, passes=3, bias=bias, resid=resid, want_planes=True)
+        outs.append(out)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T + bias.cpu().numpy() + resid.cpu().numpy()
+    assert np.abs(outs[0].cpu().numpy() - ref).max() < 3e-5 * max(1.0, np.abs(ref).max())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    hi, lo = decode_planes(planes, M, N)
+    want = ref - resid.cpu().numpy()                          # the planes carry the activated value, before the residual
+    assert np.abs((hi + lo)[:, :N] - want).max() < 3e-5 * max(1.0, np.abs(want).max())
+
+
 def test_gemm_tc_single_pass_is_bf16(ops):
     M, N, K = 256, 256, 128
     a, b, ad, bd, ap, bp = _operands(ops, M, N, K, 1)

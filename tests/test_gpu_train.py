@@ -205,6 +205,18 @@ def _dp_worker(rank, world, port, out):
                 m.p = 0.0
         set_precision(model, "fp32")
         trainer = dp.DataParallelTrainer(model, lr=1e-3)
+        # the exchange itself: the peer-memory kernel (csrc/comm.cu) against NCCL on a random buffer, three calls in a row
+        peer_used, peer_err = trainer.flat.peer is not None, 0.0
+        if peer_used:
+            g = torch.Generator(device=f"cuda:{rank}").manual_seed(100 + rank)
+            for _ in range(3):
+                x = torch.randn(trainer.flat._grad_all.numel(), device=f"cuda:{rank}", generator=g)
+                ref = x.clone()
+                dist.all_reduce(ref)
+                trainer.flat._grad_all.copy_(x)
+                trainer.flat.allreduce_sum()
+                peer_err = max(peer_err, float((trainer.flat._grad_all - ref).abs().max()))
+            trainer.flat.zero_grad()
         rs = np.random.RandomState(11)
         bags = rs.standard_normal((4, 1, c["n"], c["d"])).astype(np.float32)
         labels = [1.0, 0.0, 1.0, 0.0]
@@ -221,7 +233,7 @@ def _dp_worker(rank, world, port, out):
             trainer.train_step(None, None)
         contributors = float(trainer.flat.contributors)
         moved = float((trainer.flat.flat_param - before).abs().max())
-        out[rank] = (trainer.flat.flat_param.detach().cpu(), grads[0], contributors, moved)
+        out[rank] = (trainer.flat.flat_param.detach().cpu(), grads[0], contributors, moved, peer_used, peer_err)
     finally:
         dist.destroy_process_group()
 
@@ -238,6 +250,9 @@ def test_two_gpu_data_parallel_equals_gradient_averaging():
     mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])      # replicas stay bit-identical
     assert out[0][2] == out[1][2] == 1.0 and out[0][3] == out[1][3] > 0                 # idle rank: one contributor, same update
+    if os.environ.get("SNUFFY_B200_PEER_ALLREDUCE", "1") != "0":
+        assert out[0][4] and out[1][4], "the peer-memory all-reduce was not set up (CUDA IPC between the two GPUs failed)"
+        assert out[0][5] < 1e-5 and out[1][5] < 1e-5, (out[0][5], out[1][5])
     z, c = load_golden("bin_tiny_relu")
     params, _ = snuffy_inputs(c)
     model = load_params(build_snuffy(snuffy, c), params)
