@@ -155,6 +155,13 @@ int snuffy_gemm_tc_actgrad(const void* A_planes, int64_t a_plane_stride, const v
                            int64_t ldg, int gate_act, float dropout_p, uint64_t seed, uint64_t offset, float* out,
                            int64_t ldc, void* out_planes, int64_t out_plane_stride, float* colsum,
                            float* colsum_partials, snuffy_stream_t stream);
+/* The same for ReLU, gated by the forward's own activated planes (snuffy_gemm_tc's out_planes of FFN-up, hi plane):
+ * result = (A . B^T) * (a[m, n] > 0 ? 1 / (1 - dropout_p) : 0): neither the fp32 pre-activation nor the dropout draw is
+ * needed again (a clamped or dropped element is exactly 0 in the planes).  Autograd of snuffy.py:225 with --activation relu. */
+int snuffy_gemm_tc_relugrad(const void* A_planes, int64_t a_plane_stride, const void* B_planes,
+                            int64_t b_plane_stride, int64_t M, int64_t N, int64_t K, int passes,
+                            const void* act_planes, float dropout_p, float* out, int64_t ldc, void* out_planes,
+                            int64_t out_plane_stride, float* colsum, float* colsum_partials, snuffy_stream_t stream);
 /* out = A_window . B^T against a block-diagonal B (B[n, k] != 0 only where n / group_n == k / group_k: the head-block
  * operands of the attention backward, autograd of snuffy.py:160-168 with the head split of 187-201): every column tile
  * contracts only over the k-blocks of the groups it touches.

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "snuffy_gemm_tc_diag_ksplit": (c_int64, [I, I, I, c_int, I, I]),
     "snuffy_gemm_tc_splitk_blockdiag": (c_int, [P, I, P, I, c_int, I, I, I, c_int, I, I, I, P, P, I, P]),
     "snuffy_gemm_tc_blockdiag": (c_int, [P, I, I, I, P, I, c_int, I, I, I, c_int, I, I, P, I, P]),
+    "snuffy_gemm_tc_relugrad": (c_int, [P, I, P, I, I, I, I, c_int, P, c_float, P, I, P, I, P, P, P]),
     "snuffy_gemm_tc_actgrad": (c_int, [P, I, P, I, I, I, I, c_int, P, I, c_int, c_float, c_uint64, c_uint64, P, I, P, I, P, P,
                                        P]),
     "snuffy_attn_seg_bwd": (c_int, [P, P, I, I, I, I, c_int, c_float, c_float, c_uint64, c_uint64, P, P, P, I, P]),

@@ -21,8 +21,6 @@ from . import engine, ops
 #: GEMMs over block-diagonal head operands + row kernels), "simt" (fp32 SIMT products)
 ATTN_BWD = __import__("os").environ.get("SNUFFY_B200_ATTN_BWD", "fused")
 ATTN_BWD_TC = ATTN_BWD != "simt"
-#: weight gradients of the three all-row projections straight from row planes (MN-major descriptors); "0" = from transposed copies
-DW_BY_ROWS = __import__("os").environ.get("SNUFFY_B200_DW_BY_ROWS", "1") != "0"
 
 
 def _flat(t: torch.Tensor, d: int) -> torch.Tensor:
@@ -135,7 +133,7 @@ class EncoderLayerFunction(torch.autograd.Function):
                 w.prepare(precision)
                 w.prepare_backward()
             rc_d, rc_ff = ops._block_n(d), ops._block_n(dff)
-        by_rows = tc and DW_BY_ROWS and t.a_planes is not None
+        by_rows = tc and engine.DW_BY_ROWS and t.a_planes is not None
 
         def dx_gemm(dy, w_f32, wt_planes, n_in):                # dX = dY . W        (W = nn.Linear.weight [out, in])
             if not tc:
@@ -156,8 +154,12 @@ class EncoderLayerFunction(torch.autograd.Function):
                 # forward's GEMM operands, this pass's dX operands); db1 = column sums of dh from the same epilogue, so dh is
                 # never written as fp32
                 dh = None
-                _, dh_planes, d_b1 = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes,
-                                                         drop=t.drop_ff, want_out=False, want_colsum=True)
+                if t.h_pre is None:       # ReLU: the gate is read off the forward's activated planes (no h_pre, no dropout draw)
+                    _, dh_planes, d_b1 = ops.gemm_tc_relugrad(gfp, w.w2t_planes, t.a_planes, t.drop_ff[0], M=rows, N=dff, K=d,
+                                                              passes=passes, want_colsum=True)
+                else:
+                    _, dh_planes, d_b1 = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes,
+                                                             drop=t.drop_ff, want_out=False, want_colsum=True)
                 d_w2 = ops.gemm_tc_splitk_rows(gfp, t.a_planes, M=d, N=dff, R=rows, passes=passes)     # gf^T . dropout(act(h_pre))
                 d_w1 = ops.gemm_tc_splitk_rows(dh_planes, t.u2_planes, M=dff, N=d, R=rows, passes=passes)   # dh^T . LN2(y)
             else:

@@ -441,10 +441,37 @@ attn_tc_kernel(const AttnTcParams p) {
                     so[0] = mx * (p.c_log2 * 0.69314718055994530942f);     // max of the scaled scores (natural units)
                     so[1] = inv;
                 }
+                const DrawKey dkey = rng_resolve(p.seed, p.offset);
+                const DropFast dfast = drop_fast_setup(dkey.seed, dkey.offset, EXTRA ? p.drop_p : 0.f);
+                const bool small_index = (int64_t)p.B * p.h * p.N * p.Ksel < (1ll << 32);
+                // The attention dropout is drawn in a ROLLED loop (one 8-key group per trip) into a bit mask: unrolled over this
+                // thread's ~70 scores the hash alone was 1400 instructions in the tile loop, and the softmax warps then ran out of
+                // the instruction cache (0.146 -> 0.436 ms per 8 slides); the unrolled P phase below only tests a bit.
+                uint64_t keep_lo = 0ull, keep_hi = 0ull;
+                if (EXTRA && p.drop_p > 0.f && valid) {
+#pragma unroll 1
+                    for (int gi = 0; gi < ng; ++gi) {
+                        const int kb = (g0 + gi) * 8;
+                        uint32_t bits = 0;
+                        if (small_index) {                           // element indices below 2^32: hoisted form of the same draw
+                            const uint32_t e0 = (uint32_t)srow * (uint32_t)p.Ksel + (uint32_t)(key0 + kb);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) bits |= (drop_fast_keep(dfast, e0 + e) ? 1u : 0u) << e;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const uint64_t idx = ((uint64_t)srow * p.Ksel + key0 + kb + e);
+                                bits |= (drop_keep_scale(dkey.seed, dkey.offset, idx, p.drop_p) != 0.f ? 1u : 0u) << e;
+                            }
+                        }
+                        // the backward kernel reads the draw back instead of hashing every score again (twice)
+                        if (p.drop_mask && kb < kvalid) p.drop_mask[srow * ((p.Ksel + 7) / 8) + ((key0 + kb) >> 3)] = (uint8_t)bits;
+                        if (gi < 8) keep_lo |= (uint64_t)bits << (8 * gi); else keep_hi |= (uint64_t)bits << (8 * (gi - 8));
+                    }
+                }
                 if (stamp) DBG_STAMP(0, it, 4);
                 mbar_wait(p_empty, (it & 1) ^ 1);            // the MMAs of the previous tile have consumed P
                 if (stamp) DBG_STAMP(0, it, 5);
-                const DrawKey dkey = rng_resolve(p.seed, p.offset);
                 const float pscale = valid ? inv * rescale : 0.f;
 #pragma unroll
                 for (int gi = 0; gi < AT_VG; ++gi) {
@@ -459,16 +486,9 @@ attn_tc_kernel(const AttnTcParams p) {
                             for (int e = 0; e < 8; ++e) if (kb + e < kvalid) po[e] = w[e];
                         }
                         if (EXTRA && p.drop_p > 0.f && valid) {
-                            uint32_t bits = 0;
+                            const uint32_t b8 = (uint32_t)(gi < 8 ? keep_lo >> (8 * gi) : keep_hi >> (8 * (gi - 8))) & 0xFFu;
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const uint64_t idx = ((uint64_t)srow * p.Ksel + key0 + kb + e);
-                                const float m = drop_keep_scale(dkey.seed, dkey.offset, idx, p.drop_p);
-                                w[e] *= m;
-                                bits |= (m != 0.f ? 1u : 0u) << e;
-                            }
-                            // the backward kernel reads the draw back instead of hashing every score again (twice)
-                            if (p.drop_mask && kb < kvalid) p.drop_mask[srow * ((p.Ksel + 7) / 8) + ((key0 + kb) >> 3)] = (uint8_t)bits;
+                            for (int e = 0; e < 8; ++e) w[e] = ((b8 >> e) & 1u) ? w[e] * dfast.scale : 0.f;
                         }
                         // hi = truncated bf16 (exact), lo = bf16 of the exact remainder: integer/FMA pipes only
                         uint32_t hw[4], lw[4];

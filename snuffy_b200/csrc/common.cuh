@@ -93,8 +93,27 @@ __device__ __forceinline__ float drop_keep_scale(uint64_t seed, uint64_t offset,
     uint32_t x = (uint32_t)idx ^ (uint32_t)seed, y = (uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32) ^ (uint32_t)offset;
     x *= 0x85EBCA6Bu; x ^= x >> 13; x += y * 0x9E3779B9u + (uint32_t)(offset >> 32);
     x *= 0xC2B2AE35u; x ^= x >> 16; x *= 0x27D4EB2Fu; x ^= x >> 15; x *= 0x165667B1u; x ^= x >> 16;
-    const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
-    return u >= p ? 1.f / (1.f - p) : 0.f;
+    // keep iff u = (x >> 8) * 2^-24 >= p.  u is exact in fp32 and so is p * 2^24, so this is the integer test below: no
+    // int -> float conversion (a quarter-rate pipe) per element
+    return (x >> 8) >= (uint32_t)ceilf(p * 16777216.0f) ? 1.f / (1.f - p) : 0.f;
+}
+
+// The same draw for element indices below 2^32 with everything that does not depend on the index hoisted (bit-identical to
+// drop_keep_scale: the high word of the index is 0 there).
+struct DropFast { uint32_t s0, k, thr; float scale; };
+__device__ __forceinline__ DropFast drop_fast_setup(uint64_t seed, uint64_t offset, float p) {
+    DropFast c;
+    c.s0 = (uint32_t)seed;
+    c.k = ((uint32_t)(seed >> 32) ^ (uint32_t)offset) * 0x9E3779B9u + (uint32_t)(offset >> 32);
+    c.thr = (uint32_t)ceilf(p * 16777216.0f);
+    c.scale = 1.f / (1.f - p);
+    return c;
+}
+__device__ __forceinline__ bool drop_fast_keep(const DropFast& c, uint32_t idx) {
+    uint32_t x = idx ^ c.s0;
+    x *= 0x85EBCA6Bu; x ^= x >> 13; x += c.k;
+    x *= 0xC2B2AE35u; x ^= x >> 16; x *= 0x27D4EB2Fu; x ^= x >> 15; x *= 0x165667B1u; x ^= x >> 16;
+    return (x >> 8) >= c.thr;
 }
 
 // ---------------------------------------------------------------- folding many small partials

@@ -39,6 +39,14 @@ template <int BN> struct TcCfg {
     static constexpr uint32_t TMEM_COLS = 2 * BN;                      // two accumulator stages
 };
 
+#ifdef GEMM_DEBUG_TIMING
+// clock64 stamps of CTA 0 (tools/gemm_timeline.py): [role 0 producer | 1 mma | 2 epilogue warp 2][item < 64][4 stamps]
+__device__ long long g_gemm_dbg[3 * 64 * 4];
+#define GDBG(role, t, k) do { if (blockIdx.x == 0 && (t) < 64) g_gemm_dbg[((role) * 64 + (t)) * 4 + (k)] = clock64(); } while (0)
+#else
+#define GDBG(role, t, k) do { } while (0)
+#endif
+
 struct TcGemmParams {
     const __nv_bfloat16* A; int64_t a_plane_stride;
     const __nv_bfloat16* B; int64_t b_plane_stride;
@@ -56,6 +64,10 @@ struct TcGemmParams {
     // gate form only: column sums of the result per 32-row block, [m_tiles * 4][N] (folded by the host entry: the bias gradient
     // db = sum over rows of dh, so dh itself never has to be written as fp32)
     float* colsum_part;
+    // ReLU backward read off the forward's activated operand planes instead of a saved fp32 pre-activation:
+    // dh = (dY W) * (a > 0 ? gate_scale : 0) with a = dropout(relu(h)) as the forward wrote it (hi plane, layout of out_planes)
+    // and gate_scale = 1 / (1 - p): a dropped or clamped element is 0 there, so neither h nor the dropout draw is needed again
+    const __nv_bfloat16* gate_planes; float gate_scale;
     // block-diagonal B operand (attention backward against head-block matrices): B[n, k] is non-zero only where
     // n / group_n == k / group_k, so a column tile contracts only over the k-blocks of the groups it touches (group_n == 0: dense)
     int group_n, group_k;
@@ -216,7 +228,9 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
         for (int it = 0; tc_item<BN>(p, it, w); ++it) {
             if (w.mode < 0) continue;
             const int kb0 = w.kb0, kb1 = w.kb1;
+            if (lane == 0) GDBG(1, it, 0);
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            if (lane == 0) GDBG(1, it, 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -249,6 +263,7 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (lane == 0) GDBG(1, it, 2);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
@@ -269,7 +284,9 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
             const int rr_own = quad * 32 + lane;                   // row of the tile this thread owns in TMEM
             const int64_t m_own = (int64_t)mt * TC_BM + rr_own;
             const int64_t m_base = (int64_t)mt * TC_BM + quad * 32;
+            if (warp == 2 && lane == 0) GDBG(2, it, 0);
             mbar_wait(tfull0 + 8 * acc, acc_phase);
+            if (warp == 2 && lane == 0) GDBG(2, it, 1);
             tc_fence_after();
             // tail slices: this thread's row of the raw accumulators other slices hand over / this slice hands over
             // (stored in the register layout [warp][chunk][float4 j][lane]: every warp access is 512 contiguous bytes)
@@ -335,6 +352,26 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                     }
                     __syncwarp();
                 }
+                if (p.gate_planes) {
+                    // thread owns row m_own: its 32 gate values are four 16-byte units of the hi plane, 128 rows * 16 B apart
+                    // (the 32 lanes read 512 contiguous bytes per unit); rows >= M and columns >= N are zeros there
+                    if (col0 < kpad_next) {
+                        const __nv_bfloat16* gsrc = p.gate_planes + (((int64_t)mt * nkb_next + (col0 >> 5)) * 4) * (TC_BM * 8) + rr_own * 8;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint4 q = __ldg(reinterpret_cast<const uint4*>(gsrc + u * (TC_BM * 8)));
+                            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int16_t bits = (int16_t)(wd[j >> 1] >> ((j & 1) * 16));
+                                v[u * 8 + j] = bits > 0 ? v[u * 8 + j] * p.gate_scale : 0.f;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+                }
                 if (p.gate) {
                     // activation backward in the epilogue: the gate rows are read in the coalesced layout of the output stores
                     // (4 rows x 128 B per pass), the gated values go back through the transpose buffer for the plane writer
@@ -343,6 +380,8 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                     __syncwarp();
                     const int col = col0 + c4;
                     const DrawKey gk = rng_resolve(p.seed, p.offset);
+                    const DropFast gfast = drop_fast_setup(gk.seed, gk.offset, p.drop_p);
+                    const bool gsmall = (int64_t)p.M * p.N < (1ll << 32);
                     float4 g4[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -373,7 +412,9 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             o[jj] *= gg[jj];
-                            if (p.drop_p > 0.f) o[jj] *= drop_keep_scale(gk.seed, gk.offset, (uint64_t)(m * p.N + col + jj), p.drop_p);
+                            if (p.drop_p > 0.f)
+                                o[jj] *= gsmall ? (drop_fast_keep(gfast, (uint32_t)(m * p.N + col + jj)) ? gfast.scale : 0.f)
+                                                : drop_keep_scale(gk.seed, gk.offset, (uint64_t)(m * p.N + col + jj), p.drop_p);
                         }
                         const bool live = m < p.M && col < p.N;
 #pragma unroll
@@ -413,9 +454,16 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                 }
                 if (p.drop_p > 0.f) {
                     const DrawKey dk_ = rng_resolve(p.seed, p.offset);
+                    if ((int64_t)p.M * p.N < (1ll << 32)) {          // 32-bit element index: the hoisted form of the same draw
+                        const DropFast df = drop_fast_setup(dk_.seed, dk_.offset, p.drop_p);
+                        const uint32_t e0 = (uint32_t)(m_own * p.N + col0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        v[j] *= drop_keep_scale(dk_.seed, dk_.offset, (uint64_t)(m_own * p.N + col0 + j), p.drop_p);
+                        for (int j = 0; j < 32; ++j) v[j] = drop_fast_keep(df, e0 + j) ? v[j] * df.scale : 0.f;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] *= drop_keep_scale(dk_.seed, dk_.offset, (uint64_t)(m_own * p.N + col0 + j), p.drop_p);
+                    }
                 }
                 if (p.out_planes) {
                     // thread owns row m_own and 32 consecutive k of the next GEMM = one chunk column block:
@@ -433,6 +481,17 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                             *reinterpret_cast<bf16x8*>(dst + p.out_plane_stride + u * (TC_BM * 8)) = l;
                         }
                     }
+                }
+                if (p.colsum_part) {                      // column sums of this warp's 32 x 32 block (rows >= M count as zeros)
+                    const bool live = m_own < p.M;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = live ? v[j] : 0.f;
+                    __syncwarp();
+                    float sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) sum += stg[i * 33 + lane];
+                    if (col0 + lane < p.N) p.colsum_part[((int64_t)mt * 4 + quad) * p.N + col0 + lane] = sum;
+                    __syncwarp();
                 }
                 if (p.out) {
 #pragma unroll
@@ -484,6 +543,7 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (warp == 2 && lane == 0) GDBG(2, it, 2);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -640,7 +700,7 @@ static int gemm_tc_full(const void* A_planes, int64_t a_plane_stride, const void
                         int64_t ldr, const int32_t* row_map, const float* resid_alt, float* out, int64_t ldc,
                         float* preact, void* out_planes, int64_t out_plane_stride, float dropout_p, uint64_t seed,
                         uint64_t offset, const float* gate, int64_t ldg, int gate_act, cudaStream_t stream,
-                        float* colsum_part = nullptr) {
+                        float* colsum_part = nullptr, const void* gate_planes = nullptr, float gate_scale = 1.f) {
     SNUFFY_REQUIRE(!gate || (ldg % 4 == 0 && ldg >= N && (uintptr_t)gate % 16 == 0),
                    "snuffy_gemm_tc_actgrad: the gate matrix must be 16-byte aligned with ldg %% 4 == 0, ldg >= N");
     SNUFFY_REQUIRE(A_planes && B_planes, "snuffy_gemm_tc: null operand");
@@ -670,6 +730,7 @@ static int gemm_tc_full(const void* A_planes, int64_t a_plane_stride, const void
     p.ksplit = 1; p.kb_per = p.num_kb; p.split_stride = 0;
     p.a_nkb = p.num_kb; p.a_kb_off = 0;
     p.gate = gate; p.ldg = ldg; p.gate_act = gate_act; p.colsum_part = colsum_part;
+    p.gate_planes = reinterpret_cast<const __nv_bfloat16*>(gate_planes); p.gate_scale = gate_scale;
     return launch_gemm_tc(p, N, stream, gate ? "snuffy_gemm_tc_actgrad" : "snuffy_gemm_tc");
 }
 
@@ -759,6 +820,28 @@ int snuffy_gemm_tc_blockdiag(const void* A_planes, int64_t a_plane_stride, int64
     p.a_nkb = (int)plane_kblocks(a_cols_total); p.a_kb_off = (int)(a_col0 / 32);
     p.group_n = (int)group_n; p.group_k = (int)group_k;
     return launch_gemm_tc(p, N, stream, "snuffy_gemm_tc_blockdiag", b_rc);
+}
+
+// The same product for ReLU, gated by the forward's own activated planes: result = (A . B^T) * (a[m, n] > 0 ? 1 / (1 - p) : 0)
+// with a = dropout(relu(h)) as written by snuffy_gemm_tc's out_planes (only the hi plane is read).  Neither the fp32
+// pre-activation nor the dropout draw is needed: a clamped or dropped element is exactly 0 in the planes.
+int snuffy_gemm_tc_relugrad(const void* A_planes, int64_t a_plane_stride, const void* B_planes, int64_t b_plane_stride,
+                            int64_t M, int64_t N, int64_t K, int passes, const void* act_planes, float dropout_p, float* out,
+                            int64_t ldc, void* out_planes, int64_t out_plane_stride, float* colsum, float* colsum_partials,
+                            cudaStream_t stream) {
+    SNUFFY_REQUIRE(act_planes && (uintptr_t)act_planes % 16 == 0, "snuffy_gemm_tc_relugrad: null or misaligned activation planes");
+    SNUFFY_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "snuffy_gemm_tc_relugrad: dropout_p out of range");
+    SNUFFY_REQUIRE(!colsum || colsum_partials, "snuffy_gemm_tc_relugrad: column sums need their partials buffer");
+    if (int rc = gemm_tc_full(A_planes, a_plane_stride, B_planes, b_plane_stride, M, N, K, passes, nullptr, ACT_NONE, nullptr, 0,
+                              nullptr, nullptr, out, ldc, nullptr, out_planes, out_plane_stride, 0.f, 0, 0, nullptr, 0, 0, stream,
+                              colsum ? colsum_partials : nullptr, act_planes, 1.f / (1.f - dropout_p)))
+        return rc;
+    if (colsum) {
+        const int64_t parts = ((M + TC_BM - 1) / TC_BM) * 4;
+        fold_wide_kernel<float><<<(unsigned)((N + 15) / 16), 256, 0, stream>>>(colsum_partials, (int)parts, N, colsum);
+        return check_launch("snuffy_gemm_tc_relugrad");
+    }
+    return 0;
 }
 
 // Split-K form for the weight gradients dW[M, N] = A . B^T with a long contraction (K = all patches of the step) and few
@@ -885,6 +968,12 @@ int snuffy_gemm_tc_splitk_blockdiag(const void* A_planes, int64_t a_plane_stride
     return gemm_tc_splitk_full(A_planes, a_plane_stride, B_planes, b_plane_stride, b_rc, M, N, K, passes, ksplit, diag_m, diag_n, out,
                                workspace, workspace_bytes, stream);
 }
+
+#ifdef GEMM_DEBUG_TIMING
+int snuffy_gemm_debug_read(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_gemm_dbg, sizeof(g_gemm_dbg)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // extern "C"
 #pragma GCC visibility pop

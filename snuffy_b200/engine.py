@@ -277,6 +277,15 @@ class LayerTape:
     a_planes: Optional[Planes] = None
 
 
+#: weight gradients of the three all-row projections straight from row planes (MN-major descriptors); "0" = from transposed copies
+DW_BY_ROWS = os.environ.get("SNUFFY_B200_DW_BY_ROWS", "1") != "0"
+
+
+def dw_by_rows(d: int, dff: int) -> bool:
+    """The training tape keeps the forward's operand planes and the backward contracts them over the rows (backward.py)."""
+    return DW_BY_ROWS and ops.gemm_tc_splitk_rows_supported(d, dff) and ops.gemm_tc_splitk_rows_supported(dff, d)
+
+
 def tc_supported(d: int) -> bool:
     return d % 8 == 0
 
@@ -395,8 +404,10 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
             _, yp, ln2_stats = ops.ln_rows(x, w.g2, w.be2, row_map=row_map, alt=xs_new, want_planes=True, want_stats=save)
             w1_p, b1 = w.w1_planes, w.b1
         dff = w.w1.shape[0]
+        # ReLU training: the backward reads its gate off these activated planes (a > 0), so the fp32 pre-activation is not kept
+        relu_gate = save and activation == "relu" and not share_z and dw_by_rows(d, dff)
         _, h_pre, hp = ops.gemm_tc(yp, w1_p, M=rows, N=dff, K=d, passes=passes, bias=b1, act=activation,
-                                   want_out=False, want_preact=save, want_planes=True, drop=drop_ff)
+                                   want_out=False, want_preact=save and not relu_gate, want_planes=True, drop=drop_ff)
         x_next, _, _ = ops.gemm_tc(hp, w.w2_planes, M=rows, N=d, K=dff, passes=passes, bias=w.b2, resid=x,
                                    row_map=row_map, resid_alt=xs_new, drop=drop_enc2)
     tape = None

@@ -275,6 +275,23 @@ def gemm_tc_actgrad(a: Planes, b: Planes, gate: torch.Tensor, act: str, *, M: in
     return (out, op, cs) if want_colsum else (out, op)
 
 
+def gemm_tc_relugrad(a: Planes, b: Planes, act_planes: Planes, dropout_p: float, *, M: int, N: int, K: int, passes: int = 3,
+                     want_out: bool = False, want_planes: bool = True, want_colsum: bool = False):
+    """(A . B^T) * (act > 0 ? 1 / (1 - p) : 0) with `act_planes` = the forward's dropout(relu(h)) operand planes [M, N]:
+    ReLU backward with neither the saved pre-activation nor the dropout draw.  -> (fp32 or None, Planes or None, colsum or None)."""
+    if act_planes.rc != 128 or act_planes.K != N or act_planes.rows < M:
+        raise ValueError("gemm_tc_relugrad: act_planes are the 128-row planes of an [M, N] activation")
+    device = a.buf.device
+    out = torch.empty(M, N, dtype=torch.float32, device=device) if want_out else None
+    op = Planes(M, N, 128, device) if want_planes else None
+    cs = torch.empty(N, dtype=torch.float32, device=device) if want_colsum else None
+    csp = torch.empty((M + 127) // 128 * 4 * N, dtype=torch.float32, device=device) if want_colsum else None
+    check(lib.snuffy_gemm_tc_relugrad(a.ptr, a.stride, b.ptr, b.stride, M, N, K, passes, act_planes.ptr, float(dropout_p),
+                                      _ptr(out), N, op.ptr if op else None, op.stride if op else 0, _ptr(cs), _ptr(csp),
+                                      _stream()), "snuffy_gemm_tc_relugrad")
+    return out, op, cs
+
+
 # ------------------------------------------------------------------ a9: sparse attention
 def _rows_view(t: torch.Tensor, name: str) -> torch.Tensor:
     """2-D fp32 CUDA tensor whose last dim is contiguous (rows may be strided, e.g. a column slice of Q|V)."""

@@ -205,6 +205,26 @@ def test_gemm_tc_actgrad_epilogue(ops, act, M, N, K, p):
     assert float((cs.double() - ref).abs().max()) < 1e-5 * max(1.0, float(out.abs().sum(0).max()))
 
 
+@pytest.mark.parametrize("M,N,K,p", [(1000, 2048, 512, 0.1), (333, 96, 64, 0.25), (10000, 2048, 512, 0.0)])
+def test_gemm_tc_relugrad_reads_the_gate_off_the_forward_planes(ops, M, N, K, p):
+    """ReLU backward gated by the forward's own dropout(relu(h)) planes == the product gated by the saved pre-activation and the
+    re-drawn dropout mask (snuffy_gemm_tc_actgrad), planes and column sums included."""
+    rs = np.random.RandomState(M + N)
+    x = torch.from_numpy(rs.standard_normal((M, K)).astype(np.float32)).cuda()
+    w1 = torch.from_numpy((rs.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).cuda()
+    drop = (p, 11, 3)
+    _, xp, _ = ops.ln_rows(x, None, None, apply_ln=False, want_planes=True)
+    _, h_pre, a_planes = ops.gemm_tc(xp, ops.weight_planes(w1), M=M, N=N, K=K, act="relu", want_out=False, want_preact=True,
+                                     want_planes=True, drop=drop)
+    a, b, ad, bd, ap, bp = _operands(ops, M, N, K, 99)                       # the incoming gradient product dY W2
+    want, want_planes, want_cs = ops.gemm_tc_actgrad(ap, bp, h_pre, "relu", M=M, N=N, K=K, drop=drop, want_colsum=True)
+    out, planes, cs = ops.gemm_tc_relugrad(ap, bp, a_planes, p, M=M, N=N, K=K, want_out=True, want_colsum=True)
+    assert torch.allclose(out, want, rtol=1e-6, atol=1e-7), float((out - want).abs().max())
+    assert torch.equal(planes.buf.view(torch.int16), want_planes.buf.view(torch.int16)) or \
+        np.allclose(sum(decode_planes(planes, M, N)), sum(decode_planes(want_planes, M, N)), rtol=1e-6, atol=1e-7)
+    assert float((cs - want_cs).abs().max()) < 1e-5 * max(1.0, float(want.abs().sum(0).max()))
+
+
 @pytest.mark.parametrize("M,h,gn,gk", [(1000, 8, 200, 64), (300, 4, 24, 32), (257, 2, 40, 32), (500, 8, 64, 200), (384, 4, 16, 8),
                                        (130, 1, 96, 64)])
 def test_gemm_tc_blockdiag_skips_only_zero_blocks(ops, M, h, gn, gk):

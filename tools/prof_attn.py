@@ -15,7 +15,7 @@ _, up, _ = ops.ln_rows(x, gam, bet, want_planes=True)
 wp = ops.weight_planes(w)
 _, _, qvp = ops.gemm_tc(up, wp, M=B * n, N=2 * d, K=d, passes=3, want_out=False, want_planes=True)
 kp = torch.randn(B * ks, d, device=dev, generator=g)
-kw = dict(want_probs=False, want_stats=True, dropout_p=DROP, seed=1, offset=2, want_mask=True) if DROP > 0 else dict(want_probs=False)
+kw = dict(want_probs=False, want_stats=True, dropout_p=DROP, seed=1, offset=2, want_mask=not os.environ.get("NOMASK")) if DROP > 0 else dict(want_probs=False)
 if os.environ.get("STATS"):
     kw = dict(want_probs=False, want_stats=True)
 for _ in range(3):
