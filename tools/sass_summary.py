@@ -26,7 +26,7 @@ for line in sass.splitlines():
                 counts[cur][k] += 1
 print("# SASS mnemonics per kernel of snuffy_b200/libsnuffy_b200.so (cuobjdump -sass, every cubin is sm_100a)")
 print("# UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (1-D bulk copy),")
-print("# UTMALDG = tensor-map TMA load (not used: operands are pre-tiled planes), SYNCS = mbarrier operations")
+print("# UTMALDG = tensor-map TMA load (the row-plane weight-gradient form gemm_tc_kernel<BN, true>), SYNCS = mbarrier operations")
 print("kernel," + ",".join(KEYS) + ",instructions")
 for mangled, name in zip(order, names):
     c = counts[mangled]
