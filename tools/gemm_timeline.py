@@ -26,7 +26,7 @@ for _ in range(3):
     if shape == "relugrad":
         ops.gemm_tc_relugrad(a, w, act_planes, 0.1, M=R, N=N, K=K, want_colsum=True)
     else:
-        ops.gemm_tc(a, w, M=R, N=N, K=K, passes=3, bias=bias, resid=resid, **kw)
+        ops.gemm_tc(a, w, M=R, N=N, K=K, passes=int(os.environ.get("PASSES", 3)), bias=bias, resid=resid, **kw)
 torch.cuda.synchronize()
 raw = ctypes.CDLL(_lib.LIB_PATH)
 buf = (ctypes.c_longlong * (3 * 64 * 4))()
