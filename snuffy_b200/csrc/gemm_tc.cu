@@ -141,7 +141,21 @@ __device__ __forceinline__ bool tc_item(const TcGemmParams& p, int it, TcItem& w
     return true;
 }
 
-template <int BN, bool MN = false>
+// Cluster-pair form: the two CTAs of a cluster take the row tiles 2 mp and 2 mp + 1 of the SAME column tile and walk the same
+// k-blocks, so the weight tile is fetched from L2 once per pair (each CTA loads one plane of it and multicasts it to both).
+// mode 3: the odd row tile that does not exist (it still loads and multiplies, so that its peer's pipeline runs; no output).
+template <int BN>
+__device__ __forceinline__ bool tc_item_pair(const TcGemmParams& p, int it, int rank, TcItem& w) {
+    const int s = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
+    const int m_pairs = (p.m_tiles + 1) >> 1;
+    if (s >= m_pairs * p.n_tiles) return false;
+    w.nt = s % p.n_tiles; w.mt = 2 * (s / p.n_tiles) + rank;
+    w.ksp = 0; w.kb0 = 0; w.kb1 = p.num_kb; w.tt = 0; w.slice = 0;
+    w.mode = w.mt < p.m_tiles ? 0 : 3;
+    return true;
+}
+
+template <int BN, bool MN = false, bool CL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b) {
     using Cfg = TcCfg<BN>;
@@ -156,7 +170,9 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        // CL: a stage is refilled by both CTAs of the pair (own A planes, one multicast B plane each), so it is free only
+        // when the MMAs of BOTH CTAs have retired from it
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, CL ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -169,6 +185,8 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int crank = CL ? (int)cluster_ctarank() : 0;
+    if (CL) cluster_sync_all();                              // the peer's barriers exist before anything is sent to them
 
     const bool use_lo = p.npairs > 1;
     const uint32_t stage_tx = use_lo ? Cfg::STAGE_BYTES : (TC_A_PLANE_BYTES + Cfg::B_PLANE_BYTES);
@@ -178,10 +196,10 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
         int stage = 0; uint32_t phase = 0;
         const int64_t a_chunk = (int64_t)TC_BM * PLANE_KB, b_chunk = (int64_t)BN * PLANE_KB;   // elements
         TcItem w;
-        for (int it = 0; tc_item<BN>(p, it, w); ++it) {
+        for (int it = 0; CL ? tc_item_pair<BN>(p, it, crank, w) : tc_item<BN>(p, it, w); ++it) {
             if (w.mode < 0) continue;
             const int mt = w.mt, nt = w.nt, kb0 = w.kb0, kb1 = w.kb1;
-            const __nv_bfloat16* a_src = p.A + ((int64_t)mt * p.a_nkb + p.a_kb_off) * a_chunk;
+            const __nv_bfloat16* a_src = p.A + ((int64_t)(w.mode == 3 ? p.m_tiles - 1 : mt) * p.a_nkb + p.a_kb_off) * a_chunk;
             const __nv_bfloat16* b_src = p.B + (int64_t)nt * p.num_kb * b_chunk;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -198,6 +216,18 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                         tma_load_4d(sa, &tm_a, (kb & 3) * 256, 16 * mt, kb >> 2, 0, bar);
                         tma_load_4d(sb, &tm_b, (kb & 3) * 256, (BN / 8) * nt, kb >> 2, 0, bar);
                     }
+                } else if (CL && lane == 0) {
+                    const uint32_t bar = full0 + 8 * stage;
+                    const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + 2 * TC_A_PLANE_BYTES;
+                    mbar_expect_tx(bar, stage_tx);                 // own A planes + both B planes, whoever sends them
+                    bulk_g2s(sa, a_src + kb * a_chunk, TC_A_PLANE_BYTES, bar);
+                    if (use_lo) bulk_g2s(sa + TC_A_PLANE_BYTES, a_src + p.a_plane_stride + kb * a_chunk, TC_A_PLANE_BYTES, bar);
+                    if (crank == 0)
+                        bulk_g2s_multicast(sb, b_src + kb * b_chunk, Cfg::B_PLANE_BYTES, bar, (uint16_t)3);
+                    else if (use_lo)
+                        bulk_g2s_multicast(sb + Cfg::B_PLANE_BYTES, b_src + p.b_plane_stride + kb * b_chunk, Cfg::B_PLANE_BYTES, bar,
+                                           (uint16_t)3);
                 } else if (lane == 0) {
                     const uint32_t bar = full0 + 8 * stage;
                     const uint32_t sa = smem_u32(stage_base + (size_t)stage * Cfg::STAGE_BYTES);
@@ -214,6 +244,13 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (CL) {
+            // the peer's MMAs still arrive on this CTA's empty barriers: wait until every stage has been released once more
+            for (int s = 0; s < Cfg::STAGES; ++s) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
         constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -225,7 +262,7 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         TcItem w;
-        for (int it = 0; tc_item<BN>(p, it, w); ++it) {
+        for (int it = 0; CL ? tc_item_pair<BN>(p, it, crank, w) : tc_item<BN>(p, it, w); ++it) {
             if (w.mode < 0) continue;
             const int kb0 = w.kb0, kb1 = w.kb1;
             if (lane == 0) GDBG(1, it, 0);
@@ -257,7 +294,8 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                             tc_mma_bf16(d_tmem, a_hi, b_hi, IDESC, (kb > kb0 || ks) ? 1u : 0u);
                         }
                     }
-                    tc_commit(empty0 + 8 * stage);                 // frees the smem slot when these MMAs retire
+                    if (CL) tc_commit_multicast(empty0 + 8 * stage, (uint16_t)3);   // ... in both CTAs of the pair
+                    else tc_commit(empty0 + 8 * stage);            // frees the smem slot when these MMAs retire
                     if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);
                 }
                 __syncwarp();
@@ -277,7 +315,7 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;           // coalesced phase: 4 rows x 8 float4 per pass
         constexpr int CH = BN / 64;                                // 32-column chunks per half
         TcItem w;
-        for (int it = 0; tc_item<BN>(p, it, w); ++it) {
+        for (int it = 0; CL ? tc_item_pair<BN>(p, it, crank, w) : tc_item<BN>(p, it, w); ++it) {
             if (w.mode < 0) continue;
             const int mt = w.mt, nt = w.nt, ksp = w.ksp;
             float* const outp = p.out ? p.out + (int64_t)ksp * p.split_stride : nullptr;
@@ -304,7 +342,7 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
             for (int cc = 0; cc < CH; ++cc) {
                 const int c = half * CH + cc;
                 const int col0 = nt * BN + c * 32;
-                if (col0 >= p.N && col0 >= kpad_next) break;
+                if (w.mode == 3 || (col0 >= p.N && col0 >= kpad_next)) break;
                 float v[32];
                 tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                 if (w.mode == 2) {
@@ -549,6 +587,7 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
     }
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();                              // neither CTA leaves while the other may still send to it
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
@@ -677,6 +716,44 @@ static int launch_gemm_tc(TcGemmParams& p, int64_t N, cudaStream_t stream, const
                 p.tail_part = ws->part; p.tail_flags = ws->flags;
                 grid = p.full_items > 0 ? sm : rem * sl;
             }
+        }
+    }
+    // Large plain products with a short contraction: CTA pairs (2-CTA clusters) that share each weight tile through TMA
+    // multicast: a pair fetches the B planes from L2 once (32 instead of 48 KB per CTA and k-block).  Measured (160 000 rows,
+    // tools/time_gemm_shapes.py): FFN-up 913 -> 874 us, Q|V 459 -> 445 us at K = 512; nothing at K = 2048 and -3.6 % at K = 1024
+    // (the lockstep of the pair costs more than the feed saves once the MMAs are bound by their shared-memory operand reads),
+    // so it is used for K <= 512 only.
+    static const bool pairs = [] { const char* e = getenv("SNUFFY_B200_GEMM_PAIRS"); return !e || atoi(e) != 0; }();
+    if (pairs && !mn && p.tail_tiles == 0 && p.ksplit == 1 && p.diag_m == 0 && p.group_n == 0 && p.m_tiles >= 2 && total >= sm &&
+        sm % 2 == 0 && p.num_kb <= 16) {
+        const int supers = ((p.m_tiles + 1) / 2) * p.n_tiles;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * (supers < sm / 2 ? supers : sm / 2)));
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        // the persistent loop strides by the number of clusters: size the grid to what is co-resident (a GPC with an odd number
+        // of free SMs leaves one out), or a late cluster would run its whole share after the others have finished
+        static int resident[2] = {0, 0};                   // [bn == 256]
+        int& res = resident[bn == 256 ? 1 : 0];
+        if (bn == 256) {
+            SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<256, false, true>), (int)TcCfg<256>::SMEM_BYTES));
+            cfg.dynamicSmemBytes = TcCfg<256>::SMEM_BYTES;
+            if (res == 0) SNUFFY_CUDA(cudaOccupancyMaxActiveClusters(&res, gemm_tc_kernel<256, false, true>, &cfg));
+        } else {
+            SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<128, false, true>), (int)TcCfg<128>::SMEM_BYTES));
+            cfg.dynamicSmemBytes = TcCfg<128>::SMEM_BYTES;
+            if (res == 0) SNUFFY_CUDA(cudaOccupancyMaxActiveClusters(&res, gemm_tc_kernel<128, false, true>, &cfg));
+        }
+        if (res >= 8) {
+            const int nclusters = supers < res ? supers : res;
+            cfg.gridDim = dim3((unsigned)(2 * nclusters));
+            if (bn == 256) SNUFFY_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<256, false, true>, p, none, none));
+            else SNUFFY_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<128, false, true>, p, none, none));
+            return check_launch(who);
         }
     }
     if (mn && bn == 256) {
