@@ -23,6 +23,20 @@ ATTN_BWD = __import__("os").environ.get("SNUFFY_B200_ATTN_BWD", "fused")
 ATTN_BWD_TC = ATTN_BWD != "simt"
 
 
+#: the weight-gradient products of the all-row projections are off the critical chain (nothing in the backward pass reads them):
+#: issued on a second stream they fill the SMs the dX products leave idle in their last, partial wave (one bag = 79 row tiles:
+#: 158 tiles on 148 SMs).  "0" = everything on one stream.
+DW_SIDE_STREAM = __import__("os").environ.get("SNUFFY_B200_DW_SIDE_STREAM", "1") != "0"
+_DW_STREAMS = {}
+
+
+def _dw_stream(device: torch.device) -> torch.cuda.Stream:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _DW_STREAMS:
+        _DW_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _DW_STREAMS[key]
+
+
 def _flat(t: torch.Tensor, d: int) -> torch.Tensor:
     return t.contiguous().view(-1, d)
 
@@ -134,6 +148,17 @@ class EncoderLayerFunction(torch.autograd.Function):
                 w.prepare_backward()
             rc_d, rc_ff = ops._block_n(d), ops._block_n(dff)
         by_rows = tc and engine.DW_BY_ROWS and t.a_planes is not None
+        side = _dw_stream(g.device) if by_rows and DW_SIDE_STREAM else None
+        keep = []                 # operands of side-stream products stay referenced until the join (the allocator would hand
+                                  # their memory to later main-stream kernels the moment they are dropped)
+
+        def off_chain(fn, *operands):
+            if side is None:
+                return fn()
+            keep.extend(operands)
+            side.wait_stream(torch.cuda.current_stream(g.device))
+            with torch.cuda.stream(side):
+                return fn()
 
         def dx_gemm(dy, w_f32, wt_planes, n_in):                # dX = dY . W        (W = nn.Linear.weight [out, in])
             if not tc:
@@ -160,8 +185,10 @@ class EncoderLayerFunction(torch.autograd.Function):
                 else:
                     _, dh_planes, d_b1 = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes,
                                                              drop=t.drop_ff, want_out=False, want_colsum=True)
-                d_w2 = ops.gemm_tc_splitk_rows(gfp, t.a_planes, M=d, N=dff, R=rows, passes=passes)     # gf^T . dropout(act(h_pre))
-                d_w1 = ops.gemm_tc_splitk_rows(dh_planes, t.u2_planes, M=dff, N=d, R=rows, passes=passes)   # dh^T . LN2(y)
+                d_w2 = off_chain(lambda: ops.gemm_tc_splitk_rows(gfp, t.a_planes, M=d, N=dff, R=rows, passes=passes),
+                                 gfp, t.a_planes)                                             # gf^T . dropout(act(h_pre))
+                d_w1 = off_chain(lambda: ops.gemm_tc_splitk_rows(dh_planes, t.u2_planes, M=dff, N=d, R=rows, passes=passes),
+                                 dh_planes, t.u2_planes)                                      # dh^T . LN2(y)
             else:
                 dh, dh_planes = ops.gemm_tc_actgrad(gfp, w.w2t_planes, t.h_pre, act, M=rows, N=dff, K=d, passes=passes,
                                                     drop=t.drop_ff)
@@ -219,7 +246,8 @@ class EncoderLayerFunction(torch.autograd.Function):
         if tc:
             _, dqvp, _ = ops.ln_rows(dqv, None, None, apply_ln=False, want_planes=True)
             if by_rows and ops.gemm_tc_splitk_rows_supported(2 * d, d):
-                d_wqv = ops.gemm_tc_splitk_rows(dqvp, t.u1_planes, M=2 * d, N=d, R=rows, passes=passes)   # [dQ | dV]^T . LN1(x)
+                d_wqv = off_chain(lambda: ops.gemm_tc_splitk_rows(dqvp, t.u1_planes, M=2 * d, N=d, R=rows, passes=passes),
+                                  dqvp, t.u1_planes)                                          # [dQ | dV]^T . LN1(x)
             else:
                 d_wqv = ops.gemm_tc_splitk(ops.planes_t(dqv, 128),
                                            ops.planes_t(t.x_in, rc_d, mode=1, stats=t.ln1_stats, gamma=w.g1, beta=w.be1),
@@ -237,6 +265,9 @@ class EncoderLayerFunction(torch.autograd.Function):
             # raw selected rows also feed the key projection: dx[S] += dKp Wk  (the xs residual is already in `add`)
             ops.scatter_add_rows(dx.view(B, N, d), t.sel, dx_gemm(dkp, w.wk, w.wkt_planes, d))
             dx = dx.view(B, N, d)
+        if side is not None and keep:
+            torch.cuda.current_stream(g.device).wait_stream(side)   # join: the weight gradients are complete from here on
+        keep.clear()
         ctx.tape = None
         return (None, dx, None, d_wq, d_bq, d_wk, d_bk, d_wv, d_bv, d_wo, d_bo, d_w1, d_b1, d_w2, d_b2,
                 d_g1, d_be1, d_g2, d_be2)
