@@ -23,9 +23,9 @@ ATTN_BWD = __import__("os").environ.get("SNUFFY_B200_ATTN_BWD", "fused")
 ATTN_BWD_TC = ATTN_BWD != "simt"
 
 
-#: the weight-gradient products of the all-row projections are off the critical chain (nothing in the backward pass reads them):
-#: issued on a second stream they fill the SMs the dX products leave idle in their last, partial wave (one bag = 79 row tiles:
-#: 158 tiles on 148 SMs).  "0" = everything on one stream.
+#: the weight- and bias-gradient products are off the critical chain (nothing in the backward pass reads them): issued on a
+#: second stream they fill the SMs the dX products leave idle in their last, partial wave (one bag = 79 row tiles: 158 tiles
+#: on 148 SMs) and the small ones no longer serialise between the big ones.  "0" = everything on one stream.
 DW_SIDE_STREAM = __import__("os").environ.get("SNUFFY_B200_DW_SIDE_STREAM", "1") != "0"
 _DW_STREAMS = {}
 
@@ -169,7 +169,7 @@ class EncoderLayerFunction(torch.autograd.Function):
 
         # ---- feed-forward sub-layer
         gf = ops.act_bwd(None, g, drop=t.drop_enc2)[0] if t.drop_enc2[0] > 0 else g
-        d_b2 = ops.colsum(gf).view(-1)
+        d_b2 = off_chain(lambda: ops.colsum(gf).view(-1), gf)
         dh_planes = None
         if tc:
             # dh = (gf W2) * act'(h_pre) * mask in the epilogue of the product, as the next product's operand planes
@@ -221,9 +221,10 @@ class EncoderLayerFunction(torch.autograd.Function):
         # ---- attention sub-layer: the selected rows of y are xs_new = xs + D1(Wo O + bo)
         dxs_new = ops.gather_rows(dy.view(B, N, d), t.sel).view(B * ksel, d)
         dz = ops.act_bwd(None, dxs_new, drop=t.drop_enc1)[0] if t.drop_enc1[0] > 0 else dxs_new
-        d_bo = ops.colsum(dz).view(-1)
+        d_bo = off_chain(lambda: ops.colsum(dz).view(-1), dz)
         if tc:
-            d_wo = ops.gemm_tc_splitk(ops.planes_t(dz, 128), ops.planes_t(t.o, rc_d), M=d, N=d, K=B * ksel, passes=passes)
+            d_wo = off_chain(lambda: ops.gemm_tc_splitk(ops.planes_t(dz, 128), ops.planes_t(t.o, rc_d), M=d, N=d, K=B * ksel,
+                                                        passes=passes), dz, t.o)
         else:
             d_wo = ops.matmul_tn(dz, t.o)
         d_o = dx_gemm(dz, w.wo, w.wot_planes, d)                                   # [B*Ksel, d]
@@ -236,12 +237,13 @@ class EncoderLayerFunction(torch.autograd.Function):
             dq, dv, dkp, dqv = ops.sparse_attn_bwd_tc(t.qvp, t.qv, t.kp, d_o, t.attn_stats, B, N, ksel, heads, d, t.drop, passes)
         else:
             dq, dv, dkp, dqv = ops.sparse_attn_bwd(q, v, t.kp, d_o, t.attn_stats, B, N, ksel, heads, t.drop)
-        d_bk = ops.colsum(dkp).view(-1)                                            # == 0 up to rounding (App. B-16)
+        d_bk = off_chain(lambda: ops.colsum(dkp).view(-1), dkp)                    # == 0 up to rounding (App. B-16)
         if tc:
-            d_wk = ops.gemm_tc_splitk(ops.planes_t(dkp, 128), ops.planes_t(t.xs, rc_d), M=d, N=d, K=B * ksel, passes=passes)
+            d_wk = off_chain(lambda: ops.gemm_tc_splitk(ops.planes_t(dkp, 128), ops.planes_t(t.xs, rc_d), M=d, N=d, K=B * ksel,
+                                                        passes=passes), dkp, t.xs)
         else:
             d_wk = ops.matmul_tn(dkp, t.xs)
-        d_bqv = ops.colsum(dqv).view(-1)
+        d_bqv = off_chain(lambda: ops.colsum(dqv).view(-1), dqv)
         d_bq, d_bv = d_bqv[:d], d_bqv[d:]
         if tc:
             _, dqvp, _ = ops.ln_rows(dqv, None, None, apply_ln=False, want_planes=True)

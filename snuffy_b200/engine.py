@@ -281,6 +281,18 @@ class LayerTape:
 DW_BY_ROWS = os.environ.get("SNUFFY_B200_DW_BY_ROWS", "1") != "0"
 
 
+#: the key projection of a layer on a second stream, beside the Q|V projection; "0" = one stream
+FWD_SIDE_STREAM = os.environ.get("SNUFFY_B200_FWD_SIDE_STREAM", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def dw_by_rows(d: int, dff: int) -> bool:
     """The training tape keeps the forward's operand planes and the backward contracts them over the rows (backward.py)."""
     return DW_BY_ROWS and ops.gemm_tc_splitk_rows_supported(d, dff) and ops.gemm_tc_splitk_rows_supported(dff, d)
@@ -339,6 +351,19 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     xs = ops.gather_rows(x.view(B, N, d), sel).view(B * Ksel, d)            # raw keys (App. B-1)
     row_map = ops.build_row_map(sel, N)
 
+    # The key projection of the Ksel selected rows does not depend on the Q|V projection over all N rows: issued on a second
+    # stream (forked here, joined before the attention kernel, inside a captured graph too) it runs in the SMs the big product
+    # leaves idle instead of after it.
+    small_tc = precision != "fp32"
+    kp, kside = None, None
+    if small_tc and FWD_SIDE_STREAM and x.is_cuda:
+        kside, cur = _side_stream(x.device), torch.cuda.current_stream(x.device)
+        kside.wait_stream(cur)
+        with torch.cuda.stream(kside):
+            _, xsp, _ = ops.ln_rows(xs, None, None, apply_ln=False, want_planes=True)
+            kp, _, _ = ops.gemm_tc(xsp, w.wk_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bk)
+            del xsp
+
     # --- attention sub-layer: u = LN1(x); Q,V over all N rows; keys from the raw selected rows
     attn_tc = False
     if precision == "fp32":
@@ -361,8 +386,9 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
                                  want_out=save or not attn_tc, want_planes=attn_tc)
     # [B*Ksel, d] key / output projections: a handful of tcgen05 tiles beat the SIMT kernel even for one bag (200 rows:
     # 8 SIMT CTAs looping over K take ~90 us, four tcgen05 CTAs ~10 us)
-    small_tc = precision != "fp32"
-    if small_tc:
+    if kside is not None:
+        torch.cuda.current_stream(x.device).wait_stream(kside)
+    elif small_tc:
         _, xsp, _ = ops.ln_rows(xs, None, None, apply_ln=False, want_planes=True)
         kp, _, _ = ops.gemm_tc(xsp, w.wk_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bk)
     else:
