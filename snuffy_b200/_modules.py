@@ -323,9 +323,19 @@ class EncoderLayerBase(nn.Module):
         if x.dim() != 3:
             raise ValueError(f"EncoderLayer expects x [B, N, d], got {tuple(x.shape)}")
         state = _state if _state is not None else {}
-        sel = self.forced_selection if self.forced_selection is not None else self._select(x, c, state)
-        if sel.dim() == 1:
-            sel = sel.unsqueeze(0)
-        sel = sel.to(device=x.device, dtype=torch.int64).contiguous()
         from .autograd import encoder_layer_fn
-        return encoder_layer_fn(self, x, sel, zplanes=state.get("zplanes"))
+        # Nothing before the attention kernel but the key projection needs the selection: on the tensor-core path it is drawn
+        # on the second stream (forked here; engine.encoder_layer_forward continues there with the gather, the row map and the
+        # key projection and joins before the attention), beside LayerNorm 1 and the Q|V projection of all N rows.
+        side, on_side = engine.selection_stream("fp32" if self.forced_selection is not None else self._effective_precision(),
+                                                x.device)
+        with on_side:
+            sel = self.forced_selection if self.forced_selection is not None else self._select(x, c, state)
+            if sel.dim() == 1:
+                sel = sel.unsqueeze(0)
+            sel = sel.to(device=x.device, dtype=torch.int64).contiguous()
+        engine._SEL_PENDING = side
+        try:
+            return encoder_layer_fn(self, x, sel, zplanes=state.get("zplanes"))
+        finally:
+            engine.join_pending_selection(x.device)           # no-op when the layer joined it itself

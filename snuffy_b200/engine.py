@@ -13,6 +13,7 @@ Data layout in HBM (all fp32 unless noted):
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import os
 from dataclasses import dataclass
@@ -293,6 +294,27 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
     return _SIDE_STREAMS[key]
 
 
+#: the stream a caller drew the selection on and has not joined yet (set by EncoderLayer.forward around its call)
+_SEL_PENDING = None
+
+
+def selection_stream(precision: str, device: torch.device):
+    """Context for drawing a layer's selection beside LayerNorm 1 / the Q|V projection: forks the second stream and returns
+    (stream or None, context manager).  The caller stores the stream in `_SEL_PENDING` around its encoder-layer call."""
+    if not FWD_SIDE_STREAM or precision == "fp32" or device.type != "cuda":
+        return None, contextlib.nullcontext()
+    side = _side_stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    return side, torch.cuda.stream(side)
+
+
+def join_pending_selection(device: torch.device) -> None:
+    global _SEL_PENDING
+    if _SEL_PENDING is not None:
+        torch.cuda.current_stream(device).wait_stream(_SEL_PENDING)
+        _SEL_PENDING = None
+
+
 def dw_by_rows(d: int, dff: int) -> bool:
     """The training tape keeps the forward's operand planes and the backward contracts them over the rows (backward.py)."""
     return DW_BY_ROWS and ops.gemm_tc_splitk_rows_supported(d, dff) and ops.gemm_tc_splitk_rows_supported(dff, d)
@@ -348,17 +370,21 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     # into the weights); the training tape keeps the two LayerNorms separate (their statistics are saved per sub-layer).
     share_z = SHARE_Z and precision != "fp32" and not save
 
-    xs = ops.gather_rows(x.view(B, N, d), sel).view(B * Ksel, d)            # raw keys (App. B-1)
-    row_map = ops.build_row_map(sel, N)
+    small_tc = precision != "fp32"
+    kside = _side_stream(x.device) if small_tc and FWD_SIDE_STREAM and x.is_cuda else None
+    if kside is None:
+        join_pending_selection(x.device)                   # the selection was drawn on the second stream: wait for it here
+    else:
+        kside.wait_stream(torch.cuda.current_stream(x.device))
+    with torch.cuda.stream(kside) if kside is not None else contextlib.nullcontext():
+        xs = ops.gather_rows(x.view(B, N, d), sel).view(B * Ksel, d)        # raw keys (App. B-1)
+        row_map = ops.build_row_map(sel, N)
 
     # The key projection of the Ksel selected rows does not depend on the Q|V projection over all N rows: issued on a second
     # stream (forked here, joined before the attention kernel, inside a captured graph too) it runs in the SMs the big product
     # leaves idle instead of after it.
-    small_tc = precision != "fp32"
-    kp, kside = None, None
-    if small_tc and FWD_SIDE_STREAM and x.is_cuda:
-        kside, cur = _side_stream(x.device), torch.cuda.current_stream(x.device)
-        kside.wait_stream(cur)
+    kp = None
+    if kside is not None:
         with torch.cuda.stream(kside):
             _, xsp, _ = ops.ln_rows(xs, None, None, apply_ln=False, want_planes=True)
             kp, _, _ = ops.gemm_tc(xsp, w.wk_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bk)
@@ -387,7 +413,9 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
     # [B*Ksel, d] key / output projections: a handful of tcgen05 tiles beat the SIMT kernel even for one bag (200 rows:
     # 8 SIMT CTAs looping over K take ~90 us, four tcgen05 CTAs ~10 us)
     if kside is not None:
-        torch.cuda.current_stream(x.device).wait_stream(kside)
+        global _SEL_PENDING
+        torch.cuda.current_stream(x.device).wait_stream(kside)     # selection, gathered keys, row map, key projection
+        _SEL_PENDING = None
     elif small_tc:
         _, xsp, _ = ops.ln_rows(xs, None, None, apply_ln=False, want_planes=True)
         kp, _, _ = ops.gemm_tc(xsp, w.wk_planes, M=B * Ksel, N=d, K=d, passes=passes, bias=w.bk)

@@ -57,10 +57,19 @@ def forward_bags(milnet: MILNet, x: torch.Tensor):
     state = {}
     attn = None
     h = feats
+    from .autograd import encoder_layer_fn
     for layer in enc.layers:
-        sel = layer.forced_selection if layer.forced_selection is not None else layer.select(classes, state)
-        from .autograd import encoder_layer_fn
-        h, attn = encoder_layer_fn(layer, h, sel.to(device=h.device, dtype=torch.int64).contiguous(), zplanes=zplanes)
+        # the selection is drawn on the second stream, beside LayerNorm 1 and the Q|V projection (engine.selection_stream)
+        side, on_side = engine.selection_stream("fp32" if layer.forced_selection is not None else layer._effective_precision(),
+                                                h.device)
+        with on_side:
+            sel = layer.forced_selection if layer.forced_selection is not None else layer.select(classes, state)
+            sel = sel.to(device=h.device, dtype=torch.int64).contiguous()
+        engine._SEL_PENDING = side
+        try:
+            h, attn = encoder_layer_fn(layer, h, sel, zplanes=zplanes)
+        finally:
+            engine.join_pending_selection(h.device)
         zplanes = None
     from .autograd import ln_mean_head_fn
     b = milnet.b_classifier
