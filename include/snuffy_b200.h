@@ -128,6 +128,7 @@ typedef struct {
     int64_t dst_row0, dst_k0, k_total;
     void* dst; int64_t plane_stride;
 } snuffy_plane_job_t;
+int snuffy_plane_job_bytes(void);          /* sizeof(snuffy_plane_job_t) as the library was built: bindings check their struct */
 int snuffy_weight_planes_batch(const snuffy_plane_job_t* jobs, int64_t n_jobs, snuffy_stream_t stream);
 /* dW[M, N] = dY^T X straight from the ROW planes of dY [R, M] and X [R, N] (128 rows per chunk, as the GEMM epilogues and
  * snuffy_ln_rows_fwd write them) through MN-major tcgen05 descriptors: no transposed copy of either operand (autograd of

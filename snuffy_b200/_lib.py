@@ -55,6 +55,7 @@ _SIGNATURES = {
     "snuffy_gemm_tc_awindow": (c_int, [P, I, I, I, P, I, I, I, I, c_int, P, I, P]),
     "snuffy_gemm_tc_splitk_rows": (c_int, [P, I, P, I, I, I, I, c_int, I, P, P, I, P]),
     "snuffy_planes_zero_rows": (c_int, [P, I, I, c_int, I, I, P]),
+    "snuffy_plane_job_bytes": (c_int, []),
     "snuffy_weight_planes_batch": (c_int, [ctypes.POINTER(PlaneJob), I, P]),
     "snuffy_planes_t_fwd": (c_int, [P, I, I, I, c_int, c_int, P, P, P, P, P, c_int, c_float, c_uint64, c_uint64, P, I, P]),
     "snuffy_sparse_attn_workspace": (c_int64, [I, I, I, I, I]),
@@ -131,6 +132,8 @@ def _load() -> ctypes.CDLL:
 
 
 lib = _load()
+if lib.snuffy_plane_job_bytes() != ctypes.sizeof(PlaneJob):
+    raise ImportError("snuffy_b200: PlaneJob does not match snuffy_plane_job_t of the loaded library (rebuild with ./build.sh)")
 
 
 def last_error() -> str:

@@ -455,8 +455,17 @@ attn_tc_kernel(const AttnTcParams p) {
                         uint32_t bits = 0;
                         if (small_index) {                           // element indices below 2^32: hoisted form of the same draw
                             const uint32_t e0 = (uint32_t)srow * (uint32_t)p.Ksel + (uint32_t)(key0 + kb);
+                            if ((e0 & 1u) == 0u) {               // the usual case (even Ksel): one hash per pair of scores
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) bits |= (drop_fast_keep(dfast, e0 + e) ? 1u : 0u) << e;
+                                for (int e = 0; e < 8; e += 2) {
+                                    const uint32_t x = drop_fast_hash(dfast, (e0 + e) >> 1);
+                                    bits |= ((x & 0xFFFFu) >= dfast.thr ? 1u : 0u) << e;
+                                    bits |= ((x >> 16) >= dfast.thr ? 1u : 0u) << (e + 1);
+                                }
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) bits |= (drop_fast_keep(dfast, e0 + e) ? 1u : 0u) << e;
+                            }
                         } else {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {

@@ -89,31 +89,43 @@ __device__ __forceinline__ DrawKey rng_resolve(uint64_t seed, uint64_t offset) {
     }
     return DrawKey{seed, offset};
 }
-__device__ __forceinline__ float drop_keep_scale(uint64_t seed, uint64_t offset, uint64_t idx, float p) {
-    uint32_t x = (uint32_t)idx ^ (uint32_t)seed, y = (uint32_t)(idx >> 32) ^ (uint32_t)(seed >> 32) ^ (uint32_t)offset;
+// Dropout draw of element `idx` of a launch keyed by (seed, offset): ONE 32-bit hash per PAIR of consecutive elements, its low
+// half deciding the even element and its high half the odd one: keep iff half >= ceil(p * 2^16) (the realised drop
+// probability is within 1.6e-5 of p; kept values are scaled by 1 / (1 - p) like torch's dropout).  Producers that walk
+// consecutive elements (GEMM epilogues, the attention softmax) hash once per pair; everything else calls per element.
+__device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)ceilf(p * 65536.0f); }
+__device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint64_t offset, uint64_t pair) {
+    uint32_t x = (uint32_t)pair ^ (uint32_t)seed, y = (uint32_t)(pair >> 32) ^ (uint32_t)(seed >> 32) ^ (uint32_t)offset;
     x *= 0x85EBCA6Bu; x ^= x >> 13; x += y * 0x9E3779B9u + (uint32_t)(offset >> 32);
     x *= 0xC2B2AE35u; x ^= x >> 16; x *= 0x27D4EB2Fu; x ^= x >> 15; x *= 0x165667B1u; x ^= x >> 16;
-    // keep iff u = (x >> 8) * 2^-24 >= p.  u is exact in fp32 and so is p * 2^24, so this is the integer test below: no
-    // int -> float conversion (a quarter-rate pipe) per element
-    return (x >> 8) >= (uint32_t)ceilf(p * 16777216.0f) ? 1.f / (1.f - p) : 0.f;
+    return x;
+}
+__device__ __forceinline__ float drop_keep_scale(uint64_t seed, uint64_t offset, uint64_t idx, float p) {
+    const uint32_t x = drop_hash(seed, offset, idx >> 1);
+    const uint32_t half = (idx & 1) ? (x >> 16) : (x & 0xFFFFu);
+    return half >= drop_threshold(p) ? 1.f / (1.f - p) : 0.f;
 }
 
 // The same draw for element indices below 2^32 with everything that does not depend on the index hoisted (bit-identical to
-// drop_keep_scale: the high word of the index is 0 there).
+// drop_keep_scale: the high word of the pair index is 0 there).
 struct DropFast { uint32_t s0, k, thr; float scale; };
 __device__ __forceinline__ DropFast drop_fast_setup(uint64_t seed, uint64_t offset, float p) {
     DropFast c;
     c.s0 = (uint32_t)seed;
     c.k = ((uint32_t)(seed >> 32) ^ (uint32_t)offset) * 0x9E3779B9u + (uint32_t)(offset >> 32);
-    c.thr = (uint32_t)ceilf(p * 16777216.0f);
+    c.thr = drop_threshold(p);
     c.scale = 1.f / (1.f - p);
     return c;
 }
-__device__ __forceinline__ bool drop_fast_keep(const DropFast& c, uint32_t idx) {
-    uint32_t x = idx ^ c.s0;
+__device__ __forceinline__ uint32_t drop_fast_hash(const DropFast& c, uint32_t pair) {
+    uint32_t x = pair ^ c.s0;
     x *= 0x85EBCA6Bu; x ^= x >> 13; x += c.k;
     x *= 0xC2B2AE35u; x ^= x >> 16; x *= 0x27D4EB2Fu; x ^= x >> 15; x *= 0x165667B1u; x ^= x >> 16;
-    return (x >> 8) >= c.thr;
+    return x;
+}
+__device__ __forceinline__ bool drop_fast_keep(const DropFast& c, uint32_t idx) {
+    const uint32_t x = drop_fast_hash(c, idx >> 1);
+    return ((idx & 1u) ? (x >> 16) : (x & 0xFFFFu)) >= c.thr;
 }
 
 // ---------------------------------------------------------------- folding many small partials

@@ -494,9 +494,13 @@ gemm_tc_kernel(const TcGemmParams p, const __grid_constant__ CUtensorMap tm_a, c
                     const DrawKey dk_ = rng_resolve(p.seed, p.offset);
                     if ((int64_t)p.M * p.N < (1ll << 32)) {          // 32-bit element index: the hoisted form of the same draw
                         const DropFast df = drop_fast_setup(dk_.seed, dk_.offset, p.drop_p);
-                        const uint32_t e0 = (uint32_t)(m_own * p.N + col0);
+                        const uint32_t e0 = (uint32_t)(m_own * p.N + col0);            // even: N % 4 == 0, col0 % 32 == 0
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = drop_fast_keep(df, e0 + j) ? v[j] * df.scale : 0.f;
+                        for (int j = 0; j < 32; j += 2) {                              // one hash per pair of elements
+                            const uint32_t x = drop_fast_hash(df, (e0 + j) >> 1);
+                            v[j] = (x & 0xFFFFu) >= df.thr ? v[j] * df.scale : 0.f;
+                            v[j + 1] = (x >> 16) >= df.thr ? v[j + 1] * df.scale : 0.f;
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)

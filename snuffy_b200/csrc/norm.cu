@@ -731,6 +731,7 @@ extern "C" int snuffy_planes_t_fwd(const float* x, int64_t ldx, int64_t R, int64
     planes_t_kernel<<<grid, 256, 0, stream>>>(p);
     return check_launch("snuffy_planes_t_fwd");
 }
+extern "C" int snuffy_plane_job_bytes(void) { return (int)sizeof(snuffy_plane_job_t); }
 extern "C" int snuffy_weight_planes_batch(const snuffy_plane_job_t* jobs, int64_t n_jobs, cudaStream_t stream) {
     using namespace snuffy;
     SNUFFY_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= SNUFFY_MAX_PLANE_JOBS, "snuffy_weight_planes_batch: 1..16 jobs per launch");

@@ -55,6 +55,13 @@ def test_argument_validation_without_a_gpu():
     assert lib.snuffy_sparse_attn_workspace(1, 100, 10, 3, 64) == -1        # d % h != 0
     assert lib.snuffy_gemm_tc_block_n(2048) == 256 and lib.snuffy_gemm_tc_block_n(384) == 128
     assert lib.snuffy_plane_elems(10000, 512, 128) == 79 * 16 * 128 * 32
+    # structs and handle sizes the bindings mirror
+    from snuffy_b200 import _lib
+    assert lib.snuffy_plane_job_bytes() == ctypes.sizeof(_lib.PlaneJob) == 80
+    assert lib.snuffy_comm_handle_bytes() == 64 and lib.snuffy_comm_counter_bytes() >= 512
+    assert lib.snuffy_weight_planes_batch(None, 0, None) != 0 and "jobs" in last_error()
+    assert lib.snuffy_peer_allreduce(None, None, None, 0, 2, 16, None) != 0
+    assert lib.snuffy_gemm_tc_splitk_rows(None, 0, None, 0, 128, 128, 16, 3, 0, None, None, 0, None) != 0
 
 
 SNUFFY_CLASSES = ["FCLayer", "IClassifier", "BClassifier", "Encoder", "SublayerConnection", "EncoderLayer",
