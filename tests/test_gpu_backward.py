@@ -377,6 +377,49 @@ def test_tensor_core_backward_matches_fp32_backward_at_scale():
         assert _rel(grads["bf16x3"][k], ref) < 5e-3, (k, _rel(grads["bf16x3"][k], ref))
 
 
+@pytest.mark.parametrize("r", [0.0, 0.5])
+def test_second_stream_and_row_plane_gradients_change_nothing(r):
+    """The off-chain work on the second stream (selection, key path, weight / bias gradients), the row-plane weight gradients and
+    the ReLU gate from planes against the single-stream, transposed-copy, saved-pre-activation forms: same draws, same loss,
+    gradients equal up to the summation order of the weight-gradient products, over several repetitions (a missing stream
+    dependency would show as run-to-run differences)."""
+    from snuffy_b200 import backward, engine, snuffy
+    c = dict(n=3000, d=512, heads=8, K=200, r=r, depth=2, act="relu", wseed=0, xseed=7)
+    params, x = snuffy_inputs(c)
+    xs = torch.from_numpy(x).cuda()
+    flags = [(engine, "FWD_SIDE_STREAM"), (backward, "DW_SIDE_STREAM"), (engine, "DW_BY_ROWS")]
+    saved = [getattr(m, k) for m, k in flags]
+    runs = {}
+    try:
+        for mode in (True, False, True, True):
+            for m, k in flags:
+                setattr(m, k, mode)
+            model = load_params(build_snuffy(snuffy, c, ff_dropout=0.1, enc_dropout=0.1), params)
+            model.train()
+            set_precision(model, "bf16x3")
+            torch.manual_seed(5)
+            engine._RANDOM._seed = None              # same (seed, offset) counters -> same masks and random patches
+            classes, bag, _ = model(xs)
+            loss = mil_loss(classes, bag, torch.ones(1, 1).cuda())
+            loss.backward()
+            torch.cuda.synchronize()
+            g = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+            runs.setdefault(mode, []).append((float(loss), g))
+    finally:
+        for (m, k), v in zip(flags, saved):
+            setattr(m, k, v)
+    on, off = runs[True], runs[False][0]
+    for loss, g in on[1:]:                           # the two-stream form is deterministic from run to run
+        assert loss == on[0][0]
+        for k in g:
+            assert torch.equal(g[k], on[0][1][k]), k
+    assert abs(on[0][0] - off[0]) < 1e-6
+    for k, ref in off[1].items():
+        if ref.abs().max() < 1e-9:
+            continue
+        assert _rel(on[0][1][k].double(), ref.double()) < 2e-5, (k, _rel(on[0][1][k].double(), ref.double()))
+
+
 @pytest.mark.parametrize("B,n,ks,h,d,p", [(1, 300, 40, 2, 64, 0.0), (1, 1000, 200, 8, 512, 0.0), (2, 256, 24, 4, 128, 0.0),
                                           (1, 777, 100, 8, 768, 0.2), (3, 200, 40, 4, 128, 0.1), (1, 500, 256, 4, 256, 0.1),
                                           (2, 384, 8, 4, 64, 0.3)])
