@@ -590,6 +590,7 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------ main
 def main():
+    os.environ.setdefault("SNUFFY_B200_PEER_TIMEOUT_S", "60")           # bench runs: a lost rank fails fast (library default 600 s)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

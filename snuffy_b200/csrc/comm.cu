@@ -13,6 +13,7 @@
 // = a two-shot all-reduce: each GPU moves 2 (W - 1) / W of the buffer over NVLink, half in each direction, against NCCL's
 // ~0.14 ms latency-bound ring/tree for the 12.6 MB flat gradient of cfg2 at 8 ranks.  The barriers are per CTA: CTA c of every
 // rank only exchanges data with the CTAs c of its peers (sub-chunk c of each slice), so no grid-wide synchronisation is needed.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace snuffy {
@@ -27,6 +28,7 @@ struct PeerComm {
     unsigned int* state;                         // own: [0] calls completed, [1] CTAs done in this call
     int rank, world;
     int64_t n4;                                  // float4 elements
+    unsigned long long timeout_ns;               // a peer that has not arrived by then: trap (fail loudly instead of hanging)
 };
 
 __device__ __forceinline__ unsigned long long comm_now_ns() {
@@ -50,7 +52,7 @@ __device__ __forceinline__ void comm_barrier(const PeerComm& c, int phase, unsig
         for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
             if ((int)(seen - target) >= 0) break;
-            if (comm_now_ns() - t0 > 20000000000ull) asm volatile("trap;");      // a peer never arrived: fail, do not hang
+            if (comm_now_ns() - t0 > c.timeout_ns) asm volatile("trap;");        // a peer never arrived: fail, do not hang
         }
     }
     __syncthreads();
@@ -164,6 +166,14 @@ int snuffy_peer_allreduce(void* const* bufs, void* const* counters, void* state,
     }
     c.state = reinterpret_cast<unsigned int*>(state);
     c.rank = rank; c.world = world; c.n4 = n / 4;
+    // ranks reach the exchange at different times (data loading, a graph capture on one of them): wait long, like NCCL's
+    // watchdog, before declaring the peer lost.  SNUFFY_B200_PEER_TIMEOUT_S overrides (tests use a short one).
+    static const unsigned long long timeout_s = [] {
+        const char* e = getenv("SNUFFY_B200_PEER_TIMEOUT_S");
+        const long long v = e ? atoll(e) : 0;
+        return (unsigned long long)(v > 0 ? v : 600);
+    }();
+    c.timeout_ns = timeout_s * 1000000000ull;
     peer_allreduce_kernel<<<COMM_CTAS, COMM_THREADS, 0, stream>>>(c);
     return check_launch("snuffy_peer_allreduce");
 }

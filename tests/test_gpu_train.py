@@ -192,6 +192,7 @@ def test_idle_step_and_uneven_shards_world1():
 
 def _dp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.setdefault("SNUFFY_B200_PEER_TIMEOUT_S", "30")              # a lost peer fails the test instead of hanging the box
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
