@@ -47,6 +47,13 @@ int snuffy_select_topk(const float* scores, int64_t B, int64_t N, int64_t C, int
  * that every bag has at least K un-flagged rows (the reference's Krand = min(int(K r), N - Ktop) does).          */
 int snuffy_select_random(const uint8_t* flags, int64_t B, int64_t N, int64_t K, uint64_t seed,
                          uint64_t offset, int64_t* idx_out, snuffy_stream_t stream);
+/* The whole binary-path selection in one launch (snuffy.py:128-147 selection, 131 / 145-147 gathers, 152-155 row
+ * replacement): per bag the k_top highest-scoring rows (descending, ties to the lower index), k_rand distinct rows drawn
+ * from the rest (the Philox stream of snuffy_select_random: identical indices), sel[B, k_top + k_rand] = T ++ R,
+ * flags[B, N] and row_map[B * N] (row -> slot or -1) written from scratch, xs[B, k_top + k_rand, d] = x[b, sel[b, k], :]. */
+int snuffy_select_gather(const float* scores, const float* x, int64_t B, int64_t N, int64_t d, int64_t k_top,
+                         int64_t k_rand, uint64_t seed, uint64_t offset, int64_t* sel, uint8_t* flags,
+                         int32_t* row_map, float* xs, snuffy_stream_t stream);
 /* ascending distinct flagged rows per bag = torch.unique of the flattened per-class top-K
  * (snuffy_multiclass.py:139-141).  out [B,cap] int64, counts [B] int32.                                */
 int snuffy_compact_flags(const uint8_t* flags, int64_t B, int64_t N, int64_t cap, int64_t* out,

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "snuffy_scores_fwd": (c_int, [P, P, P, P, I, I, I, P]),
     "snuffy_select_topk": (c_int, [P, I, I, I, I, P, P, P]),
     "snuffy_select_random": (c_int, [P, I, I, I, c_uint64, c_uint64, P, P]),
+    "snuffy_select_gather": (c_int, [P, P, I, I, I, I, I, c_uint64, c_uint64, P, P, P, P, P]),
     "snuffy_compact_flags": (c_int, [P, I, I, I, P, P, P]),
     "snuffy_gather_rows": (c_int, [P, P, I, I, I, I, P, P]),
     "snuffy_build_row_map": (c_int, [P, I, I, I, P, P]),

@@ -99,13 +99,13 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t seed, uint64_t offset, 
 }
 
 // MODE 0: key = score of (bag, class).  MODE 1: key = Philox word, 0 for flagged (taken) rows.
+// One CTA selects the K best keys of one (bag, class) column: shared by the stand-alone kernel and the fused selection kernel.
 template <int MODE>
-__global__ void __launch_bounds__(SEL_THREADS, 1)
-select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, int cache_keys,
-              uint8_t* __restrict__ flags, uint64_t seed, uint64_t offset, int64_t* __restrict__ out,
-              const int64_t* __restrict__ cu_seqlens) {
+__device__ __forceinline__ void select_cta(const float* __restrict__ scores, int N, int C, int K, int Kpad, int cache_keys,
+                                           uint8_t* __restrict__ flags, uint64_t seed, uint64_t offset,
+                                           int64_t* __restrict__ o, const int64_t* __restrict__ cu_seqlens, int col, int bag,
+                                           unsigned char* sel_smem) {
     if (MODE == 1) { const DrawKey key_ = rng_resolve(seed, offset); seed = key_.seed; offset = key_.offset; }
-    extern __shared__ __align__(16) unsigned char sel_smem[];
     uint64_t* sortbuf = reinterpret_cast<uint64_t*>(sel_smem);
     uint32_t* keys = reinterpret_cast<uint32_t*>(sel_smem + (size_t)Kpad * 8);
     __shared__ uint32_t hist[256];
@@ -113,7 +113,6 @@ select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, i
     __shared__ int s_need, s_bucket, s_count;
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int col = blockIdx.x, bag = blockIdx.y;
     // packed variable-length bags: rows [cu[bag], cu[bag+1]) of one [T, C] score matrix; the indices written are GLOBAL
     // rows of the packed tensor, so every row-wise kernel downstream runs on it as one "bag" of T rows
     int64_t base = (int64_t)bag * N;
@@ -228,11 +227,55 @@ select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, i
             __syncthreads();
         }
     }
-    int64_t* o = out + ((int64_t)bag * gridDim.x + col) * K;
     for (int r = tid; r < K; r += SEL_THREADS) {
         const uint32_t idx = ~(uint32_t)sortbuf[r];
         o[r] = (int64_t)idx + idx_add;
         if (MODE == 0 && fl) fl[idx] = 1;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+select_kernel(const float* __restrict__ scores, int N, int C, int K, int Kpad, int cache_keys,
+              uint8_t* __restrict__ flags, uint64_t seed, uint64_t offset, int64_t* __restrict__ out,
+              const int64_t* __restrict__ cu_seqlens) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    select_cta<MODE>(scores, N, C, K, Kpad, cache_keys, flags, seed, offset,
+                     out + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * K, cu_seqlens, (int)blockIdx.x, (int)blockIdx.y, sel_smem);
+}
+
+// The selection of the binary path in ONE launch per bag batch (snuffy.py:128-147 + 131, 145-147, 152-155): one CTA per bag
+// clears the bag's taken-flags and row map, selects the Ktop highest-scoring rows, draws Krand of the remaining rows (same
+// Philox stream as the stand-alone kernel: identical indices), writes S = T ++ R, the row map (row -> slot) and gathers the
+// selected rows of x into xs [B, Ksel, d].
+__global__ void __launch_bounds__(SEL_THREADS, 1)
+select_gather_kernel(const float* __restrict__ scores, const float* __restrict__ x, int N, int d, int Ktop, int Krand,
+                     int Kpad_top, int Kpad_rand, int cache_keys, uint8_t* __restrict__ flags, uint64_t seed, uint64_t offset,
+                     int64_t* __restrict__ sel, int32_t* __restrict__ row_map, float* __restrict__ xs, int vec_ok) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    const int bag = blockIdx.x, tid = threadIdx.x, Ksel = Ktop + Krand;
+    uint8_t* fl = flags + (int64_t)bag * N;
+    int32_t* rm = row_map + (int64_t)bag * N;
+    for (int i = tid; i < N; i += SEL_THREADS) { fl[i] = 0; rm[i] = -1; }
+    __syncthreads();
+    int64_t* s_out = sel + (int64_t)bag * Ksel;
+    select_cta<0>(scores, N, 1, Ktop, Kpad_top, cache_keys, flags, 0, 0, s_out, nullptr, 0, bag, sel_smem);
+    __syncthreads();
+    if (Krand > 0) {
+        select_cta<1>(nullptr, N, 1, Krand, Kpad_rand, cache_keys, flags, seed, offset, s_out + Ktop, nullptr, 0, bag, sel_smem);
+        __syncthreads();
+    }
+    for (int r = tid; r < Ksel; r += SEL_THREADS) rm[s_out[r]] = (int32_t)(bag * Ksel + r);
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < Ksel; r += SEL_THREADS / 32) {
+        const float* src = x + ((int64_t)bag * N + s_out[r]) * d;
+        float* dst = xs + ((int64_t)bag * Ksel + r) * d;
+        if (vec_ok) {
+            for (int e = lane * 4; e < d; e += 128)
+                *reinterpret_cast<float4*>(dst + e) = __ldg(reinterpret_cast<const float4*>(src + e));
+        } else {
+            for (int e = lane; e < d; e += 32) dst[e] = src[e];
+        }
     }
 }
 
@@ -357,6 +400,25 @@ int snuffy_select_random(const uint8_t* flags, int64_t B, int64_t N, int64_t K, 
                          int64_t* idx_out, cudaStream_t stream) {
     SNUFFY_REQUIRE(flags && idx_out, "snuffy_select_random: null pointer");
     return launch_select(1, nullptr, B, N, 1, K, const_cast<uint8_t*>(flags), seed, offset, idx_out, stream);
+}
+
+// Fused selection of the binary path: sel[B, Ktop + Krand] int64 (top-k in descending score order, then the random rows),
+// flags[B, N] uint8 and row_map[B * N] int32 (both written from scratch), xs[B, Ktop + Krand, d] = the selected rows of x.
+int snuffy_select_gather(const float* scores, const float* x, int64_t B, int64_t N, int64_t d, int64_t k_top, int64_t k_rand,
+                         uint64_t seed, uint64_t offset, int64_t* sel, uint8_t* flags, int32_t* row_map, float* xs,
+                         cudaStream_t stream) {
+    SNUFFY_REQUIRE(scores && x && sel && flags && row_map && xs, "snuffy_select_gather: null pointer");
+    SNUFFY_REQUIRE(B >= 1 && N >= 1 && d >= 1 && N < (1ll << 31) && B <= 65535, "snuffy_select_gather: bad shape");
+    SNUFFY_REQUIRE(k_top >= 1 && k_rand >= 0 && k_top + k_rand <= N && k_top <= SEL_MAX_K && k_rand <= SEL_MAX_K &&
+                       B * (k_top + k_rand) < (1ll << 31), "snuffy_select_gather: bad selection sizes");
+    const int kp_top = next_pow2((int)k_top), kp_rand = k_rand > 0 ? next_pow2((int)k_rand) : 2;
+    const int cache = N <= SEL_KEY_CACHE ? 1 : 0;
+    const size_t smem = (size_t)(kp_top > kp_rand ? kp_top : kp_rand) * 8 + (cache ? (size_t)N * 4 : 0);
+    SNUFFY_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(&select_gather_kernel), 220 * 1024));
+    select_gather_kernel<<<(unsigned)B, SEL_THREADS, smem, stream>>>(scores, x, (int)N, (int)d, (int)k_top, (int)k_rand, kp_top,
+                                                                   kp_rand, cache, flags, seed, offset, sel, row_map, xs,
+                                                                   vec_ok4(x, d) && vec_ok4(xs, d));
+    return check_launch("snuffy_select_gather");
 }
 
 // Packed variable-length forms (BASELINE configs[3]): bag b owns rows [cu_seqlens[b], cu_seqlens[b+1]) of the packed

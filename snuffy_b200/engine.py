@@ -296,6 +296,11 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
 
 #: the stream a caller drew the selection on and has not joined yet (set by EncoderLayer.forward around its call)
 _SEL_PENDING = None
+#: the binary path's selection as one launch (top-k + random-k + row map + key gather); "0" = four launches
+FUSED_SELECT = os.environ.get("SNUFFY_B200_FUSED_SELECT", "1") != "0"
+FUSED_SELECT_MAX_K = 4096
+#: (sel, xs, row_map) of a fused selection, picked up by the encoder-layer call that follows it
+_GATHERED = None
 
 
 def selection_stream(precision: str, device: torch.device):
@@ -376,9 +381,14 @@ def encoder_layer_forward(x: torch.Tensor, B: int, N: int, sel: torch.Tensor, w:
         join_pending_selection(x.device)                   # the selection was drawn on the second stream: wait for it here
     else:
         kside.wait_stream(torch.cuda.current_stream(x.device))
+    global _GATHERED
+    fused, _GATHERED = _GATHERED, None
     with torch.cuda.stream(kside) if kside is not None else contextlib.nullcontext():
-        xs = ops.gather_rows(x.view(B, N, d), sel).view(B * Ksel, d)        # raw keys (App. B-1)
-        row_map = ops.build_row_map(sel, N)
+        if fused is not None and varlen is None and fused[0].data_ptr() == sel.data_ptr() and fused[1].shape == (B * Ksel, d):
+            xs, row_map = fused[1], fused[2]                                # written by the selection launch itself
+        else:
+            xs = ops.gather_rows(x.view(B, N, d), sel).view(B * Ksel, d)    # raw keys (App. B-1)
+            row_map = ops.build_row_map(sel, N)
 
     # The key projection of the Ksel selected rows does not depend on the Q|V projection over all N rows: issued on a second
     # stream (forked here, joined before the attention kernel, inside a captured graph too) it runs in the SMs the big product

@@ -616,6 +616,23 @@ def gemm_tc_splitk(a: Planes, b: Planes, *, M: int, N: int, K: int, passes: int 
     return out
 
 
+def select_gather(c: torch.Tensor, x: torch.Tensor, k_top: int, k_rand: int, seed: int = 0, offset: int = 0):
+    """Binary-path selection in one launch: c [B, N, 1] scores, x [B, N, d] ->
+    (sel [B, k_top + k_rand] int64, flags [B, N] uint8, row_map [B * N] int32, xs [B * Ksel, d])."""
+    c = _f32(c, "c")
+    x = _f32(x, "x")
+    B, N, d = x.shape
+    ksel = k_top + k_rand
+    dev = x.device
+    sel = torch.empty(B, ksel, dtype=torch.int64, device=dev)
+    flags = torch.empty(B, N, dtype=torch.uint8, device=dev)
+    row_map = torch.empty(B * N, dtype=torch.int32, device=dev)
+    xs = torch.empty(B * ksel, d, dtype=torch.float32, device=dev)
+    check(lib.snuffy_select_gather(c.data_ptr(), x.data_ptr(), B, N, d, k_top, k_rand, seed & _U64, offset & _U64, sel.data_ptr(),
+                                   flags.data_ptr(), row_map.data_ptr(), xs.data_ptr(), _stream()), "snuffy_select_gather")
+    return sel, flags, row_map, xs
+
+
 # ------------------------------------------------------------------ packed variable-length bags (inference)
 def select_topk_varlen(c: torch.Tensor, cu: torch.Tensor, B: int, max_n: int, k: int, flags: Optional[torch.Tensor] = None):
     """c [T, C] packed scores -> idx [B, C, k] int64 GLOBAL rows (per bag and class, descending score)."""

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from . import engine
+from . import engine, ops
 from ._modules import (BClassifier, Encoder, EncoderLayerBase, FCLayer, IClassifier, MILNet,  # noqa: F401
                        MultiHeadedAttention, PositionwiseFeedForward, SublayerConnection, attention, clones)
 
@@ -30,7 +30,30 @@ class EncoderLayer(EncoderLayerBase):
             # the reference breaks at .squeeze()/index_select for B > 1 or C > 1 (snuffy.py:129-131)
             raise ValueError(f"binary snuffy.EncoderLayer needs x [1, N, d] and c [1, N, 1]; got x {tuple(x.shape)}, "
                              f"c {tuple(c.shape)} (use snuffy_multiclass or forward_bags for batches)")
-        return self.select(c, state)
+        sel = self.select_fused(c, state, x)
+        return sel if sel is not None else self.select(c, state)
+
+    def select_fused(self, c, state, x):
+        """The same selection as `select` in ONE launch (csrc/select.cu select_gather_kernel) when the layer input x [B, N, d]
+        is at hand and the random rows come from the device sampler: top-k, random-k, the row map and the gathered key rows,
+        which the encoder-layer call that follows picks up.  Returns S, or None when this form does not apply (the caller then
+        uses `select`): a `select` patched on the instance, a forced selection, the NumPy sampler."""
+        if not engine.FUSED_SELECT or "select" in self.__dict__ or self.forced_selection is not None:
+            return None
+        if not (c.dim() == 3 and c.shape[-1] == 1 and x.dim() == 3 and x.is_cuda and x.dtype == torch.float32
+                and x.is_contiguous() and c.shape[:2] == x.shape[:2]):
+            return None
+        n = c.shape[1]
+        kt = min(engine.k_top_of(self.big_lambda, self.random_patch_share), n)
+        kr = engine.k_rand_of(self.big_lambda, self.random_patch_share, n)
+        if not (1 <= kt <= engine.FUSED_SELECT_MAX_K and kr <= engine.FUSED_SELECT_MAX_K and (kr == 0 or self.random_mode == "device")):
+            return None
+        seed, offset = engine._RANDOM.next() if kr > 0 else (0, 0)
+        sel, flags, row_map, xs = ops.select_gather(c.detach(), x.detach(), kt, kr, seed, offset)
+        if state is not None:
+            state["top"], state["flags"] = sel[:, :kt], flags
+        engine._GATHERED = (sel, xs, row_map)
+        return sel
 
     def select(self, c, state=None):
         """S = T ++ R for c [B, N, 1] (batched extension of snuffy.py:128-147).  T is computed once per forward
@@ -63,7 +86,9 @@ def forward_bags(milnet: MILNet, x: torch.Tensor):
         side, on_side = engine.selection_stream("fp32" if layer.forced_selection is not None else layer._effective_precision(),
                                                 h.device)
         with on_side:
-            sel = layer.forced_selection if layer.forced_selection is not None else layer.select(classes, state)
+            sel = layer.select_fused(classes, state, h)
+            if sel is None:
+                sel = layer.forced_selection if layer.forced_selection is not None else layer.select(classes, state)
             sel = sel.to(device=h.device, dtype=torch.int64).contiguous()
         engine._SEL_PENDING = side
         try:

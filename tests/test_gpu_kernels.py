@@ -121,6 +121,27 @@ def test_gather_and_row_map(ops):
         assert np.array_equal(rm[b], exp)
 
 
+@pytest.mark.parametrize("B,n,d,kt,kr", [(1, 10000, 512, 200, 0), (3, 777, 96, 60, 60), (2, 50000, 64, 512, 512), (4, 256, 384, 32, 0),
+                                         (1, 300, 30, 1, 299)])
+def test_fused_selection_equals_the_four_launches(ops, B, n, d, kt, kr):
+    """select_gather_kernel (top-k + random-k + row map + key gather in one launch) writes exactly what select_topk,
+    select_random, build_row_map and gather_rows write, ties and the Philox stream included."""
+    rs = np.random.RandomState(n + kt)
+    c = torch.from_numpy(np.round(rs.standard_normal((B, n, 1)) * 8).astype(np.float32) / 8).cuda()     # many ties
+    x = torch.from_numpy(rs.standard_normal((B, n, d)).astype(np.float32)).cuda()
+    seed, offset = 1234, 77
+    junk = torch.full((B * n,), 7, dtype=torch.int32, device="cuda")       # the fused kernel clears its outputs itself
+    del junk
+    sel, flags, row_map, xs = ops.select_gather(c, x, kt, kr, seed, offset)
+    fl = torch.zeros(B, n, dtype=torch.uint8, device="cuda")
+    top = ops.select_topk(c, kt, fl).view(B, kt)
+    want = top if kr == 0 else torch.cat((top, ops.select_random(fl, kr, seed, offset)), dim=1).contiguous()
+    assert torch.equal(sel, want)
+    assert torch.equal(flags, fl)
+    assert torch.equal(row_map, ops.build_row_map(want, n))
+    assert torch.equal(xs, ops.gather_rows(x, want).view(B * (kt + kr), d))
+
+
 # ------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("rows,d", [(100, 32), (1000, 512), (257, 768), (64, 384), (50, 36), (30, 2048)])
 def test_ln_rows(ops, rows, d):
