@@ -82,8 +82,7 @@ struct TcGemmParams {
     int a_nkb, a_kb_off;
     // MN-major form (gemm_tc_kernel<BN, true>): both operands are ROW planes of activations ([rows, features], 128 rows per
     // chunk) contracted over their rows: A = planes of dY [K rows, M features], B = planes of X [K rows, N features], k-blocks
-    // of 32 rows; a_nkb / b_nkb = feature k-blocks per row tile of each plane set
-    int b_nkb;
+    // of 32 rows, fetched through the two tensor maps passed beside this struct
     // Tail split ("stream-K" for the last, partial wave): items [0, full_items) are whole tiles (times ksplit); the remaining
     // tail_tiles tiles, which would keep only tail_tiles of the SMs busy for a whole tile time, are cut into tail_s K slices of
     // tail_per k-blocks, one CTA each.  Slice 0 owns the tile's epilogue; the others hand their raw accumulators over through
@@ -1027,7 +1026,7 @@ int snuffy_gemm_tc_splitk_rows(const void* dY_planes, int64_t a_plane_stride, co
     p.act = ACT_NONE;
     p.out = ksplit > 1 ? reinterpret_cast<float*>(workspace) : out; p.ldc = N;
     p.ksplit = (int)ksplit; p.kb_per = (int)per; p.split_stride = M * N;
-    p.a_nkb = (int)plane_kblocks(M); p.b_nkb = (int)plane_kblocks(N);
+    p.a_nkb = (int)plane_kblocks(M);
     CUtensorMap tm_a, tm_b;
     if (int rc = row_planes_tensor_map(&tm_a, dY_planes, a_plane_stride, R, M, 16)) return rc;
     if (int rc = row_planes_tensor_map(&tm_b, X_planes, b_plane_stride, R, N, bn / 8)) return rc;
