@@ -255,6 +255,10 @@ int snuffy_ln_rows_bwd(const float* dy, const float* dy_bcast, int64_t rows_per_
                        const float* x, const int32_t* row_map, const float* alt, const float* stats,
                        const float* gamma, const float* add, int64_t rows, int64_t d, float* dx,
                        float* dgamma_dbeta, float* partials, snuffy_stream_t stream);
+/* dgamma_dbeta == NULL above leaves the per-CTA partial sums [snuffy_ln_rows_bwd_blocks(rows), 2 d] in `partials`; this folds
+ * them (or any [splits, n] partial rows, n % 4 == 0) in a fixed order.  The parameter gradients are off the critical chain of
+ * the backward pass, so the fold may be issued on another stream.                                                         */
+int snuffy_fold_partials(const float* partials, int64_t splits, int64_t n, float* out, snuffy_stream_t stream);
 /* dh = da * dropout_mask * act'(hpre), a_out = act(hpre) * dropout_mask   (snuffy.py:216-225 backward)      */
 int snuffy_act_bwd(const float* hpre, const float* da, int act, float dropout_p, uint64_t seed,
                    uint64_t offset, int64_t total, float* dh, float* a_out, snuffy_stream_t stream);

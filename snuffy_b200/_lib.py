@@ -74,6 +74,7 @@ _SIGNATURES = {
     "snuffy_gemm_f32_batched": (c_int, [P, I, c_int, P, I, c_int, P, I, I, I, I, c_float, P, I, I, I, I, I, I, I, I, I, P, I, P]),
     "snuffy_ln_rows_bwd_blocks": (c_int64, [I]),
     "snuffy_ln_rows_bwd": (c_int, [P, P, I, c_float, P, P, P, P, P, P, I, I, P, P, P, P]),
+    "snuffy_fold_partials": (c_int, [P, I, I, P, P]),
     "snuffy_act_bwd": (c_int, [P, P, c_int, c_float, c_uint64, c_uint64, I, P, P, P]),
     "snuffy_residual_dropout": (c_int, [P, P, c_float, c_uint64, c_uint64, I, P, P]),
     "snuffy_colsum_chunks": (c_int64, [I]),

@@ -215,7 +215,9 @@ class EncoderLayerFunction(torch.autograd.Function):
         else:
             du2 = dx_gemm(dh, w.w1, w.w1t_planes, d)                               # [rows, d]
         del dh, dh_planes
-        dy, d_g2, d_be2 = ops.ln_rows_bwd(t.x_in, t.ln2_stats, w.g2, dy=du2, row_map=t.row_map, alt=t.xs_new, add=g)
+        # the dgamma / dbeta partial sums are folded off the chain
+        dy, fold2 = ops.ln_rows_bwd(t.x_in, t.ln2_stats, w.g2, dy=du2, row_map=t.row_map, alt=t.xs_new, add=g, defer_fold=True)
+        d_g2, d_be2 = off_chain(fold2, fold2.partials)
         del du2
 
         # ---- attention sub-layer: the selected rows of y are xs_new = xs + D1(Wo O + bo)
@@ -262,7 +264,8 @@ class EncoderLayerFunction(torch.autograd.Function):
             d_wq, d_wv = ops.matmul_tn(dq, u1), ops.matmul_tn(dv, u1)
             del u1
             du1 = ops.matmul_nn(dv, w.wv, resid=ops.matmul_nn(dq, w.wq))           # [rows, d]
-        dx, d_g1, d_be1 = ops.ln_rows_bwd(t.x_in, t.ln1_stats, w.g1, dy=du1, add=dy, want_dx=need[1])
+        dx, fold1 = ops.ln_rows_bwd(t.x_in, t.ln1_stats, w.g1, dy=du1, add=dy, want_dx=need[1], defer_fold=True)
+        d_g1, d_be1 = off_chain(fold1, fold1.partials)
         if dx is not None:
             # raw selected rows also feed the key projection: dx[S] += dKp Wk  (the xs residual is already in `add`)
             ops.scatter_add_rows(dx.view(B, N, d), t.sel, dx_gemm(dkp, w.wk, w.wkt_planes, d))

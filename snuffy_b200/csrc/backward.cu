@@ -263,7 +263,7 @@ int snuffy_ln_rows_bwd(const float* dy, const float* dy_bcast, int64_t rows_per_
                        const int32_t* row_map, const float* alt, const float* stats, const float* gamma,
                        const float* add, int64_t rows, int64_t d, float* dx, float* dgamma_dbeta, float* partials,
                        cudaStream_t stream) {
-    SNUFFY_REQUIRE((dy || dy_bcast) && x && stats && gamma && dgamma_dbeta && partials, "snuffy_ln_rows_bwd: null pointer");
+    SNUFFY_REQUIRE((dy || dy_bcast) && x && stats && gamma && partials, "snuffy_ln_rows_bwd: null pointer");
     SNUFFY_REQUIRE(!row_map || alt, "snuffy_ln_rows_bwd: row_map given without the replacement rows");
     SNUFFY_REQUIRE(d % 4 == 0 && d >= 4 && rows >= 1 && (dy || rows_per_bag >= 1), "snuffy_ln_rows_bwd: needs d %% 4 == 0 (d=%lld)",
                    (long long)d);
@@ -280,8 +280,19 @@ int snuffy_ln_rows_bwd(const float* dy, const float* dy_bcast, int64_t rows_per_
     const int64_t blocks = snuffy_ln_rows_bwd_blocks(rows);
     ln_rows_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(dy, dy_bcast, rows_per_bag, bscale, x, row_map, alt,
                                                                       stats, gamma, add, rows, (int)d, dx, partials);
+    if (!dgamma_dbeta) return check_launch("snuffy_ln_rows_bwd");     // the caller folds the partials (snuffy_fold_partials)
     launch_fold_partials(partials, (int)blocks, 2 * d / 4, dgamma_dbeta, stream);
     return check_launch("snuffy_ln_rows_bwd", 2);
+}
+
+// out[n] = sum over `splits` partial rows of part[splits, n] (n % 4 == 0), in a fixed order.  The deferred second half of
+// snuffy_ln_rows_bwd (dgamma_dbeta == NULL there): the parameter gradients are not on the backward pass's critical chain, so a
+// caller may issue this fold on another stream.
+int snuffy_fold_partials(const float* partials, int64_t splits, int64_t n, float* out, cudaStream_t stream) {
+    SNUFFY_REQUIRE(partials && out && splits >= 1 && n >= 4 && n % 4 == 0 && (uintptr_t)partials % 16 == 0 && (uintptr_t)out % 16 == 0,
+                   "snuffy_fold_partials: bad arguments");
+    launch_fold_partials(partials, (int)splits, n / 4, out, stream);
+    return check_launch("snuffy_fold_partials");
 }
 
 // dh = da * mask * act'(hpre) and/or a_out = act(hpre) * mask over `total` contiguous elements (total % 4 == 0).

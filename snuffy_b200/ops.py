@@ -410,8 +410,9 @@ def matmul_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def ln_rows_bwd(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, *, dy: Optional[torch.Tensor] = None,
                 dy_bcast: Optional[torch.Tensor] = None, rows_per_bag: int = 1, bscale: float = 1.0, row_map=None,
-                alt=None, add=None, want_dx: bool = True):
-    """LayerNorm backward.  Returns (dx [rows, d] or None, dgamma [d], dbeta [d])."""
+                alt=None, add=None, want_dx: bool = True, defer_fold: bool = False):
+    """LayerNorm backward.  Returns (dx [rows, d] or None, dgamma [d], dbeta [d]); with defer_fold (dx, fold) where fold()
+    -> (dgamma, dbeta) sums the per-CTA partials later, on whatever stream is current then."""
     x = _f32(x, "x")
     d = x.shape[-1]
     rows = x.numel() // d
@@ -427,8 +428,15 @@ def ln_rows_bwd(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, *, dy
     if add is not None:
         add = _f32(add, "add")
     check(lib.snuffy_ln_rows_bwd(_ptr(dy), _ptr(dy_bcast), rows_per_bag, float(bscale), x.data_ptr(), _ptr(row_map), _ptr(alt),
-                                 stats.data_ptr(), gamma.data_ptr(), _ptr(add), rows, d, _ptr(dx), gb.data_ptr(),
-                                 partials.data_ptr(), _stream()), "snuffy_ln_rows_bwd")
+                                 stats.data_ptr(), gamma.data_ptr(), _ptr(add), rows, d, _ptr(dx),
+                                 None if defer_fold else gb.data_ptr(), partials.data_ptr(), _stream()), "snuffy_ln_rows_bwd")
+    if defer_fold:
+        def fold():
+            out = torch.empty(2, d, dtype=torch.float32, device=dev)
+            check(lib.snuffy_fold_partials(partials.data_ptr(), blocks, 2 * d, out.data_ptr(), _stream()), "snuffy_fold_partials")
+            return out[0], out[1]
+        fold.partials = partials
+        return dx, fold
     return dx, gb[0], gb[1]
 
 
